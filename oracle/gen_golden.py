@@ -1,0 +1,262 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference in the build container.
+
+TEST INFRASTRUCTURE ONLY.  Run:  python -m oracle.gen_golden   (needs /root/reference; CPU, gloo).
+The vectors are small, seeded (numpy RandomState = frozen stream) and committed; tests regenerate the
+*inputs* from the same seeds and compare outputs, so nothing reads /root/reference at test time.
+
+What is executed from the reference, untouched:
+  loss.py             clip_loss, cache_loss, grad_cache_loss (whole functions)
+  distributed.py      gather_with_grad (torch.distributed.nn.all_gather over gloo)
+  modeling_dual_encoder.py:46-65   (loss block, exec'd from the file text with stand-in towers)
+  trainers/text_text.py:352-369    (Matryoshka loop, exec'd from the file text)
+  modeling_biencoder.py:79-90      (MeanPooling, exec'd from the file text)
+  models/huggingface/modeling_hf_nomic_bert.py  NomicBertModel (pure torch)
+"""
+from __future__ import annotations
+
+import os
+import sys
+import textwrap
+import types
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+from oracle import ref_loader  # noqa: E402
+from oracle.cases import (INFONCE_CASES, DUAL_CASES, MATRYOSHKA_CASES, ENCODER_CASES, GRADCACHE_CASE,  # noqa: E402
+                          make_infonce_inputs, make_encoder_inputs, make_gradcache_inputs, encoder_cfg,
+                          TinyTower)
+from oracle.encoder import random_state_dict  # noqa: E402
+
+
+class RefLogitScale(torch.nn.Module):
+    """Same arithmetic as the reference LogitScale (modeling_biencoder.py:30-41), which cannot be imported
+    here because its module pulls in flash-attn extensions; x * exp(p)."""
+
+    def __init__(self, scale, trainable=True):
+        super().__init__()
+        self.logit_scale = torch.nn.Parameter(torch.ones([]) * np.log(scale), requires_grad=trainable)
+
+    def forward(self, x):
+        return x * self.logit_scale.exp()
+
+
+def _ref_lines(relpath, lo, hi):
+    with open(os.path.join(ref_loader.REF_ROOT, relpath)) as f:
+        lines = f.readlines()
+    return textwrap.dedent("".join(lines[lo - 1:hi]))
+
+
+def _init_pg(rank, ws, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+
+
+def _infonce_worker(rank, ws, port, case, out_dir):
+    _init_pg(rank, ws, port)
+    ref = ref_loader.load()
+    qs, ds = make_infonce_inputs(case)
+    q = torch.tensor(qs[rank], requires_grad=True)
+    d = torch.tensor(ds[rank], requires_grad=True)
+    ls = RefLogitScale(case["scale"])
+
+    class Tracker:
+        def __init__(self):
+            self.logged = {}
+
+        def log(self, m, step=None):
+            self.logged.update(m)
+
+    tr = Tracker()
+    res = {}
+    try:
+        loss = ref.loss.clip_loss(q, d, ls, gather_enabled=ws > 1, tracker=tr, dataset="x",
+                                  bidirectional=case.get("bidirectional", False))
+        loss.backward()
+        res = dict(loss=np.float64(loss.item()), dq=q.grad.numpy(), dd=d.grad.numpy(),
+                   dlogit=np.float64(ls.logit_scale.grad.item()), accuracy=np.float64(tr.logged["accuracy/accuracy_x"]))
+    except ValueError as e:  # bidirectional with M != N (loss.py:119-123)
+        res = dict(error=np.array(str(e)))
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), **res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _dual_worker(rank, ws, port, case, out_dir):
+    _init_pg(rank, ws, port)
+    ref = ref_loader.load()
+    ts, vs = make_infonce_inputs(case)  # reuse generator: "queries" = text, "documents" = vision (un-normalised)
+    t = torch.tensor(ts[rank] * 3.0, requires_grad=True)
+    v = torch.tensor(vs[rank] * 0.5, requires_grad=True)
+    ls = RefLogitScale(case["scale"])
+    src = _ref_lines("models/dual_encoder/modeling_dual_encoder.py", 46, 66)
+    ns = dict(text_outputs={"embedding": t}, vision_outputs={"embedding": v}, F=F, torch=torch, dist=dist,
+              gather_with_grad=ref.distributed.gather_with_grad, self=types.SimpleNamespace(logit_scale=ls))
+    exec(src, ns)
+    loss = ns["metrics"]["loss"]
+    loss.backward()
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), loss=np.float64(loss.item()), dtext=t.grad.numpy(),
+             dvision=v.grad.numpy(), dlogit=np.float64(ls.logit_scale.grad.item()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _matryoshka_worker(rank, ws, port, case, out_dir):
+    _init_pg(rank, ws, port)
+    ref = ref_loader.load()
+    qs, ds = make_infonce_inputs(case)
+    q = torch.tensor(qs[rank] * 2.0, requires_grad=True)
+    d = torch.tensor(ds[rank] * 0.7, requires_grad=True)
+    ls = RefLogitScale(case["scale"], trainable=False)
+    src = _ref_lines("trainers/text_text.py", 349, 369)
+    ns = dict(query_outputs={"embedding": q}, document_outputs={"embedding": d}, F=F, torch=torch,
+              gather_with_grad=ref.distributed.gather_with_grad, clip_loss=ref.loss.clip_loss, logit_scale=ls,
+              matryoshka_dims=case["dims"], matroyshka_loss_weights=case["weights"], dataset_name="x",
+              self=types.SimpleNamespace(tracker=None), kwargs={})
+    exec(src, ns)
+    loss = ns["loss"]
+    loss.backward()
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), loss=np.float64(loss.item()), dq=q.grad.numpy(), dd=d.grad.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _gradcache_worker(rank, ws, port, case, out_dir):
+    _init_pg(rank, ws, port)
+    ref = ref_loader.load()
+    torch.manual_seed(0)
+    tower = TinyTower(case)
+    xq, xd = make_gradcache_inputs(case, rank)
+    ls = RefLogitScale(case["scale"], trainable=False)
+    loss = ref.loss.grad_cache_loss(tower, {"input_ids": torch.tensor(xq)}, tower, {"input_ids": torch.tensor(xd)},
+                                    case["chunk"], ls)
+    g_gc = {k: p.grad.clone().numpy() for k, p in tower.named_parameters()}
+    # the plain (non-GradCache) step on the same weights: SURVEY Appendix A.10 -- they must agree
+    tower.zero_grad()
+    q = tower(input_ids=torch.tensor(xq))["embedding"]
+    d = tower(input_ids=torch.tensor(xd))["embedding"]
+    loss2 = ref.loss.clip_loss(q, d, ls, gather_enabled=ws > 1)
+    loss2.backward()
+    res = dict(loss=np.float64(loss.item()), loss_plain=np.float64(loss2.item()))
+    for k, g in g_gc.items():
+        res["gc_" + k] = g
+    for k, p in tower.named_parameters():
+        res["plain_" + k] = p.grad.numpy()
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), **res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run(worker, ws, case, port):
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        if ws == 1:
+            worker(0, 1, port, case, tmp)
+        else:
+            mp.spawn(worker, args=(ws, port, case, tmp), nprocs=ws, join=True)
+        out = {}
+        for r in range(ws):
+            with np.load(os.path.join(tmp, f"r{r}.npz")) as z:
+                for k in z.files:
+                    out[f"r{r}_{k}"] = z[k]
+        return out
+
+
+def gen_kat():
+    """tests/test_loss.py:5-17 (identity scale; the shipped call omits logit_scale and is stale)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = "29431"
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    ref = ref_loader.load()
+    query = torch.tensor([[1, 2], [2, 3], [3, 4]], dtype=torch.float32)
+    query /= torch.norm(query, dim=1, keepdim=True)
+    document = torch.tensor([[1, 2], [3, 4], [2, 3]], dtype=torch.float32)
+    document /= torch.norm(document, dim=1, keepdim=True)
+    loss = ref.loss.clip_loss(query, document, lambda x: x)
+    sim = torch.exp(query.matmul(document.T))
+    softmax = sim / sim.sum(dim=1, keepdim=True)
+    naive = -torch.log(softmax[torch.arange(3), torch.arange(3)]).mean()
+    assert torch.allclose(loss, naive)
+    dist.destroy_process_group()
+    np.savez(os.path.join(GOLDEN, "kat_test_loss.npz"), loss=np.float64(loss.item()), naive=np.float64(naive.item()))
+    print("kat", loss.item())
+
+
+def gen_encoder():
+    ref = ref_loader.load()
+    for name, case in ENCODER_CASES.items():
+        cfg = encoder_cfg(case)
+        hf_cfg = ref.hf_cfg.NomicBertConfig(
+            vocab_size=cfg.vocab_size, n_embd=cfg.n_embd, n_head=cfg.n_head, n_inner=cfg.n_inner, n_layer=cfg.n_layer,
+            n_positions=case["seq"], activation_function="swiglu", resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0,
+            layer_norm_epsilon=cfg.layer_norm_epsilon, rotary_emb_fraction=1.0, rotary_emb_base=cfg.rotary_emb_base,
+            qkv_proj_bias=False, mlp_fc1_bias=False, mlp_fc2_bias=False, prenorm=False, type_vocab_size=2,
+            pad_token_id=None, rotary_scaling_factor=None)
+        model = ref.hf.NomicBertModel(hf_cfg, add_pooling_layer=False)
+        sd = random_state_dict(cfg, seed=case["wseed"])
+        missing, unexpected = model.load_state_dict(sd, strict=True), None
+        model.train()  # dropout p = 0
+        ids, mask, gproj = make_encoder_inputs(case)
+        ids_t, mask_t = torch.tensor(ids), torch.tensor(mask)
+        out = model(ids_t, attention_mask=mask_t).last_hidden_state
+        ns = {"nn": torch.nn, "torch": torch}
+        exec(_ref_lines("models/biencoder/modeling_biencoder.py", 79, 90), ns)
+        pooled = ns["MeanPooling"]()(out, ids_t, mask_t)
+        emb = F.normalize(pooled, dim=-1)
+        emb_h = F.normalize(F.layer_norm(pooled, (cfg.n_embd,)), dim=-1)  # hamming=True variant (:282-285,307)
+        (emb * torch.tensor(gproj)).sum().backward()
+        grads = {k: p.grad.numpy() for k, p in model.named_parameters()}
+        keep = ["emb_ln.weight", "emb_ln.bias", "encoder.layers.0.attn.Wqkv.weight", "encoder.layers.0.norm1.weight",
+                f"encoder.layers.{cfg.n_layer - 1}.mlp.fc2.weight", f"encoder.layers.{cfg.n_layer - 1}.mlp.fc11.weight",
+                "encoder.layers.0.attn.out_proj.weight", "embeddings.token_type_embeddings.weight"]
+        res = dict(hidden_valid=(out * mask_t.unsqueeze(-1)).detach().numpy(), pooled=pooled.detach().numpy(),
+                   embedding=emb.detach().numpy(), embedding_hamming=emb_h.detach().numpy(),
+                   gsum_word=grads["embeddings.word_embeddings.weight"] @ np.linspace(-1.0, 1.0, cfg.n_embd).astype(np.float32))
+        for k in keep:
+            res["g_" + k] = grads[k]
+        res["gnorm_all"] = np.array([np.sqrt(sum(float((g.astype(np.float64) ** 2).sum()) for g in grads.values()))])
+        np.savez_compressed(os.path.join(GOLDEN, f"encoder_{name}.npz"), **res)
+        print("encoder", name, "emb[0,:4]", emb[0, :4].tolist())
+
+
+def main():
+    if not ref_loader.available():
+        raise SystemExit("needs /root/reference (build container only)")
+    os.makedirs(GOLDEN, exist_ok=True)
+    gen_kat()
+    port = 29440
+    for name, case in INFONCE_CASES.items():
+        out = _run(_infonce_worker, case["ws"], case, port)
+        port += 1
+        np.savez_compressed(os.path.join(GOLDEN, f"infonce_{name}.npz"), **out)
+        print("infonce", name, {k: (v.item() if v.ndim == 0 else v.shape) for k, v in out.items() if "loss" in k or "error" in k})
+    for name, case in DUAL_CASES.items():
+        out = _run(_dual_worker, case["ws"], case, port)
+        port += 1
+        np.savez_compressed(os.path.join(GOLDEN, f"dual_{name}.npz"), **out)
+        print("dual", name, {k: v.item() for k, v in out.items() if "loss" in k})
+    for name, case in MATRYOSHKA_CASES.items():
+        out = _run(_matryoshka_worker, case["ws"], case, port)
+        port += 1
+        np.savez_compressed(os.path.join(GOLDEN, f"matryoshka_{name}.npz"), **out)
+        print("matryoshka", name, {k: v.item() for k, v in out.items() if "loss" in k})
+    for ws in (1, 2):
+        case = dict(GRADCACHE_CASE, ws=ws)
+        out = _run(_gradcache_worker, ws, case, port)
+        port += 1
+        np.savez_compressed(os.path.join(GOLDEN, f"gradcache_ws{ws}.npz"), **out)
+        print("gradcache", ws, {k: v.item() for k, v in out.items() if "loss" in k})
+    gen_encoder()
+
+
+if __name__ == "__main__":
+    main()
