@@ -1,0 +1,124 @@
+// Host launcher + C entry point for the tcgen05 GEMM (see cx_gemm.cuh for the kernel).
+#include "cx_gemm.cuh"
+
+namespace cx {
+
+int gemm_block_n(int N) { return (N % 256 == 0) ? 256 : 128; }
+
+int gemm_grid(int M, int N, int splits) {
+  const int bn = gemm_block_n(N);
+  const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + bn - 1) / bn) * splits;
+  const int sms = sm_count();
+  return tiles < sms ? tiles : sms;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int MODE, bool OUT_F32, bool ACCUM>
+static int launch_one(const GemmArgs& g, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC) {
+  auto kern = gemm_kernel<BLOCK_N, A_MN, B_MN, MODE, OUT_F32, ACCUM>;
+  constexpr int smem = GemmSmem<BLOCK_N>::kTotal;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    CX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int grid = gemm_grid(g.M, g.N, g.splits);
+  kern<<<grid, kGemmThreads, smem, g.stream>>>(tmA, tmB, tmC, g.M, g.N, g.K, g.splits, g.ep);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int BLOCK_N, int MODE, bool OUT_F32, bool ACCUM>
+static int launch_majors(const GemmArgs& g, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c) {
+  if (MODE != EPI_STORE) {  // InfoNCE epilogues only exist for K-major operands
+    if (g.a_mn || g.b_mn) return fail(CX_ERR_UNSUPPORTED, "InfoNCE epilogues need K-major operands");
+    return launch_one<BLOCK_N, false, false, MODE, OUT_F32, ACCUM>(g, a, b, c);
+  } else {
+    if (!g.a_mn && !g.b_mn) return launch_one<BLOCK_N, false, false, EPI_STORE, OUT_F32, ACCUM>(g, a, b, c);
+    if (!g.a_mn && g.b_mn) return launch_one<BLOCK_N, false, true, EPI_STORE, OUT_F32, ACCUM>(g, a, b, c);
+    if (g.a_mn && !g.b_mn) return launch_one<BLOCK_N, true, false, EPI_STORE, OUT_F32, ACCUM>(g, a, b, c);
+    return launch_one<BLOCK_N, true, true, EPI_STORE, OUT_F32, ACCUM>(g, a, b, c);
+  }
+}
+
+template <int BLOCK_N>
+static int launch_bn(const GemmArgs& g, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c) {
+  switch (g.mode) {
+    case EPI_NCE_STATS:
+      return launch_majors<BLOCK_N, EPI_NCE_STATS, false, false>(g, a, b, c);
+    case EPI_NCE_DS:
+      return launch_majors<BLOCK_N, EPI_NCE_DS, false, false>(g, a, b, c);
+    case EPI_STORE:
+      if (!g.out_f32) return launch_majors<BLOCK_N, EPI_STORE, false, false>(g, a, b, c);
+      if (!g.accumulate) return launch_majors<BLOCK_N, EPI_STORE, true, false>(g, a, b, c);
+      return launch_majors<BLOCK_N, EPI_STORE, true, true>(g, a, b, c);
+  }
+  return fail(CX_ERR_INVALID, "bad epilogue mode");
+}
+
+int launch_gemm(const GemmArgs& g_in) {
+  GemmArgs g = g_in;
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return fail(CX_ERR_INVALID, "gemm: empty problem");
+  if (g.accumulate && !g.out_f32) return fail(CX_ERR_INVALID, "gemm: accumulate needs an fp32 output");
+  const int bn = gemm_block_n(g.N);
+  {
+    // split-K: fp32 outputs only (partials are combined by TMA reduce-add at L2)
+    const int tiles = ((g.M + kBlockM - 1) / kBlockM) * ((g.N + bn - 1) / bn);
+    const int num_kb = (g.K + kBlockK - 1) / kBlockK;
+    int splits = g.splits;
+    if (splits <= 0) {
+      splits = 1;
+      if (g.mode == EPI_STORE && g.out_f32 && tiles * 2 <= sm_count()) {
+        splits = sm_count() / tiles;
+        if (splits > num_kb / 4) splits = num_kb / 4;
+        if (splits < 1) splits = 1;
+      }
+    }
+    if (splits > 1 && !(g.mode == EPI_STORE && g.out_f32)) return fail(CX_ERR_INVALID, "gemm: split-K needs an fp32 output");
+    if (splits > num_kb) splits = num_kb;
+    g.splits = splits;
+    if (splits > 1 && !g.accumulate) {
+      CX_CUDA_CHECK(cudaMemset2DAsync(g.C, (size_t)g.ldc * 4, 0, (size_t)g.N * 4, (size_t)g.M, g.stream));
+      g.accumulate = true;
+    }
+  }
+  CUtensorMap tmA, tmB, tmC;
+  const auto BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const auto SW = CU_TENSOR_MAP_SWIZZLE_128B;
+  int rc;
+  if (!g.a_mn) rc = make_tmap_2d(&tmA, BF, 2, g.A, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)g.lda * 2, kBlockK, kBlockM, SW);
+  else rc = make_tmap_2d(&tmA, BF, 2, g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda * 2, 64, kBlockK, SW);
+  if (rc) return rc;
+  if (!g.b_mn) rc = make_tmap_2d(&tmB, BF, 2, g.B, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb * 2, kBlockK, (uint32_t)bn, SW);
+  else rc = make_tmap_2d(&tmB, BF, 2, g.B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb * 2, 64, kBlockK, SW);
+  if (rc) return rc;
+  if (g.mode == EPI_NCE_STATS) {
+    tmC = tmA;
+  } else if (g.out_f32) {
+    rc = make_tmap_2d(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.C, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldc * 4, 32, kBlockM, SW);
+  } else {
+    rc = make_tmap_2d(&tmC, BF, 2, g.C, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldc * 2, 64, kBlockM, SW);
+  }
+  if (rc) return rc;
+  return bn == 256 ? launch_bn<256>(g, tmA, tmB, tmC) : launch_bn<128>(g, tmA, tmB, tmC);
+}
+
+}  // namespace cx
+
+extern "C" int cx_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int a_major, int b_major,
+                            int64_t lda, int64_t ldb, int64_t ldc, int c_dtype, int accumulate, float alpha,
+                            cx_stream_t stream) {
+  CX_REQUIRE(A && B && C, "cx_gemm_bf16: null pointer");
+  CX_REQUIRE(c_dtype == CX_BF16 || c_dtype == CX_F32, "cx_gemm_bf16: bad c_dtype");
+  cx::GemmArgs g{};
+  g.A = A; g.B = B; g.C = C;
+  g.M = M; g.N = N; g.K = K;
+  g.a_mn = a_major == CX_MAJOR_MN;
+  g.b_mn = b_major == CX_MAJOR_MN;
+  g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+  g.out_f32 = c_dtype == CX_F32;
+  g.accumulate = accumulate != 0;
+  g.mode = cx::EPI_STORE;
+  g.ep.alpha = alpha;
+  g.stream = static_cast<cudaStream_t>(stream);
+  return cx::launch_gemm(g);
+}

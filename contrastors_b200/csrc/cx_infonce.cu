@@ -1,0 +1,292 @@
+// Fused InfoNCE forward / backward on the tcgen05 GEMM core (C ABI: cx_infonce_*).
+//
+// Replaces the reference's unfused chain  matmul -> LogitScale -> F.cross_entropy -> argmax  and its autograd
+// backward (/root/reference/src/contrastors/loss.py:105-130, modeling_biencoder.py:37-38).  The [n x m] logits never
+// exist in HBM in fp32: the forward keeps them in TMEM and reduces them to per-row statistics in the GEMM epilogue;
+// the backward recomputes them, emits dS = coef*(softmax - onehot) as bf16 into a workspace that stays L2-resident
+// (n*m*2 bytes), and contracts it twice (dQ = dS D, dD = dS^T Q) with the same GEMM core (MN-major operands, so no
+// transposes are materialised).
+#include <math.h>
+
+#include "cx_gemm.cuh"
+
+namespace cx {
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct NceWorkspace {
+  float* part_max;
+  float* part_sum;
+  int* part_arg;
+  float* dlogit_part;
+  float* block_part;     // [2 * kMaxCombineBlocks]
+  unsigned int* ticket;  // [1]
+  __nv_bfloat16* ds;
+  int64_t ld_ds;
+  size_t bytes;
+};
+constexpr int kMaxCombineBlocks = 1024;
+constexpr int kMaxGrid = 1024;
+
+static NceWorkspace carve(void* base, int n, int m) {
+  NceWorkspace w{};
+  const size_t ct = (size_t)(m + 127) / 128;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return reinterpret_cast<uint8_t*>(base) + o;
+  };
+  w.part_max = reinterpret_cast<float*>(take(ct * n * 4));
+  w.part_sum = reinterpret_cast<float*>(take(ct * n * 4));
+  w.part_arg = reinterpret_cast<int*>(take(ct * n * 4));
+  w.dlogit_part = reinterpret_cast<float*>(take((size_t)kMaxGrid * 128 * 4));
+  w.block_part = reinterpret_cast<float*>(take((size_t)2 * kMaxCombineBlocks * 4));
+  w.ticket = reinterpret_cast<unsigned int*>(take(256));
+  w.ld_ds = (int64_t)align_up((size_t)m, 8);
+  w.ds = reinterpret_cast<__nv_bfloat16*>(take((size_t)n * w.ld_ds * 2));
+  w.bytes = off;
+  return w;
+}
+
+// One thread per row: merge the per-column-tile partials (in ascending tile order, so the first maximum wins exactly
+// like ATen's argmax), produce lse / argmax, and reduce the loss sum and the hit count deterministically (fixed-order
+// block partials summed by the last block to arrive).
+__global__ void nce_combine_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum,
+                                   const int* __restrict__ part_arg, const float* __restrict__ label_logit, int n,
+                                   int n_col_tiles, int label_offset, int label_stride, float* __restrict__ lse,
+                                   int* __restrict__ argmax, float* __restrict__ stats, float* __restrict__ block_part,
+                                   unsigned int* __restrict__ ticket) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  float loss_term = 0.f, hit = 0.f;
+  if (row < n) {
+    float gmax = -INFINITY;
+    int garg = 0;
+    for (int t = 0; t < n_col_tiles; ++t) {
+      const float mx = part_max[(size_t)t * n + row];
+      if (mx > gmax) {
+        gmax = mx;
+        garg = part_arg[(size_t)t * n + row];
+      }
+    }
+    float sum = 0.f;
+    for (int t = 0; t < n_col_tiles; ++t) {
+      const float mx = part_max[(size_t)t * n + row];
+      sum += part_sum[(size_t)t * n + row] * exp2f((mx - gmax) * 1.4426950408889634f);
+    }
+    const float l = gmax + logf(sum);
+    lse[row] = l;
+    argmax[row] = garg;
+    loss_term = l - label_logit[row];
+    hit = (garg == (row + label_offset) * label_stride) ? 1.f : 0.f;
+  }
+  __shared__ float s_loss[32], s_hit[32];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 16; o > 0; o >>= 1) {
+    loss_term += __shfl_xor_sync(0xffffffffu, loss_term, o);
+    hit += __shfl_xor_sync(0xffffffffu, hit, o);
+  }
+  if (lane == 0) {
+    s_loss[warp] = loss_term;
+    s_hit[warp] = hit;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      a += s_loss[w];
+      b += s_hit[w];
+    }
+    block_part[2 * blockIdx.x] = a;
+    block_part[2 * blockIdx.x + 1] = b;
+    __threadfence();
+    const unsigned int t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < (int)gridDim.x; ++i) {
+      a += reinterpret_cast<volatile float*>(block_part)[2 * i];
+      b += reinterpret_cast<volatile float*>(block_part)[2 * i + 1];
+    }
+    stats[0] = a;
+    stats[1] = b;
+    *ticket = 0;  // ready for the next call on this workspace
+  }
+}
+
+__global__ void nce_dlogit_kernel(const float* __restrict__ part, int count, float* __restrict__ stats) {
+  __shared__ float s[1024];
+  float a = 0.f;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) a += part[i];
+  s[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) stats[2] = s[0];
+}
+
+// ---------------------------------------------------------------- row utilities
+// One warp per row.
+__global__ void rows_to_bf16_kernel(const float* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ y, int64_t ldy,
+                                    float* __restrict__ inv_norm, int rows, int k, int normalize) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (size_t)row * ldx;
+  float inv = 1.f;
+  if (normalize) {
+    float ss = 0.f;
+    for (int j = lane; j < k; j += 32) ss = fmaf(xr[j], xr[j], ss);
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize: x / max(||x||, eps)
+  }
+  if (inv_norm != nullptr && lane == 0) inv_norm[row] = inv;
+  if (y != nullptr) {
+    __nv_bfloat16* yr = y + (size_t)row * ldy;
+    for (int j = lane; j < k; j += 32) yr[j] = __float2bfloat16_rn(xr[j] * inv);
+  }
+}
+
+// gx = g' - y (g'.y),  y = x*inv, g' = g * (g_prescaled ? 1 : inv)   (backward of F.normalize)
+__global__ void l2norm_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ g, int64_t ldg,
+                                  const float* __restrict__ inv_norm, float* __restrict__ gx, int64_t ldgx, int rows,
+                                  int k, int g_prescaled, int accumulate) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float inv = inv_norm[row];
+  const float gs = g_prescaled ? 1.f : inv;
+  const float* xr = x + (size_t)row * ldx;
+  const float* gr = g + (size_t)row * ldg;
+  float dot = 0.f;
+  for (int j = lane; j < k; j += 32) dot = fmaf(gr[j] * gs, xr[j] * inv, dot);
+  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  float* o_ = gx + (size_t)row * ldgx;
+  for (int j = lane; j < k; j += 32) {
+    const float v = gr[j] * gs - xr[j] * inv * dot;
+    o_[j] = accumulate ? o_[j] + v : v;
+  }
+}
+
+}  // namespace cx
+
+using namespace cx;
+
+extern "C" size_t cx_infonce_workspace_bytes(int n, int m) {
+  if (n <= 0 || m <= 0) return 0;
+  return carve(nullptr, n, m).bytes + 256;
+}
+
+static void* align256(void* p) { return reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(p) + 255) & ~uintptr_t(255)); }
+
+extern "C" int cx_infonce_fwd(const void* q, int64_t ldq, const void* d, int64_t ldd, int n, int m, int k_dim,
+                              float scale, const float* scale_dev, const float* rq, const float* rd, int label_offset, int label_stride,
+                              float* lse, int32_t* argmax, float* label_logit, float* stats, void* workspace,
+                              cx_stream_t stream_) {
+  CX_REQUIRE(q && d && lse && argmax && label_logit && stats && workspace, "cx_infonce_fwd: null pointer");
+  CX_REQUIRE(n > 0 && m > 0 && k_dim > 0, "cx_infonce_fwd: empty problem");
+  CX_REQUIRE((long long)(n - 1 + label_offset) * label_stride < m && label_offset >= 0 && label_stride >= 1,
+             "cx_infonce_fwd: labels out of range");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NceWorkspace w = carve(align256(workspace), n, m);
+  GemmArgs g{};
+  g.A = q; g.B = d; g.C = nullptr;
+  g.M = n; g.N = m; g.K = k_dim;
+  g.a_mn = false; g.b_mn = false;
+  g.lda = ldq; g.ldb = ldd; g.ldc = 0;
+  g.out_f32 = false; g.accumulate = false; g.splits = 1;
+  g.mode = EPI_NCE_STATS;
+  g.ep.scale = scale; g.ep.scale_dev = scale_dev; g.ep.rq = rq; g.ep.rd = rd;
+  g.ep.label_offset = label_offset; g.ep.label_stride = label_stride;
+  g.ep.part_max = w.part_max; g.ep.part_sum = w.part_sum; g.ep.part_arg = w.part_arg;
+  g.ep.label_logit = label_logit;
+  g.stream = stream;
+  int rc = launch_gemm(g);
+  if (rc) return rc;
+  const int bn = gemm_block_n(m);
+  const int n_col_tiles = (m + bn - 1) / bn;
+  const int threads = 128;
+  const int blocks = (n + threads - 1) / threads;
+  CX_REQUIRE(blocks <= kMaxCombineBlocks, "cx_infonce_fwd: n too large");
+  CX_CUDA_CHECK(cudaMemsetAsync(w.ticket, 0, 4, stream));
+  nce_combine_kernel<<<blocks, threads, 0, stream>>>(w.part_max, w.part_sum, w.part_arg, label_logit, n, n_col_tiles,
+                                                     label_offset, label_stride, lse, argmax, stats, w.block_part, w.ticket);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cx_infonce_bwd(const void* q, int64_t ldq, const void* d, int64_t ldd, int n, int m, int k_dim,
+                              float scale, const float* scale_dev, const float* rq, const float* rd, int label_offset, int label_stride,
+                              const float* lse, float coef, const float* coef_dev, float* dq, int64_t lddq, float* dd, int64_t lddd,
+                              int accumulate_dd, float* stats, void* workspace, cx_stream_t stream_) {
+  CX_REQUIRE(q && d && lse && dq && dd && stats && workspace, "cx_infonce_bwd: null pointer");
+  CX_REQUIRE(n > 0 && m > 0 && k_dim > 0, "cx_infonce_bwd: empty problem");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NceWorkspace w = carve(align256(workspace), n, m);
+  // stage 1: dS (bf16) = coef * (softmax - onehot) [* rq_i rd_j]
+  GemmArgs g{};
+  g.A = q; g.B = d; g.C = w.ds;
+  g.M = n; g.N = m; g.K = k_dim;
+  g.a_mn = false; g.b_mn = false;
+  g.lda = ldq; g.ldb = ldd; g.ldc = w.ld_ds;
+  g.out_f32 = false; g.accumulate = false; g.splits = 1;
+  g.mode = EPI_NCE_DS;
+  g.ep.scale = scale; g.ep.scale_dev = scale_dev; g.ep.rq = rq; g.ep.rd = rd;
+  g.ep.label_offset = label_offset; g.ep.label_stride = label_stride;
+  g.ep.lse = lse; g.ep.coef = coef; g.ep.coef_dev = coef_dev;
+  g.ep.dlogit_part = w.dlogit_part;
+  g.stream = stream;
+  const int grid1 = gemm_grid(n, m, 1);
+  CX_REQUIRE(grid1 <= kMaxGrid, "cx_infonce_bwd: grid too large");
+  int rc = launch_gemm(g);
+  if (rc) return rc;
+  nce_dlogit_kernel<<<1, 1024, 0, stream>>>(w.dlogit_part, grid1 * 128, stats);
+  CX_LAUNCH_CHECK();
+  // stage 2a: dQ[n,k] = scale * dS[n,m] (K-major A) x D[m,k] (MN-major B), split-K over m
+  GemmArgs a{};
+  a.A = w.ds; a.B = d; a.C = dq;
+  a.M = n; a.N = k_dim; a.K = m;
+  a.a_mn = false; a.b_mn = true;
+  a.lda = w.ld_ds; a.ldb = ldd; a.ldc = lddq;
+  a.out_f32 = true; a.accumulate = false; a.splits = 0;
+  a.mode = EPI_STORE; a.ep.alpha = scale; a.ep.alpha_dev = scale_dev; a.stream = stream;
+  rc = launch_gemm(a);
+  if (rc) return rc;
+  // stage 2b: dD[m,k] = scale * dS^T (MN-major A: stored [n,m]) x Q[n,k] (MN-major B)
+  GemmArgs b{};
+  b.A = w.ds; b.B = q; b.C = dd;
+  b.M = m; b.N = k_dim; b.K = n;
+  b.a_mn = true; b.b_mn = true;
+  b.lda = w.ld_ds; b.ldb = ldq; b.ldc = lddd;
+  b.out_f32 = true; b.accumulate = accumulate_dd != 0; b.splits = 0;
+  b.mode = EPI_STORE; b.ep.alpha = scale; b.ep.alpha_dev = scale_dev; b.stream = stream;
+  return launch_gemm(b);
+}
+
+extern "C" int cx_rows_to_bf16(const float* x, int64_t ldx, void* y_bf16, int64_t ldy, float* inv_norm, int rows, int k,
+                               int normalize, cx_stream_t stream) {
+  CX_REQUIRE(x && (y_bf16 || inv_norm), "cx_rows_to_bf16: null pointer");
+  if (rows <= 0 || k <= 0) return 0;
+  const int warps = 8;
+  rows_to_bf16_kernel<<<(rows + warps - 1) / warps, warps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, ldx, reinterpret_cast<__nv_bfloat16*>(y_bf16), ldy, inv_norm, rows, k, normalize);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cx_l2norm_bwd(const float* x, int64_t ldx, const float* g, int64_t ldg, const float* inv_norm, float* gx,
+                             int64_t ldgx, int rows, int k, int g_prescaled, int accumulate, cx_stream_t stream) {
+  CX_REQUIRE(x && g && inv_norm && gx, "cx_l2norm_bwd: null pointer");
+  if (rows <= 0 || k <= 0) return 0;
+  const int warps = 8;
+  l2norm_bwd_kernel<<<(rows + warps - 1) / warps, warps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, ldx, g, ldg, inv_norm, gx, ldgx, rows, k, g_prescaled, accumulate);
+  CX_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,281 @@
+"""InfoNCE / GradCache with the reference's names and call contracts, backed by the fused sm_100a kernels.
+
+Reference: /root/reference/src/contrastors/loss.py
+  clip_loss :76-132, get_chunked_embeddings :135-146, accumulate_gradients :149-161, cache_loss :164-184,
+  grad_cache_loss :187-213; Matryoshka loop trainers/text_text.py:352-369; symmetric CLIP loss
+  models/dual_encoder/modeling_dual_encoder.py:46-68.
+
+What differs from the reference is *how*, not *what*: the [N x M] logits are never materialised in HBM (tcgen05 tiles
+reduced in the GEMM epilogue), the gather of document embeddings is a single bf16 all_gather_into_tensor, the backward
+emits dQ / dD from the recomputed tiles, and neither the logit scale nor autograd's grad_output is read back to the
+host.  Semantics kept on purpose: the ``* world_size`` factor, the label stride for in-batch
+hard negatives, the ``rank * N`` label offset, per-rank accuracy, the bidirectional branch's shape error when M != N,
+and the requirement of an initialised process group.
+"""
+from __future__ import annotations
+
+from contextlib import nullcontext
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .distributed import _rank, all_gather_rows, gather_with_grad, reduce_scatter_rows  # noqa: F401
+from .rand_state import RandContext
+
+
+def _scale_tensor(logit_scale, device) -> torch.Tensor:
+    """The scalar e^p a LogitScale-style callable multiplies by (modeling_biencoder.py:37-38), as a 0-dim fp32
+    device tensor that stays attached to the parameter's autograd graph (works through a DDP wrapper too)."""
+    with torch.autocast(device_type=device.type, enabled=False):
+        s = logit_scale(torch.ones((), device=device, dtype=torch.float32))
+    if not isinstance(s, torch.Tensor):
+        s = torch.tensor(float(s), device=device, dtype=torch.float32)
+    return s.to(torch.float32).reshape(())
+
+
+@dataclass
+class _NceSpec:
+    label_offset: int
+    label_stride: int
+    mult: float                      # loss = mult * mean_i CE_i   (world size, or ws/2 for the CLIP form)
+    gather: bool = False             # all-gather `document` inside (gather_with_grad semantics)
+    dims: Optional[List[int]] = None  # Matryoshka prefix dims (None = full width)
+    weights: Optional[List[float]] = None
+    normalize: bool = False          # L2-normalise each prefix inside the kernel (rq / rd epilogue scales)
+    out: dict = field(default_factory=dict)  # per-dim stats tensors for logging (accuracy), filled by forward
+
+
+def _as_bf16_rows(x: torch.Tensor):
+    """bf16, row-contiguous, row stride a multiple of 8 elements (16 B, TMA requirement)."""
+    if x.dtype == torch.bfloat16 and x.stride(1) == 1 and x.stride(0) % 8 == 0 and x.data_ptr() % 16 == 0:
+        return x
+    if x.dtype != torch.float32 or x.stride(1) != 1:
+        x = x.float().contiguous()
+    y, _ = ops.rows_to_bf16(x)
+    return y
+
+
+class _FusedInfoNCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, query, document, scale_t, spec: _NceSpec):
+        if not (query.is_cuda and document.is_cuda):
+            raise RuntimeError("contrastors_b200.clip_loss needs CUDA tensors on a B200 (there is no CPU fallback); "
+                               "the CPU restatement lives in oracle/ and is test infrastructure only")
+        n, width = query.shape
+        q_bf = _as_bf16_rows(query.detach())
+        d_loc = _as_bf16_rows(document.detach())
+        d_bf = all_gather_rows(d_loc) if spec.gather else d_loc
+        m = d_bf.shape[0]
+        dims = spec.dims or [width]
+        weights = spec.weights or [1.0] * len(dims)
+        ws_buf = ops.infonce_workspace(n, m, query.device)
+        scale_dev = scale_t.detach().contiguous()
+        loss = torch.zeros((), device=query.device, dtype=torch.float32)
+        saved_lse, saved_rq, saved_rd = [], [], []
+        q32 = d32 = None
+        if spec.normalize:
+            # prefix norms from the same bf16-rounded rows the MMA consumes
+            q32, d32 = q_bf.float(), d_bf.float()
+        for w, k in zip(weights, dims):
+            rq = rd = None
+            if spec.normalize:
+                rq, rd = ops.row_inv_norms(q32, k), ops.row_inv_norms(d32, k)
+            lse, argmax, label_logit, stats = ops.infonce_fwd(q_bf, d_bf, k, 1.0, scale_dev, rq, rd, spec.label_offset,
+                                                              spec.label_stride, ws_buf)
+            loss = loss + stats[0] * (w * spec.mult / n)
+            spec.out[k] = dict(stats=stats, argmax=argmax, lse=lse)
+            saved_lse.append(lse)
+            saved_rq.append(rq)
+            saved_rd.append(rd)
+        ctx.spec, ctx.dims, ctx.weights = spec, dims, weights
+        ctx.n, ctx.m, ctx.width = n, m, width
+        ctx.local_rows = document.shape[0]
+        ctx.q_dtype, ctx.d_dtype = query.dtype, document.dtype
+        ctx.ws_buf = ws_buf
+        ctx.aux = (saved_lse, saved_rq, saved_rd, q32, d32)
+        ctx.save_for_backward(q_bf, d_bf, scale_dev)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        q_bf, d_bf, scale_dev = ctx.saved_tensors
+        spec = ctx.spec
+        saved_lse, saved_rq, saved_rd, q32, d32 = ctx.aux
+        n, m, width = ctx.n, ctx.m, ctx.width
+        dev = q_bf.device
+        coef_dev = grad_loss.detach().to(torch.float32).contiguous()
+        dq = torch.empty(n, width, device=dev, dtype=torch.float32)
+        dd = torch.empty(m, width, device=dev, dtype=torch.float32)
+        if spec.normalize or len(ctx.dims) > 1 or ctx.dims[0] != width:
+            dq.zero_()
+            dd.zero_()
+        dlogit = torch.zeros((), device=dev, dtype=torch.float32)
+        for i, (w, k) in enumerate(zip(ctx.weights, ctx.dims)):
+            stats = torch.zeros(4, device=dev, dtype=torch.float32)
+            coef = w * spec.mult / n
+            if not spec.normalize and k == width and len(ctx.dims) == 1:
+                ops.infonce_bwd(q_bf, d_bf, k, 1.0, scale_dev, None, None, spec.label_offset, spec.label_stride,
+                                saved_lse[i], coef, coef_dev, dq, dd, False, stats, ctx.ws_buf)
+            else:
+                gq = torch.empty(n, k, device=dev, dtype=torch.float32)
+                gd = torch.empty(m, k, device=dev, dtype=torch.float32)
+                ops.infonce_bwd(q_bf, d_bf, k, 1.0, scale_dev, saved_rq[i], saved_rd[i], spec.label_offset,
+                                spec.label_stride, saved_lse[i], coef, coef_dev, gq, gd, False, stats, ctx.ws_buf)
+                if spec.normalize:
+                    ops.l2norm_bwd(q32, gq, saved_rq[i], k, out=dq, g_prescaled=True, accumulate=True)
+                    ops.l2norm_bwd(d32, gd, saved_rd[i], k, out=dd, g_prescaled=True, accumulate=True)
+                else:
+                    dq[:, :k] += gq
+                    dd[:, :k] += gd
+            dlogit = dlogit + stats[2]
+        if spec.gather:
+            dd = reduce_scatter_rows(dd)
+        gscale = None
+        if ctx.needs_input_grad[2]:
+            gscale = dlogit / scale_dev  # d loss / d (e^p); autograd chains exp'() = e^p back to p
+        return dq.to(ctx.q_dtype), dd.to(ctx.d_dtype), gscale, None
+
+
+def _fused_infonce(query, document, logit_scale, spec: _NceSpec):
+    scale_t = _scale_tensor(logit_scale, query.device)
+    return _FusedInfoNCE.apply(query, document, scale_t, spec)
+
+
+def clip_loss(query, document, logit_scale, step=None, gather_enabled=False, tracker=None, dataset="",
+              bidirectional=False):
+    """InfoNCE for N queries against M >= N documents (reference loss.py:76-132, same signature).
+
+    ``logit_scale`` is a callable x -> x * e^p (``LogitScale`` or a DDP-wrapped one).  Returns a 0-dim fp32 tensor
+    attached to autograd: loss = CE(scale * q d^T, labels) * world_size with labels = (arange(N) + rank*N) * stride.
+    """
+    ws = dist.get_world_size()  # raises without a process group, exactly like the reference (loss.py:117)
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    n = query.shape[0]
+    gather = bool(gather_enabled) and ws > 1
+    m = document.shape[0] * (ws if gather else 1)
+    stride = m // (n * ws)
+    if bidirectional:
+        if m != n:  # F.cross_entropy's complaint in the reference (loss.py:119-123)
+            raise ValueError(f"Expected input batch_size ({m}) to match target batch_size ({n}).")
+        spec_q = _NceSpec(label_offset=rank * n, label_stride=stride, mult=1.0, gather=gather)
+        spec_d = _NceSpec(label_offset=rank * n, label_stride=stride, mult=1.0, gather=False)
+        loss = _fused_infonce(query, document, logit_scale, spec_q)
+        doc_full = gather_with_grad(document) if gather else document
+        loss = loss + _fused_infonce(doc_full, query, logit_scale, spec_d)
+        spec = spec_q
+    else:
+        spec = _NceSpec(label_offset=rank * n, label_stride=stride, mult=float(ws), gather=gather)
+        loss = _fused_infonce(query, document, logit_scale, spec)
+    if tracker is not None:
+        # per-rank top-1 accuracy, as the reference (loss.py:127-130); the hit count came out of the same kernel
+        k = query.shape[1]
+        accuracy = (spec.out[k]["stats"][1] / n).detach().cpu().item()
+        tracker.log({f"accuracy/accuracy_{dataset}": accuracy}, step=step)
+    return loss
+
+
+def matryoshka_clip_loss(queries, all_documents, logit_scale, dims, weights, tracker=None, dataset="", step=None):
+    """sum_w w * clip_loss(normalize(q[:, :dim]), normalize(all_d[:, :dim])) (reference text_text.py:352-369) as one
+    autograd node: every prefix reuses the same bf16 operands (K = dim prefix of the row stride) and the fused kernel's
+    per-row inverse norms, so no sliced/normalised copies are materialised.  ``all_documents`` is already gathered."""
+    ws = dist.get_world_size()
+    rank = dist.get_rank()
+    n, m = queries.shape[0], all_documents.shape[0]
+    spec = _NceSpec(label_offset=rank * n, label_stride=m // (n * ws), mult=float(ws), gather=False,
+                    dims=list(dims), weights=[float(w) for w in weights], normalize=True)
+    loss = _fused_infonce(queries, all_documents, logit_scale, spec)
+    if tracker is not None:
+        for dim in dims:
+            acc = (spec.out[dim]["stats"][1] / n).detach().cpu().item()
+            tracker.log({f"accuracy/accuracy_{dataset}_matryoshka_{dim}": acc}, step=step)
+    return loss
+
+
+def symmetric_clip_loss(text_emb, vision_emb, logit_scale):
+    """(CE(scale v t_all^T) + CE(scale t v_all^T)) / 2 * world_size on un-normalised tower outputs
+    (reference modeling_dual_encoder.py:46-65): normalisation, both gathers and both directions run fused."""
+    ws = dist.get_world_size()
+    rank = dist.get_rank()
+    n = vision_emb.shape[0]
+    gather = ws > 1
+    mk = lambda: _NceSpec(label_offset=rank * n, label_stride=1, mult=ws / 2.0, gather=gather, normalize=True)
+    loss_i = _fused_infonce(vision_emb, text_emb, logit_scale, mk())
+    loss_t = _fused_infonce(text_emb, vision_emb, logit_scale, mk())
+    return loss_i + loss_t
+
+
+# ----------------------------------------------------------------------------------------------- GradCache
+def _autocast_for(tensors):
+    dev = "cuda"
+    for t in (tensors.values() if isinstance(tensors, dict) else tensors):
+        if isinstance(t, torch.Tensor):
+            dev = t.device.type
+            break
+    return torch.autocast(dev, dtype=torch.bfloat16)
+
+
+def get_chunked_embeddings(model, chunks):
+    """Pass 1 of GradCache (reference loss.py:135-146): no-grad bf16 forwards, one RNG snapshot per chunk."""
+    embeddings, rand_states = [], []
+    with torch.no_grad():
+        for chunk in chunks:
+            rand_states.append(RandContext(chunk))
+            with _autocast_for(chunk):
+                emb = model(**chunk)
+            embeddings.append(emb["embedding"])
+    return torch.concat(embeddings, dim=0), rand_states
+
+
+def accumulate_gradients(model, inputs, cache, rand_states, router_aux_coeff):
+    """Pass 2 of GradCache (reference loss.py:149-161): re-forward each chunk with its RNG replayed and back-propagate
+    <embedding, cached gradient>; DDP gradient sync only on the last chunk."""
+    length = len(inputs)
+    no_sync = getattr(model, "no_sync", nullcontext)
+    sync_contexts = [no_sync] * (length - 1) + [nullcontext]
+    for inp, grad, state, sync_context in zip(inputs, cache, rand_states, sync_contexts):
+        with sync_context():
+            with state:
+                with _autocast_for(inp):
+                    embedding = model(**inp)
+            surrogate = torch.dot(embedding["embedding"].flatten().float(), grad.flatten().float())
+            if "router_loss" in embedding and embedding["router_loss"] is not None:
+                surrogate = surrogate + embedding["router_loss"] * router_aux_coeff
+            surrogate.backward()
+
+
+def cache_loss(tower1, tower2, query_embeddings, document_embeddings, logit_scale, bidirectional=False):
+    """Loss on the cached embeddings and its gradients w.r.t. them (reference loss.py:164-184).
+    Returns (dQ, dD, loss.detach()).  tower1/tower2 are unused, as in the reference (Appendix A.6)."""
+    query_embs = query_embeddings.detach().requires_grad_()
+    document_embs = document_embeddings.detach().requires_grad_()
+    loss = clip_loss(query_embs, document_embs, logit_scale, gather_enabled=True, bidirectional=bidirectional)
+    loss.backward()
+    return query_embs.grad, document_embs.grad, loss.detach()
+
+
+def grad_cache_loss(tower1, t1_inputs, tower2, t2_inputs, chunk_size, logit_scale, bidirectional=False,
+                    router_aux_coeff=False):
+    """GradCache step (reference loss.py:187-213): chunked no-grad embeddings for both towers, the loss and its
+    embedding gradients, then chunked re-forward/backward per tower; leaves gradients in ``param.grad`` and returns
+    the detached loss.  Tower 2 is skipped when it is not training (reference :210)."""
+    total_bs = t1_inputs["input_ids"].shape[0]
+    chunked_queries, chunked_documents = [], []
+    for start in range(0, total_bs, chunk_size):
+        chunked_queries.append({k: v[start:start + chunk_size] for k, v in t1_inputs.items()})
+        chunked_documents.append({k: v[start:start + chunk_size] for k, v in t2_inputs.items()})
+
+    query_embs, query_rand_states = get_chunked_embeddings(tower1, chunked_queries)
+    document_embs, doc_rand_states = get_chunked_embeddings(tower2, chunked_documents)
+
+    query_cache, document_cache, loss = cache_loss(tower1, tower2, query_embs, document_embs, logit_scale,
+                                                   bidirectional=bidirectional)
+
+    accumulate_gradients(tower1, chunked_queries, query_cache.split(chunk_size), query_rand_states,
+                         router_aux_coeff=router_aux_coeff)
+    if tower2.training:
+        accumulate_gradients(tower2, chunked_documents, document_cache.split(chunk_size), doc_rand_states,
+                             router_aux_coeff=router_aux_coeff)
+    return loss

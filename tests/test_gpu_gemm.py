@@ -1,0 +1,55 @@
+"""tcgen05 GEMM core (through the C ABI) against a plain fp32 torch reference of the same contraction."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a, b, a_major, b_major):
+    A = a.float() if a_major == 0 else a.float().t()
+    B = b.float() if b_major == 0 else b.float().t()
+    return A @ B.t()
+
+
+@pytest.mark.parametrize("a_major,b_major", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (384, 768, 768), (200, 136, 72), (128, 2304, 768)])
+def test_gemm_majors_bf16_out(a_major, b_major, M, N, K):
+    from contrastors_b200 import ops
+    torch.manual_seed(0)
+    dev = "cuda"
+    a = torch.randn((M, K) if a_major == 0 else (K, M), device=dev).to(torch.bfloat16)
+    b = torch.randn((N, K) if b_major == 0 else (K, N), device=dev).to(torch.bfloat16)
+    c = ops.gemm(a, b, a_major=a_major, b_major=b_major)
+    ref = _ref(a, b, a_major, b_major)
+    err = (c.float() - ref).abs().max().item()
+    # bf16 output rounding: 2^-9 relative on values up to ~4*sqrt(K)
+    assert err <= 2.0 ** -8 * ref.abs().max().item() + 1e-3, err
+
+
+@pytest.mark.parametrize("a_major,b_major,M,N,K", [(0, 0, 256, 256, 4096), (1, 1, 768, 768, 8192), (0, 1, 2048, 768, 16384),
+                                                    (1, 1, 16384, 768, 2048), (1, 0, 130, 72, 200)])
+def test_gemm_fp32_out_splitk_and_accumulate(a_major, b_major, M, N, K):
+    from contrastors_b200 import ops
+    torch.manual_seed(1)
+    dev = "cuda"
+    a = torch.randn((M, K) if a_major == 0 else (K, M), device=dev).to(torch.bfloat16)
+    b = torch.randn((N, K) if b_major == 0 else (K, N), device=dev).to(torch.bfloat16)
+    ref = _ref(a, b, a_major, b_major)
+    c = ops.gemm(a, b, a_major=a_major, b_major=b_major, out_dtype=torch.float32, alpha=0.5)
+    tol = 1e-5 * ref.abs().max().item() * (K ** 0.5) + 1e-4
+    assert (c - 0.5 * ref).abs().max().item() <= tol
+    base = torch.randn(M, N, device=dev)
+    out = base.clone()
+    ops.gemm(a, b, a_major=a_major, b_major=b_major, out=out, accumulate=True)
+    assert (out - (base + ref)).abs().max().item() <= tol
+
+
+def test_gemm_strided_operands():
+    from contrastors_b200 import ops
+    torch.manual_seed(2)
+    big_a = torch.randn(300, 1024, device="cuda").to(torch.bfloat16)
+    big_b = torch.randn(520, 1024, device="cuda").to(torch.bfloat16)
+    a, b = big_a[:, :256], big_b[:, :256]  # K prefix of a wider row stride (the Matryoshka access pattern)
+    c = ops.gemm(a, b, out_dtype=torch.float32)
+    ref = a.float() @ b.float().t()
+    assert (c - ref).abs().max().item() <= 1e-3
