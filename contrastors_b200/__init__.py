@@ -9,6 +9,7 @@ from .distributed import gather, gather_with_grad  # noqa: F401
 from .logit_scale import LogitScale  # noqa: F401
 from .loss import (accumulate_gradients, cache_loss, clip_loss, get_chunked_embeddings, grad_cache_loss,  # noqa: F401
                    matryoshka_clip_loss, symmetric_clip_loss)
+from .models import BiEncoder, BiEncoderConfig, NomicBertConfig, NomicBertModel, nomic_bert_base  # noqa: F401
 from .rand_state import RandContext  # noqa: F401
 
 __version__ = "0.1.0"

@@ -23,12 +23,33 @@ SIGNATURES = {
     "cx_version": (_i, []),
     "cx_launch_count": (C.c_ulonglong, []),
     "cx_gemm_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i, _i, _f, _vp]),
-    "cx_infonce_workspace_bytes": (_sz, [_i, _i]),
+    "cx_infonce_workspace_bytes": (_sz, [_i, _i, _i]),
     "cx_infonce_fwd": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cx_infonce_bwd": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp, _f, _vp, _vp, _i64, _vp,
                             _i64, _i, _vp, _vp, _vp]),
     "cx_rows_to_bf16": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _i, _i, _vp]),
     "cx_l2norm_bwd": (_i, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
+    "cx_add_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "cx_layernorm_bwd_workspace_bytes": (_sz, [_i]),
+    "cx_add_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "cx_embed_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "cx_embed_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _vp]),
+    "cx_token_positions": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "cx_rope_inplace": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "cx_dq_finalize_rope": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "cx_dq_finalize": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "cx_swiglu_fwd": (_i, [_vp, _vp, _i64, _i, _vp]),
+    "cx_swiglu_bwd": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
+    "cx_mean_pool_fwd": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "cx_mean_pool_bwd": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "cx_embed_head_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "cx_embed_head_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "cx_grad_clip_workspace_bytes": (_sz, []),
+    "cx_grad_clip_coef": (_i, [_vp, _i64, _f, _vp, _vp, _vp]),
+    "cx_adamw_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _vp, _f, _i, _vp]),
+    "cx_cast_f32_bf16": (_i, [_vp, _vp, _i64, _vp]),
+    "cx_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
+    "cx_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
 }
 
 

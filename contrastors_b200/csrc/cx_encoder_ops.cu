@@ -1,0 +1,757 @@
+// HBM-bound encoder kernels (C ABI: cx_add_layernorm_*, cx_embed_layernorm_*, cx_rope_*, cx_swiglu_*, cx_mean_pool_*,
+// cx_embed_head_*, cx_token_positions, cx_adamw_*, cx_sumsq, cx_cast_*).
+//
+// They replace the flash-attn side extensions the reference calls:
+//   K2 dropout_add_layer_norm (layers/block.py:422-431,453-462; models/encoder/modeling_nomic_bert.py:531-535)
+//   K4 swiglu (layers/mlp.py:73-75)      K5 rotary (layers/embedding.py:685-706)
+//   K6 unpad/pad bookkeeping             K11 MeanPooling / hamming LN / F.normalize (modeling_biencoder.py:79-90,307-317)
+// plus the optimizer tail (optimizer.py:7-47, trainers/base.py:372-385) as one fused pass.
+// All are one-pass, 16-byte vectorised, one warp per row where rows are independent; roofline = HBM bytes.
+#include <math.h>
+
+#include "cx_host.h"
+#include "cx_ptx.cuh"
+
+namespace cx {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+struct BF8 {  // 8 bf16 = 16 bytes
+  uint4 raw;
+  __device__ __forceinline__ void unpack(float (&f)[8]) const {
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = __low2float(p[i]);
+      f[2 * i + 1] = __high2float(p[i]);
+    }
+  }
+  __device__ __forceinline__ void pack(const float (&f)[8]) {
+    raw.x = pack_bf16x2(f[0], f[1]);
+    raw.y = pack_bf16x2(f[2], f[3]);
+    raw.z = pack_bf16x2(f[4], f[5]);
+    raw.w = pack_bf16x2(f[6], f[7]);
+  }
+};
+
+constexpr int kLnMaxVec = 4;  // up to d = 32 lanes * 8 * 4 = 1024 columns per row
+
+// ---------------------------------------------------------------------------------------------- LayerNorm forward
+// z = a (+ b) ; y = (z - mean) * rstd * gamma + beta.  EMBED: a-row = word_emb[ids[r]] + type_emb[type_ids[r]].
+template <bool EMBED>
+__global__ void add_layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                         const int64_t* __restrict__ ids, const int64_t* __restrict__ type_ids,
+                                         const __nv_bfloat16* __restrict__ type_emb, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                                         float* __restrict__ stats, int rows, int d, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const __nv_bfloat16* ar = EMBED ? a + (size_t)ids[row] * d : a + (size_t)row * d;
+  const __nv_bfloat16* br = EMBED ? type_emb + (size_t)(type_ids ? type_ids[row] : 0) * d : (b ? b + (size_t)row * d : nullptr);
+  float z[kLnMaxVec][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < kLnMaxVec; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    if (col < d) {
+      BF8 va, vb;
+      va.raw = *reinterpret_cast<const uint4*>(ar + col);
+      va.unpack(z[c]);
+      if (br != nullptr) {
+        float t[8];
+        vb.raw = *reinterpret_cast<const uint4*>(br + col);
+        vb.unpack(t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z[c][i] += t[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sum += z[c][i];
+    }
+  }
+  const float mean = warp_sum(sum) / d;
+  float var = 0.f;
+#pragma unroll
+  for (int c = 0; c < kLnMaxVec; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    if (col < d) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float t = z[c][i] - mean;
+        var = fmaf(t, t, var);
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(var) / d + eps);
+  if (lane == 0 && stats != nullptr) {
+    stats[2 * (size_t)row] = mean;
+    stats[2 * (size_t)row + 1] = rstd;
+  }
+#pragma unroll
+  for (int c = 0; c < kLnMaxVec; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    if (col < d) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float v = (z[c][i] - mean) * rstd;
+        if (gamma != nullptr) v = fmaf(v, gamma[col + i], beta[col + i]);
+        o[i] = v;
+      }
+      BF8 vo;
+      vo.pack(o);
+      *reinterpret_cast<uint4*>(y + (size_t)row * d + col) = vo.raw;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- LayerNorm backward
+// g = g1 (+ g2); dz = rstd * (g*gamma - mean_d(g*gamma) - xhat * mean_d(g*gamma*xhat)); per-CTA dgamma/dbeta partials.
+// EMBED: z is recomputed from the embedding tables and dz is scattered (atomicAdd fp32) into the table gradients.
+template <bool EMBED>
+__global__ void add_layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                         const int64_t* __restrict__ ids, const int64_t* __restrict__ type_ids,
+                                         const __nv_bfloat16* __restrict__ type_emb, const __nv_bfloat16* __restrict__ g1,
+                                         const __nv_bfloat16* __restrict__ g2, const float* __restrict__ gamma,
+                                         const float* __restrict__ stats, __nv_bfloat16* __restrict__ dz,
+                                         float* __restrict__ dword, float* __restrict__ dtype_emb,
+                                         float* __restrict__ partials, int rows, int d, int64_t padding_idx) {
+  extern __shared__ float sh[];  // [warps][2][d]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  float dg[kLnMaxVec][8], db[kLnMaxVec][8];
+#pragma unroll
+  for (int c = 0; c < kLnMaxVec; ++c)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dg[c][i] = db[c][i] = 0.f;
+
+  for (int row = blockIdx.x * nwarps + warp; row < rows; row += gridDim.x * nwarps) {
+    const __nv_bfloat16* ar = EMBED ? a + (size_t)ids[row] * d : a + (size_t)row * d;
+    const int64_t tid = EMBED ? (type_ids ? type_ids[row] : 0) : 0;
+    const __nv_bfloat16* br = EMBED ? type_emb + (size_t)tid * d : (b ? b + (size_t)row * d : nullptr);
+    const float mean = stats[2 * (size_t)row], rstd = stats[2 * (size_t)row + 1];
+    float xh[kLnMaxVec][8], wg[kLnMaxVec][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < kLnMaxVec; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < d) {
+        BF8 v;
+        float z[8], t[8], g[8];
+        v.raw = *reinterpret_cast<const uint4*>(ar + col);
+        v.unpack(z);
+        if (br != nullptr) {
+          v.raw = *reinterpret_cast<const uint4*>(br + col);
+          v.unpack(t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) z[i] += t[i];
+        }
+        v.raw = *reinterpret_cast<const uint4*>(g1 + (size_t)row * d + col);
+        v.unpack(g);
+        if (g2 != nullptr) {
+          v.raw = *reinterpret_cast<const uint4*>(g2 + (size_t)row * d + col);
+          v.unpack(t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] += t[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float x = (z[i] - mean) * rstd;
+          const float w = g[i] * (gamma != nullptr ? gamma[col + i] : 1.f);
+          xh[c][i] = x;
+          wg[c][i] = w;
+          s1 += w;
+          s2 = fmaf(w, x, s2);
+          dg[c][i] = fmaf(g[i], x, dg[c][i]);
+          db[c][i] += g[i];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / d;
+    s2 = warp_sum(s2) / d;
+#pragma unroll
+    for (int c = 0; c < kLnMaxVec; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < d) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = (wg[c][i] - s1 - xh[c][i] * s2) * rstd;
+        if (EMBED) {
+          float* dw = dword + (size_t)ids[row] * d + col;
+          float* dt = dtype_emb + (size_t)tid * d + col;
+          const bool pad = ids[row] == padding_idx;  // nn.Embedding(padding_idx=...) never receives a gradient there
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (!pad) atomicAdd(dw + i, o[i]);
+            atomicAdd(dt + i, o[i]);
+          }
+        } else {
+          BF8 vo;
+          vo.pack(o);
+          *reinterpret_cast<uint4*>(dz + (size_t)row * d + col) = vo.raw;
+        }
+      }
+    }
+  }
+  if (partials == nullptr) return;
+  // CTA reduction of dgamma/dbeta partials (fixed order => deterministic)
+#pragma unroll
+  for (int c = 0; c < kLnMaxVec; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    if (col < d) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sh[(warp * 2 + 0) * d + col + i] = dg[c][i];
+        sh[(warp * 2 + 1) * d + col + i] = db[c][i];
+      }
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < 2 * d; j += blockDim.x) {
+    const int which = j / d, col = j % d;
+    float acc = 0.f;
+    for (int w = 0; w < nwarps; ++w) acc += sh[(w * 2 + which) * d + col];
+    partials[(size_t)blockIdx.x * 2 * d + j] = acc;
+  }
+}
+
+__global__ void ln_param_grad_reduce_kernel(const float* __restrict__ partials, int nblocks, int d, float* __restrict__ dgamma,
+                                            float* __restrict__ dbeta) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= 2 * d) return;
+  float acc = 0.f;
+  for (int b = 0; b < nblocks; ++b) acc += partials[(size_t)b * 2 * d + j];
+  if (j < d) dgamma[j] += acc;
+  else dbeta[j - d] += acc;
+}
+
+// ---------------------------------------------------------------------------------------------- token bookkeeping
+// pos[t] = t - cu_seqlens[seq(t)]  for packed (unpadded) tokens
+__global__ void token_positions_kernel(const int* __restrict__ cu, int nseq, int* __restrict__ pos, int* __restrict__ seq_id) {
+  const int s = blockIdx.x;
+  if (s >= nseq) return;
+  const int b = cu[s], e = cu[s + 1];
+  for (int t = b + threadIdx.x; t < e; t += blockDim.x) {
+    pos[t] = t - b;
+    if (seq_id != nullptr) seq_id[t] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- RoPE (NeoX halves)
+// In place on q and k of qkv [T, 3, H, Dh]: (x1, x2) -> (x1 c - x2 s, x2 c + x1 s); dir = -1 applies the transpose
+// (the backward).  cos/sin tables are fp32 [max_pos, Dh/2].
+__global__ void rope_kernel(__nv_bfloat16* __restrict__ qkv, const int* __restrict__ pos, const float* __restrict__ cos_t,
+                            const float* __restrict__ sin_t, int T, int H, int Dh, float dir, int first_slot, int num_slots) {
+  const int half = Dh / 2;
+  const int per_tok = num_slots * H * (half / 8);  // 8 (x1, x2) pairs per thread
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)T * per_tok) return;
+  const int t = (int)(i / per_tok);
+  int r = (int)(i % per_tok);
+  const int which = first_slot + r / (H * (half / 8));
+  r %= H * (half / 8);
+  const int h = r / (half / 8), j0 = (r % (half / 8)) * 8;
+  __nv_bfloat16* base = qkv + ((size_t)t * 3 + which) * H * Dh + (size_t)h * Dh;
+  const float* c = cos_t + (size_t)pos[t] * half + j0;
+  const float* s = sin_t + (size_t)pos[t] * half + j0;
+  BF8 v1, v2;
+  float x1[8], x2[8], o1[8], o2[8];
+  v1.raw = *reinterpret_cast<const uint4*>(base + j0);
+  v2.raw = *reinterpret_cast<const uint4*>(base + half + j0);
+  v1.unpack(x1);
+  v2.unpack(x2);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float cs = c[k], sn = s[k] * dir;
+    o1[k] = x1[k] * cs - x2[k] * sn;
+    o2[k] = x2[k] * cs + x1[k] * sn;
+  }
+  v1.pack(o1);
+  v2.pack(o2);
+  *reinterpret_cast<uint4*>(base + j0) = v1.raw;
+  *reinterpret_cast<uint4*>(base + half + j0) = v2.raw;
+}
+
+// fp32 dq accumulator [T, H*Dh] -> bf16 into dqkv's q slot, with the RoPE transpose fused (attention backward tail)
+__global__ void dq_finalize_rope_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dqkv,
+                                        const int* __restrict__ pos, const float* __restrict__ cos_t,
+                                        const float* __restrict__ sin_t, int T, int H, int Dh) {
+  const int half = Dh / 2;
+  const int per_tok = H * (half / 8);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)T * per_tok) return;
+  const int t = (int)(i / per_tok);
+  const int r = (int)(i % per_tok);
+  const int h = r / (half / 8), j0 = (r % (half / 8)) * 8;
+  const float* src = dq_acc + ((size_t)t * H + h) * Dh;
+  const float* c = cos_t + (size_t)pos[t] * half + j0;
+  const float* s = sin_t + (size_t)pos[t] * half + j0;
+  float o1[8], o2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float x1 = src[j0 + k], x2 = src[half + j0 + k];
+    o1[k] = x1 * c[k] + x2 * s[k];
+    o2[k] = x2 * c[k] - x1 * s[k];
+  }
+  BF8 v1, v2;
+  v1.pack(o1);
+  v2.pack(o2);
+  __nv_bfloat16* dst = dqkv + ((size_t)t * 3) * H * Dh + (size_t)h * Dh;
+  *reinterpret_cast<uint4*>(dst + j0) = v1.raw;
+  *reinterpret_cast<uint4*>(dst + half + j0) = v2.raw;
+}
+
+// ---------------------------------------------------------------------------------------------- SwiGLU
+// yg [T, 2I] = [y | gate];  out = y * silu(gate)   (mlp.py:68-75: fc11 -> y, fc12 -> gate)
+__global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ yg, __nv_bfloat16* __restrict__ out, int64_t T, int I) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_row = I / 8;
+  if (i >= T * per_row) return;
+  const int64_t t = i / per_row;
+  const int c = (int)(i % per_row) * 8;
+  BF8 vy, vg, vo;
+  float y[8], g[8], o[8];
+  vy.raw = *reinterpret_cast<const uint4*>(yg + t * 2 * I + c);
+  vg.raw = *reinterpret_cast<const uint4*>(yg + t * 2 * I + I + c);
+  vy.unpack(y);
+  vg.unpack(g);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) o[k] = y[k] * g[k] / (1.f + __expf(-g[k]));
+  vo.pack(o);
+  *reinterpret_cast<uint4*>(out + t * I + c) = vo.raw;
+}
+
+__global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ yg,
+                                  __nv_bfloat16* __restrict__ dyg, int64_t T, int I) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_row = I / 8;
+  if (i >= T * per_row) return;
+  const int64_t t = i / per_row;
+  const int c = (int)(i % per_row) * 8;
+  BF8 vy, vg, vd, o1, o2;
+  float y[8], g[8], d[8], dy[8], dg[8];
+  vy.raw = *reinterpret_cast<const uint4*>(yg + t * 2 * I + c);
+  vg.raw = *reinterpret_cast<const uint4*>(yg + t * 2 * I + I + c);
+  vd.raw = *reinterpret_cast<const uint4*>(dout + t * I + c);
+  vy.unpack(y);
+  vg.unpack(g);
+  vd.unpack(d);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float sg = 1.f / (1.f + __expf(-g[k]));
+    const float silu = g[k] * sg;
+    dy[k] = d[k] * silu;
+    dg[k] = d[k] * y[k] * (sg * (1.f + g[k] * (1.f - sg)));
+  }
+  o1.pack(dy);
+  o2.pack(dg);
+  *reinterpret_cast<uint4*>(dyg + t * 2 * I + c) = o1.raw;
+  *reinterpret_cast<uint4*>(dyg + t * 2 * I + I + c) = o2.raw;
+}
+
+// ---------------------------------------------------------------------------------------------- pooling + head
+// pooled[s, :] = mean over the tokens of sequence s (packed rows), fp32.  One CTA per (sequence, 256-column slab).
+__global__ void mean_pool_fwd_kernel(const __nv_bfloat16* __restrict__ h, const int* __restrict__ cu, float* __restrict__ pooled,
+                                     int d) {
+  const int s = blockIdx.x;
+  const int col = (blockIdx.y * 32 + (threadIdx.x & 31)) * 8;
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int b = cu[s], e = cu[s + 1];
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (col < d) {
+    for (int t = b + warp; t < e; t += nwarps) {
+      BF8 v;
+      float f[8];
+      v.raw = *reinterpret_cast<const uint4*>(h + (size_t)t * d + col);
+      v.unpack(f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += f[k];
+    }
+  }
+  __shared__ float sh[8][32][8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sh[warp][threadIdx.x & 31][k] = acc[k];
+  __syncthreads();
+  if (warp == 0 && col < d) {
+    const float inv = 1.f / (float)max(e - b, 1);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float a = 0.f;
+      for (int w = 0; w < nwarps; ++w) a += sh[w][threadIdx.x][k];
+      pooled[(size_t)s * d + col + k] = a * inv;
+    }
+  }
+}
+
+// dh[t, :] = dpooled[seq(t), :] / len(seq(t))   (bf16)
+__global__ void mean_pool_bwd_kernel(const float* __restrict__ dpooled, const int* __restrict__ cu, __nv_bfloat16* __restrict__ dh,
+                                     int d) {
+  const int s = blockIdx.x;
+  const int b = cu[s], e = cu[s + 1];
+  const float inv = 1.f / (float)max(e - b, 1);
+  const int per_row = d / 8;
+  for (int64_t i = threadIdx.x; i < (int64_t)(e - b) * per_row; i += blockDim.x) {
+    const int t = b + (int)(i / per_row), c = (int)(i % per_row) * 8;
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = dpooled[(size_t)s * d + c + k] * inv;
+    BF8 v;
+    v.pack(o);
+    *reinterpret_cast<uint4*>(dh + (size_t)t * d + c) = v.raw;
+  }
+}
+
+// BiEncoder tail on [B, d] (modeling_biencoder.py:307-317): optional affine-free LayerNorm ("hamming"), cast to the trunk
+// dtype (bf16), optional F.normalize; fp32 output.  One warp per row.  Saves (mean, rstd, inv_norm) for the backward.
+__global__ void embed_head_fwd_kernel(const float* __restrict__ pooled, float* __restrict__ out, float* __restrict__ save,
+                                      int rows, int d, int hamming, int normalize) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* x = pooled + (size_t)row * d;
+  float mean = 0.f, rstd = 1.f;
+  if (hamming) {
+    float s = 0.f;
+    for (int j = lane; j < d; j += 32) s += x[j];
+    mean = warp_sum(s) / d;
+    float v = 0.f;
+    for (int j = lane; j < d; j += 32) v = fmaf(x[j] - mean, x[j] - mean, v);
+    rstd = rsqrtf(warp_sum(v) / d + 1e-5f);
+  }
+  float ss = 0.f;
+  for (int j = lane; j < d; j += 32) {
+    const float r = __bfloat162float(__float2bfloat16_rn((x[j] - mean) * rstd));
+    ss = fmaf(r, r, ss);
+  }
+  const float inv = normalize ? 1.f / fmaxf(sqrtf(warp_sum(ss)), 1e-12f) : 1.f;
+  for (int j = lane; j < d; j += 32) {
+    const float r = __bfloat162float(__float2bfloat16_rn((x[j] - mean) * rstd));
+    out[(size_t)row * d + j] = r * inv;
+  }
+  if (lane == 0) {
+    save[3 * (size_t)row] = mean;
+    save[3 * (size_t)row + 1] = rstd;
+    save[3 * (size_t)row + 2] = inv;
+  }
+}
+
+__global__ void embed_head_bwd_kernel(const float* __restrict__ pooled, const float* __restrict__ gout, const float* __restrict__ save,
+                                      float* __restrict__ gpooled, int rows, int d, int hamming, int normalize) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* x = pooled + (size_t)row * d;
+  const float* g = gout + (size_t)row * d;
+  const float mean = save[3 * (size_t)row], rstd = save[3 * (size_t)row + 1], inv = save[3 * (size_t)row + 2];
+  // through F.normalize: gr = inv * (g - y (g.y)), y = r * inv  (the bf16 cast is treated as identity, as autograd does)
+  float dot = 0.f;
+  if (normalize)
+    for (int j = lane; j < d; j += 32) {
+      const float r = __bfloat162float(__float2bfloat16_rn((x[j] - mean) * rstd));
+      dot = fmaf(g[j], r * inv, dot);
+    }
+  dot = warp_sum(dot);
+  float s1 = 0.f, s2 = 0.f;
+  if (hamming)
+    for (int j = lane; j < d; j += 32) {
+      const float r = __bfloat162float(__float2bfloat16_rn((x[j] - mean) * rstd));
+      const float gr = normalize ? inv * (g[j] - r * inv * dot) : g[j];
+      const float xh = (x[j] - mean) * rstd;
+      s1 += gr;
+      s2 = fmaf(gr, xh, s2);
+    }
+  s1 = warp_sum(s1) / d;
+  s2 = warp_sum(s2) / d;
+  for (int j = lane; j < d; j += 32) {
+    const float r = __bfloat162float(__float2bfloat16_rn((x[j] - mean) * rstd));
+    const float gr = normalize ? inv * (g[j] - r * inv * dot) : g[j];
+    float o = gr;
+    if (hamming) o = (gr - s1 - (x[j] - mean) * rstd * s2) * rstd;
+    gpooled[(size_t)row * d + j] = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- optimizer tail
+__global__ void sumsq_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ partial) {
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i * 4 < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i * 4 + 4 <= n) {
+      const float4 v = *reinterpret_cast<const float4*>(x + i * 4);
+      acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    } else {
+      for (int64_t j = i * 4; j < n; ++j) acc = fmaf(x[j], x[j], acc);
+    }
+  }
+  acc = warp_sum(acc);
+  __shared__ float sh[32];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += sh[w];
+    partial[blockIdx.x] = a;
+  }
+}
+// out[0] = ||g||, out[1] = clip coefficient = min(1, max_norm / (||g|| + 1e-6))   (torch.nn.utils.clip_grad_norm_)
+__global__ void clip_coef_kernel(const float* __restrict__ partial, int n, float max_norm, float* __restrict__ out) {
+  float a = 0.f;
+  for (int i = threadIdx.x; i < n; i += 32) a += partial[i];
+  a = warp_sum(a);
+  if (threadIdx.x == 0) {
+    const float norm = sqrtf(a);
+    out[0] = norm;
+    out[1] = max_norm > 0.f ? fminf(1.f, max_norm / (norm + 1e-6f)) : 1.f;
+  }
+}
+
+// AdamW (decoupled decay, torch.optim.AdamW semantics) over a flat fp32 master buffer; also refreshes the bf16 shadow
+// the GEMMs read and zeroes the gradient.  grad_scale_dev: optional device scalar (the clip coefficient).
+__global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                             __nv_bfloat16* __restrict__ shadow, int64_t n, float lr, float beta1, float beta2, float eps,
+                             float wd, float bc1, float bc2, const float* __restrict__ grad_scale_dev, float grad_scale,
+                             int zero_grad) {
+  const float gs = grad_scale * (grad_scale_dev != nullptr ? grad_scale_dev[0] : 1.f);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gs;
+    float pi = p[i];
+    pi *= (1.f - lr * wd);
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+    pi -= (lr / bc1) * (mi / denom);
+    p[i] = pi;
+    if (shadow != nullptr) shadow[i] = __float2bfloat16_rn(pi);
+    if (zero_grad) g[i] = 0.f;
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i * 4 < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i * 4 + 4 <= n) {
+      const float4 v = *reinterpret_cast<const float4*>(x + i * 4);
+      uint2 o;
+      o.x = pack_bf16x2(v.x, v.y);
+      o.y = pack_bf16x2(v.z, v.w);
+      *reinterpret_cast<uint2*>(y + i * 4) = o;
+    } else {
+      for (int64_t j = i * 4; j < n; ++j) y[j] = __float2bfloat16_rn(x[j]);
+    }
+  }
+}
+
+}  // namespace cx
+
+using namespace cx;
+#define STREAM static_cast<cudaStream_t>(stream)
+
+static int ln_rows_grid(int rows, int warps) { return (rows + warps - 1) / warps; }
+
+extern "C" int cx_add_layernorm_fwd(const void* a, const void* b, const float* gamma, const float* beta, void* y, float* stats,
+                                    int rows, int d, float eps, cx_stream_t stream) {
+  CX_REQUIRE(a && y, "cx_add_layernorm_fwd: null pointer");
+  CX_REQUIRE(d % 8 == 0 && d <= 256 * kLnMaxVec, "cx_add_layernorm_fwd: d must be a multiple of 8 and <= 1024");
+  if (rows <= 0) return 0;
+  add_layernorm_fwd_kernel<false><<<ln_rows_grid(rows, 8), 256, 0, STREAM>>>(
+      (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, nullptr, nullptr, nullptr, gamma, beta, (__nv_bfloat16*)y, stats, rows, d, eps);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cx_embed_layernorm_fwd(const int64_t* ids, const int64_t* type_ids, const void* word_emb, const void* type_emb,
+                                      const float* gamma, const float* beta, void* y, float* stats, int rows, int d, float eps,
+                                      cx_stream_t stream) {
+  CX_REQUIRE(ids && word_emb && type_emb && y, "cx_embed_layernorm_fwd: null pointer");
+  CX_REQUIRE(d % 8 == 0 && d <= 256 * kLnMaxVec, "cx_embed_layernorm_fwd: d must be a multiple of 8 and <= 1024");
+  if (rows <= 0) return 0;
+  add_layernorm_fwd_kernel<true><<<ln_rows_grid(rows, 8), 256, 0, STREAM>>>(
+      (const __nv_bfloat16*)word_emb, nullptr, ids, type_ids, (const __nv_bfloat16*)type_emb, gamma, beta, (__nv_bfloat16*)y,
+      stats, rows, d, eps);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+static int ln_bwd_grid(int rows) {
+  int g = (rows + 7) / 8;
+  const int cap = 2 * sm_count();
+  return g < cap ? (g < 1 ? 1 : g) : cap;
+}
+
+extern "C" size_t cx_layernorm_bwd_workspace_bytes(int d) { return (size_t)2 * sm_count() * 2 * d * sizeof(float); }
+
+extern "C" int cx_add_layernorm_bwd(const void* a, const void* b, const void* g1, const void* g2, const float* gamma,
+                                    const float* stats, void* dz, float* dgamma, float* dbeta, void* workspace, int rows, int d,
+                                    cx_stream_t stream) {
+  CX_REQUIRE(a && g1 && stats && dz, "cx_add_layernorm_bwd: null pointer");
+  CX_REQUIRE(d % 8 == 0 && d <= 256 * kLnMaxVec, "cx_add_layernorm_bwd: d must be a multiple of 8 and <= 1024");
+  CX_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "cx_add_layernorm_bwd: dgamma/dbeta go together");
+  CX_REQUIRE(dgamma == nullptr || workspace != nullptr, "cx_add_layernorm_bwd: workspace required for parameter grads");
+  if (rows <= 0) return 0;
+  const int grid = ln_bwd_grid(rows);
+  const size_t smem = (size_t)8 * 2 * d * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    CX_CUDA_CHECK(cudaFuncSetAttribute(add_layernorm_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4));
+    CX_CUDA_CHECK(cudaFuncSetAttribute(add_layernorm_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4));
+    configured = true;
+  }
+  add_layernorm_bwd_kernel<false><<<grid, 256, smem, STREAM>>>(
+      (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, nullptr, nullptr, nullptr, (const __nv_bfloat16*)g1,
+      (const __nv_bfloat16*)g2, gamma, stats, (__nv_bfloat16*)dz, nullptr, nullptr, dgamma ? (float*)workspace : nullptr, rows, d, -1);
+  CX_LAUNCH_CHECK();
+  if (dgamma) {
+    ln_param_grad_reduce_kernel<<<(2 * d + 255) / 256, 256, 0, STREAM>>>((const float*)workspace, grid, d, dgamma, dbeta);
+    CX_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int cx_embed_layernorm_bwd(const int64_t* ids, const int64_t* type_ids, const void* word_emb, const void* type_emb,
+                                      const void* g1, const void* g2, const float* gamma, const float* stats, float* dword,
+                                      float* dtype_emb, float* dgamma, float* dbeta, void* workspace, int rows, int d,
+                                      int64_t padding_idx, cx_stream_t stream) {
+  CX_REQUIRE(ids && word_emb && type_emb && g1 && stats && dword && dtype_emb && dgamma && dbeta && workspace,
+             "cx_embed_layernorm_bwd: null pointer");
+  CX_REQUIRE(d % 8 == 0 && d <= 256 * kLnMaxVec, "cx_embed_layernorm_bwd: d must be a multiple of 8 and <= 1024");
+  if (rows <= 0) return 0;
+  const int grid = ln_bwd_grid(rows);
+  const size_t smem = (size_t)8 * 2 * d * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    CX_CUDA_CHECK(cudaFuncSetAttribute(add_layernorm_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4));
+    configured = true;
+  }
+  add_layernorm_bwd_kernel<true><<<grid, 256, smem, STREAM>>>(
+      (const __nv_bfloat16*)word_emb, nullptr, ids, type_ids, (const __nv_bfloat16*)type_emb, (const __nv_bfloat16*)g1,
+      (const __nv_bfloat16*)g2, gamma, stats, nullptr, dword, dtype_emb, (float*)workspace, rows, d, padding_idx);
+  CX_LAUNCH_CHECK();
+  ln_param_grad_reduce_kernel<<<(2 * d + 255) / 256, 256, 0, STREAM>>>((const float*)workspace, grid, d, dgamma, dbeta);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cx_token_positions(const int32_t* cu_seqlens, int nseq, int32_t* pos, int32_t* seq_id, cx_stream_t stream) {
+  CX_REQUIRE(cu_seqlens && pos, "cx_token_positions: null pointer");
+  if (nseq <= 0) return 0;
+  token_positions_kernel<<<nseq, 128, 0, STREAM>>>(cu_seqlens, nseq, pos, seq_id);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cx_rope_inplace(void* qkv, const int32_t* pos, const float* cos_t, const float* sin_t, int T, int H, int Dh,
+                               int backward, int first_slot, int num_slots, cx_stream_t stream) {
+  CX_REQUIRE(qkv && pos && cos_t && sin_t, "cx_rope_inplace: null pointer");
+  CX_REQUIRE(Dh % 16 == 0, "cx_rope_inplace: head dim must be a multiple of 16");
+  if (T <= 0) return 0;
+  CX_REQUIRE(first_slot >= 0 && num_slots >= 1 && first_slot + num_slots <= 2, "cx_rope_inplace: slots are q (0) and k (1)");
+  const int64_t n = (int64_t)T * num_slots * H * (Dh / 16);
+  rope_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>((__nv_bfloat16*)qkv, pos, cos_t, sin_t, T, H, Dh, backward ? -1.f : 1.f,
+                                                               first_slot, num_slots);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cx_dq_finalize_rope(const float* dq_acc, void* dqkv, const int32_t* pos, const float* cos_t, const float* sin_t,
+                                   int T, int H, int Dh, cx_stream_t stream) {
+  CX_REQUIRE(dq_acc && dqkv && pos && cos_t && sin_t, "cx_dq_finalize_rope: null pointer");
+  CX_REQUIRE(Dh % 16 == 0, "cx_dq_finalize_rope: head dim must be a multiple of 16");
+  if (T <= 0) return 0;
+  const int64_t n = (int64_t)T * H * (Dh / 16);
+  dq_finalize_rope_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>(dq_acc, (__nv_bfloat16*)dqkv, pos, cos_t, sin_t, T, H, Dh);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cx_swiglu_fwd(const void* yg, void* out, int64_t T, int I, cx_stream_t stream) {
+  CX_REQUIRE(yg && out, "cx_swiglu_fwd: null pointer");
+  CX_REQUIRE(I % 8 == 0, "cx_swiglu_fwd: inner dim must be a multiple of 8");
+  if (T <= 0) return 0;
+  const int64_t n = T * (I / 8);
+  swiglu_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>((const __nv_bfloat16*)yg, (__nv_bfloat16*)out, T, I);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cx_swiglu_bwd(const void* dout, const void* yg, void* dyg, int64_t T, int I, cx_stream_t stream) {
+  CX_REQUIRE(dout && yg && dyg, "cx_swiglu_bwd: null pointer");
+  CX_REQUIRE(I % 8 == 0, "cx_swiglu_bwd: inner dim must be a multiple of 8");
+  if (T <= 0) return 0;
+  const int64_t n = T * (I / 8);
+  swiglu_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)yg,
+                                                                     (__nv_bfloat16*)dyg, T, I);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cx_mean_pool_fwd(const void* h, const int32_t* cu_seqlens, float* pooled, int nseq, int d, cx_stream_t stream) {
+  CX_REQUIRE(h && cu_seqlens && pooled, "cx_mean_pool_fwd: null pointer");
+  CX_REQUIRE(d % 8 == 0, "cx_mean_pool_fwd: d must be a multiple of 8");
+  if (nseq <= 0) return 0;
+  dim3 grid(nseq, (d + 255) / 256);
+  mean_pool_fwd_kernel<<<grid, 256, 0, STREAM>>>((const __nv_bfloat16*)h, cu_seqlens, pooled, d);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cx_mean_pool_bwd(const float* dpooled, const int32_t* cu_seqlens, void* dh, int nseq, int d, cx_stream_t stream) {
+  CX_REQUIRE(dpooled && cu_seqlens && dh, "cx_mean_pool_bwd: null pointer");
+  CX_REQUIRE(d % 8 == 0, "cx_mean_pool_bwd: d must be a multiple of 8");
+  if (nseq <= 0) return 0;
+  mean_pool_bwd_kernel<<<nseq, 256, 0, STREAM>>>(dpooled, cu_seqlens, (__nv_bfloat16*)dh, d);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cx_embed_head_fwd(const float* pooled, float* out, float* save, int rows, int d, int hamming, int normalize,
+                                 cx_stream_t stream) {
+  CX_REQUIRE(pooled && out && save, "cx_embed_head_fwd: null pointer");
+  if (rows <= 0) return 0;
+  embed_head_fwd_kernel<<<(rows + 7) / 8, 256, 0, STREAM>>>(pooled, out, save, rows, d, hamming, normalize);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cx_embed_head_bwd(const float* pooled, const float* gout, const float* save, float* gpooled, int rows, int d,
+                                 int hamming, int normalize, cx_stream_t stream) {
+  CX_REQUIRE(pooled && gout && save && gpooled, "cx_embed_head_bwd: null pointer");
+  if (rows <= 0) return 0;
+  embed_head_bwd_kernel<<<(rows + 7) / 8, 256, 0, STREAM>>>(pooled, gout, save, gpooled, rows, d, hamming, normalize);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cx_grad_clip_coef(const float* grad, int64_t n, float max_norm, float* out2, void* workspace, cx_stream_t stream) {
+  CX_REQUIRE(grad && out2 && workspace, "cx_grad_clip_coef: null pointer");
+  const int blocks = 4 * sm_count();
+  sumsq_kernel<<<blocks, 256, 0, STREAM>>>(grad, n, (float*)workspace);
+  CX_LAUNCH_CHECK();
+  clip_coef_kernel<<<1, 32, 0, STREAM>>>((const float*)workspace, blocks, max_norm, out2);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" size_t cx_grad_clip_workspace_bytes(void) { return (size_t)4 * sm_count() * sizeof(float); }
+
+extern "C" int cx_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, int64_t n, float lr,
+                             float beta1, float beta2, float eps, float weight_decay, int step, const float* grad_scale_dev,
+                             float grad_scale, int zero_grad, cx_stream_t stream) {
+  CX_REQUIRE(param && grad && exp_avg && exp_avg_sq, "cx_adamw_step: null pointer");
+  CX_REQUIRE(step >= 1, "cx_adamw_step: step counts from 1");
+  if (n <= 0) return 0;
+  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  adamw_kernel<<<8 * sm_count(), 256, 0, STREAM>>>(param, grad, exp_avg, exp_avg_sq, (__nv_bfloat16*)shadow_bf16, n, lr, beta1, beta2,
+                                                  eps, weight_decay, bc1, bc2, grad_scale_dev, grad_scale, zero_grad);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cx_cast_f32_bf16(const float* x, void* y, int64_t n, cx_stream_t stream) {
+  CX_REQUIRE(x && y, "cx_cast_f32_bf16: null pointer");
+  if (n <= 0) return 0;
+  cast_f32_bf16_kernel<<<8 * sm_count(), 256, 0, STREAM>>>(x, (__nv_bfloat16*)y, n);
+  CX_LAUNCH_CHECK();
+  return 0;
+}

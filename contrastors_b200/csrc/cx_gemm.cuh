@@ -3,8 +3,8 @@
 //   C[M,N] = A (x) B,  bf16 operands via TMA (128B swizzle), fp32 accumulators in TMEM (double-buffered),
 //   one CTA per SM looping over 128 x BLOCK_N output tiles.
 //
-// Warp roles (256 threads):  warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
-//                            warps 4..7 = epilogue (thread t <-> accumulator row t of the tile).
+// Warp roles (384 threads):  warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
+//                            warps 4..11 = epilogue: warp w owns TMEM lanes 32*(w%4).. (rows) and column half (w-4)/4.
 // Pipelines: smem ring full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).
 //
 // Operand layouts (CX_MAJOR_K / CX_MAJOR_MN, see include/contrastors_b200.h):
@@ -27,7 +27,8 @@ enum EpiMode { EPI_STORE = 0, EPI_NCE_STATS = 1, EPI_NCE_DS = 2 };
 
 struct EpiParams {
   float alpha = 1.f;
-  const float* alpha_dev = nullptr;  // optional device scalar multiplied into alpha (keeps the host sync-free)
+  const float* alpha_dev = nullptr;  // optional device scalars multiplied into alpha (keep the host sync-free)
+  const float* alpha_dev2 = nullptr;
   // InfoNCE
   float scale = 1.f;
   const float* scale_dev = nullptr;  // optional device scalar multiplied into scale
@@ -38,17 +39,19 @@ struct EpiParams {
   int label_stride = 1;
   const float* lse = nullptr;
   float coef = 0.f;
-  float* part_max = nullptr;   // [n_col_tiles][M]
-  float* part_sum = nullptr;   // [n_col_tiles][M]
-  int* part_arg = nullptr;     // [n_col_tiles][M]
+  float* part_max = nullptr;   // [2 * n_col_tiles][M]  (one partial per column half of each tile, log2 domain)
+  float* part_sum = nullptr;   // [2 * n_col_tiles][M]
+  int* part_arg = nullptr;     // [2 * n_col_tiles][M]
   float* label_logit = nullptr;  // [M]
-  float* dlogit_part = nullptr;  // [gridDim.x * 128]
+  float* dlogit_part = nullptr;  // [gridDim.x]
+  int ab_f16 = 0;  // A and B operands hold IEEE fp16 instead of bf16 (kind::f16 wants one input type): fp16 dS path
+  int ds_f16 = 0;  // EPI_NCE_DS: store (softmax - onehot) UNSCALED as fp16 (11-bit mantissa) instead of coef*(...) as bf16
 };
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;  // 4 control warps + 8 epilogue warps (2 per SMSP: TLP hides TMEM-load latency)
 constexpr int kStageCBytes = 16384;  // 128 rows x 128 B
 
 template <int BLOCK_N>
@@ -99,7 +102,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], 256);
     }
     fence_barrier_init();
   }
@@ -146,7 +149,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (single thread)
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+      // a_format [7,10) / b_format [10,13): 1 = bf16, 0 = f16
+      const uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, A_MN ? 1u : 0u, B_MN ? 1u : 0u) & ~(ep.ab_f16 ? ((1u << 7) | (1u << 10)) : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -181,142 +185,200 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue (128 threads)
-    const int ew = warp - 4;            // == warp % 4: TMEM lane quarter this warp may access
+    // ------------------------------------------------------------ epilogue (2 x 128 threads, one group per column half)
+    constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+    constexpr int HALF_N = BLOCK_N / 2;
+    constexpr int NC = HALF_N / 32;
+    const int ew = warp & 3;            // TMEM lane quarter this warp may access
+    const int hf = (warp - 4) >> 2;     // column half handled by this warp group
     const int row_in_tile = ew * 32 + lane;
-    const int etid = threadIdx.x - 128;
+    const int etid = (threadIdx.x - 128) & 127;  // thread index within the half's group
+    uint8_t* const stage_c = smem_c + hf * kStageCBytes;  // one staging buffer per half
     int it = 0;
-    int cbuf = 0;
-    float dlogit_acc = 0.f;
+    float dl0 = 0.f, dl1 = 0.f, dl2 = 0.f, dl3 = 0.f;  // sum p*t (log2 domain) for the logit-scale gradient
     const float ep_scale = ep.scale * (ep.scale_dev != nullptr ? *ep.scale_dev : 1.f);
     const float ep_coef = ep.coef * (ep.coef_dev != nullptr ? *ep.coef_dev : 1.f);
-    const float ep_alpha = ep.alpha * (ep.alpha_dev != nullptr ? *ep.alpha_dev : 1.f);
+    const float ep_alpha = ep.alpha * (ep.alpha_dev != nullptr ? *ep.alpha_dev : 1.f) * (ep.alpha_dev2 != nullptr ? *ep.alpha_dev2 : 1.f);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int mn = tile / splits;
       const int mt = mn / n_tiles, nt = mn % n_tiles;
-      const int m0 = mt * kBlockM, n0 = nt * BLOCK_N;
+      const int m0 = mt * kBlockM, n0 = nt * BLOCK_N + hf * HALF_N;
       const int row = m0 + row_in_tile;
       const bool row_ok = row < M;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N;
+      // fast path: no column masks and no per-column scale anywhere in this tile
+      const bool plain = (n0 + HALF_N <= N) && ep.rd == nullptr;
 
-      // per-row InfoNCE state
-      float rscale = 1.f, row_lse = 0.f;
+      // per-row InfoNCE state, in the log2 domain: t = s * log2(e)
+      float rs2 = 1.f, lse2 = 0.f, rowf = 1.f;
       int label = -1;
       float run_max = -INFINITY, run_sum = 0.f;
       int run_arg = 0;
       if (MODE != EPI_STORE) {
-        rscale = ep_scale * ((ep.rq != nullptr && row_ok) ? ep.rq[row] : 1.f);
+        const float rqi = (ep.rq != nullptr && row_ok) ? ep.rq[row] : 1.f;
+        rs2 = ep_scale * rqi * kLog2e;
         label = (row + ep.label_offset) * ep.label_stride;
-        if (MODE == EPI_NCE_DS) row_lse = row_ok ? ep.lse[row] : 0.f;
+        if (MODE == EPI_NCE_DS) {
+          lse2 = row_ok ? ep.lse[row] * kLog2e : INFINITY;  // +inf => p == 0 for rows past M
+          rowf = ep.ds_f16 ? 1.f : ep_coef * rqi;           // bf16 path stores coef * p * rq_i * rd_j
+        }
       }
 
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N + hf * HALF_N;
+
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
+      for (int c = 0; c < NC; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + c * 32, v);
         tmem_ld_wait();
         const int col0 = n0 + c * 32;
 
         if (MODE == EPI_NCE_STATS) {
-          float s[32];
-          float cmax = -INFINITY;
+          float t[32];
+          if (plain) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = col0 + j;
-            float x = __uint_as_float(v[j]) * rscale;
-            if (ep.rd != nullptr) x *= (col < N ? ep.rd[col] : 0.f);
-            x = (col < N) ? x : -INFINITY;
-            s[j] = x;
-            cmax = fmaxf(cmax, x);
+            for (int j = 0; j < 32; ++j) t[j] = __uint_as_float(v[j]) * rs2;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = col0 + j;
+              const float r = (ep.rd != nullptr) ? rs2 * (col < N ? ep.rd[col] : 0.f) : rs2;
+              t[j] = (col < N) ? __uint_as_float(v[j]) * r : -INFINITY;
+            }
           }
+          float m0_ = t[0], m1_ = t[1], m2_ = t[2], m3_ = t[3];
+#pragma unroll
+          for (int j = 4; j < 32; j += 4) {
+            m0_ = fmaxf(m0_, t[j]);
+            m1_ = fmaxf(m1_, t[j + 1]);
+            m2_ = fmaxf(m2_, t[j + 2]);
+            m3_ = fmaxf(m3_, t[j + 3]);
+          }
+          const float cmax = fmaxf(fmaxf(m0_, m1_), fmaxf(m2_, m3_));
           if (cmax > run_max) {  // first max wins: only a strictly larger value moves the argmax
             int arg = 0;
 #pragma unroll
-            for (int j = 31; j >= 0; --j) arg = (s[j] == cmax) ? j : arg;
+            for (int j = 31; j >= 0; --j) arg = (t[j] == cmax) ? j : arg;
             run_arg = col0 + arg;
-            run_sum *= exp2f((run_max - cmax) * 1.4426950408889634f);
+            run_sum *= fast_exp2(run_max - cmax);
             run_max = cmax;
           }
-          if (run_max > -INFINITY) {
-            const float mb = run_max * 1.4426950408889634f;
-            float acc_s = 0.f;
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          const float mref = (run_max == -INFINITY) ? 0.f : run_max;  // a fully masked half tile contributes exactly 0
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc_s += exp2f(fmaf(s[j], 1.4426950408889634f, -mb));
-            run_sum += acc_s;
+          for (int j = 0; j < 32; j += 4) {
+            s0 += fast_exp2(t[j] - mref);
+            s1 += fast_exp2(t[j + 1] - mref);
+            s2 += fast_exp2(t[j + 2] - mref);
+            s3 += fast_exp2(t[j + 3] - mref);
           }
+          run_sum += (s0 + s1) + (s2 + s3);
           if (label >= col0 && label < col0 + 32 && row_ok) {
             float lv = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) lv = (col0 + j == label) ? s[j] : lv;
-            ep.label_logit[row] = lv;
+            for (int j = 0; j < 32; ++j) lv = (col0 + j == label) ? t[j] : lv;
+            ep.label_logit[row] = lv * kLn2;
           }
         } else {
           // value transform
           if (MODE == EPI_NCE_DS) {
+            const bool has_label = (label >= col0 && label < col0 + 32 && row_ok);
+            float tl = 0.f;
+            if (plain) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = col0 + j;
-              const float rdj = (ep.rd != nullptr) ? (col < N ? ep.rd[col] : 0.f) : 1.f;
-              const float s = __uint_as_float(v[j]) * rscale * rdj;
-              float p = exp2f((s - row_lse) * 1.4426950408889634f);
-              p = (col == label) ? p - 1.f : p;
-              float ds = ep_coef * p;
-              ds = (col < N && row_ok) ? ds : 0.f;
-              dlogit_acc = fmaf(ds, s, dlogit_acc);
-              if (ep.rq != nullptr || ep.rd != nullptr) ds *= (rscale / ep_scale) * rdj;
-              v[j] = __float_as_uint(ds);
+              for (int j = 0; j < 32; j += 4) {
+                const float t0 = __uint_as_float(v[j]) * rs2, t1 = __uint_as_float(v[j + 1]) * rs2;
+                const float t2 = __uint_as_float(v[j + 2]) * rs2, t3 = __uint_as_float(v[j + 3]) * rs2;
+                const float p0 = fast_exp2(t0 - lse2), p1 = fast_exp2(t1 - lse2), p2 = fast_exp2(t2 - lse2), p3 = fast_exp2(t3 - lse2);
+                dl0 = fmaf(p0, t0, dl0);
+                dl1 = fmaf(p1, t1, dl1);
+                dl2 = fmaf(p2, t2, dl2);
+                dl3 = fmaf(p3, t3, dl3);
+                if (has_label) {
+                  tl = (col0 + j == label) ? t0 : tl;
+                  tl = (col0 + j + 1 == label) ? t1 : tl;
+                  tl = (col0 + j + 2 == label) ? t2 : tl;
+                  tl = (col0 + j + 3 == label) ? t3 : tl;
+                }
+                v[j] = __float_as_uint(p0 * rowf);
+                v[j + 1] = __float_as_uint(p1 * rowf);
+                v[j + 2] = __float_as_uint(p2 * rowf);
+                v[j + 3] = __float_as_uint(p3 * rowf);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int col = col0 + j;
+                const float rdj = (ep.rd != nullptr) ? (col < N ? ep.rd[col] : 0.f) : 1.f;
+                const float t = __uint_as_float(v[j]) * rs2 * rdj;
+                const float p = (col < N) ? fast_exp2(t - lse2) : 0.f;
+                dl0 = fmaf(p, t, dl0);
+                tl = (col == label) ? t : tl;
+                v[j] = __float_as_uint(p * rowf * ((ep.ds_f16 || ep.rd == nullptr) ? 1.f : rdj));
+              }
+            }
+            if (has_label) {  // subtract the one-hot: rare (one chunk per row per pass)
+              dl0 -= tl;
+              const float one = rowf * ((ep.ds_f16 || ep.rd == nullptr) ? 1.f : ep.rd[label]);
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j == label) v[j] = __float_as_uint(__uint_as_float(v[j]) - one);
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * ep_alpha);
           }
-          // stage + TMA store.  fp32: one 32-col chunk = 128 B per row; bf16: two chunks = 128 B per row.
+          // stage + TMA store.  fp32: one 32-col chunk = 128 B per row; 16-bit: two chunks = 128 B per row.
           if (OUT_F32) {
-            if (etid == 0) tma_store_wait_read<1>();
-            named_bar_sync(1, 128);
-            uint8_t* dst = smem_c + cbuf * kStageCBytes + row_in_tile * 128;
+            if (etid == 0) tma_store_wait_read<0>();
+            named_bar_sync(1 + hf, 128);
+            uint8_t* dst = stage_c + row_in_tile * 128;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               uint4 w = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
               *reinterpret_cast<uint4*>(dst + ((j ^ (row_in_tile & 7)) << 4)) = w;
             }
             fence_proxy_async_smem();
-            named_bar_sync(1, 128);
+            named_bar_sync(1 + hf, 128);
             if (etid == 0) {
-              if (ACCUM) tma_reduce_add_2d(&tmC, smem_c + cbuf * kStageCBytes, col0, m0);
-              else tma_store_2d(&tmC, smem_c + cbuf * kStageCBytes, col0, m0);
+              if (ACCUM) tma_reduce_add_2d(&tmC, stage_c, col0, m0);
+              else tma_store_2d(&tmC, stage_c, col0, m0);
               tma_store_commit();
             }
-            cbuf ^= 1;
           } else {
             const int half = c & 1;
             if (half == 0) {
-              if (etid == 0) tma_store_wait_read<1>();
-              named_bar_sync(1, 128);
+              if (etid == 0) tma_store_wait_read<0>();
+              named_bar_sync(1 + hf, 128);
             }
-            uint8_t* dst = smem_c + cbuf * kStageCBytes + row_in_tile * 128;
+            uint8_t* dst = stage_c + row_in_tile * 128;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 w;
-              w.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
-              w.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
-              w.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
-              w.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+              if (MODE == EPI_NCE_DS && ep.ds_f16) {
+                w.x = pack_f16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+                w.y = pack_f16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+                w.z = pack_f16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+                w.w = pack_f16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+              } else {
+                w.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+                w.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+                w.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+                w.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+              }
               const int chunk = half * 4 + j;
               *reinterpret_cast<uint4*>(dst + ((chunk ^ (row_in_tile & 7)) << 4)) = w;
             }
             if (half == 1) {
               fence_proxy_async_smem();
-              named_bar_sync(1, 128);
+              named_bar_sync(1 + hf, 128);
               if (etid == 0) {
-                tma_store_2d(&tmC, smem_c + cbuf * kStageCBytes, col0 - 32, m0);
+                tma_store_2d(&tmC, stage_c, col0 - 32, m0);
                 tma_store_commit();
               }
-              cbuf ^= 1;
             }
           }
         }
@@ -325,15 +387,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
 
-      if (MODE == EPI_NCE_STATS && row_ok) {
-        const size_t o = static_cast<size_t>(nt) * M + row;
+      if (MODE == EPI_NCE_STATS && row_ok) {  // partials stay in the log2 domain; the combine kernel converts
+        const size_t o = static_cast<size_t>(nt * 2 + hf) * M + row;
         ep.part_max[o] = run_max;
         ep.part_sum[o] = run_sum;
         ep.part_arg[o] = run_arg;
       }
     }
-    if (MODE == EPI_NCE_DS) ep.dlogit_part[blockIdx.x * 128 + etid] = dlogit_acc;
     if (MODE != EPI_NCE_STATS && etid == 0) tma_store_wait<0>();
+    if (MODE == EPI_NCE_DS) {
+      // deterministic per-CTA reduction of the logit-scale gradient partial: d/dlog(scale) = coef * ln2 * sum (p - 1hot) t
+      float dl = (dl0 + dl1) + (dl2 + dl3);
+      for (int o = 16; o > 0; o >>= 1) dl += __shfl_xor_sync(0xffffffffu, dl, o);
+      float* red = reinterpret_cast<float*>(bars) + 48;  // spare bytes behind the barriers
+      if (lane == 0) red[warp - 4] = dl;
+      named_bar_sync(3, 256);
+      if (threadIdx.x == 128)
+        ep.dlogit_part[blockIdx.x] = (((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]))) * ep_coef * kLn2;
+    }
   }
 
   tc_fence_before();

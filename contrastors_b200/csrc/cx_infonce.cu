@@ -23,14 +23,17 @@ struct NceWorkspace {
   unsigned int* ticket;  // [1]
   __nv_bfloat16* ds;
   int64_t ld_ds;
+  __half* qh;  // fp16 copies of q / d for the backward contractions (exact for |x| >= 2^-14)
+  __half* dh;
+  int64_t ld_h;
   size_t bytes;
 };
-constexpr int kMaxCombineBlocks = 1024;
+constexpr int kMaxCombineBlocks = 8192;
 constexpr int kMaxGrid = 1024;
 
-static NceWorkspace carve(void* base, int n, int m) {
+static NceWorkspace carve(void* base, int n, int m, int k) {
   NceWorkspace w{};
-  const size_t ct = (size_t)(m + 127) / 128;
+  const size_t ct = 2 * ((size_t)(m + 127) / 128);  // one partial per 64/128-column half tile
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
@@ -40,53 +43,65 @@ static NceWorkspace carve(void* base, int n, int m) {
   w.part_max = reinterpret_cast<float*>(take(ct * n * 4));
   w.part_sum = reinterpret_cast<float*>(take(ct * n * 4));
   w.part_arg = reinterpret_cast<int*>(take(ct * n * 4));
-  w.dlogit_part = reinterpret_cast<float*>(take((size_t)kMaxGrid * 128 * 4));
+  w.dlogit_part = reinterpret_cast<float*>(take((size_t)kMaxGrid * 4));
   w.block_part = reinterpret_cast<float*>(take((size_t)2 * kMaxCombineBlocks * 4));
   w.ticket = reinterpret_cast<unsigned int*>(take(256));
   w.ld_ds = (int64_t)align_up((size_t)m, 8);
   w.ds = reinterpret_cast<__nv_bfloat16*>(take((size_t)n * w.ld_ds * 2));
+  w.ld_h = (int64_t)align_up((size_t)k, 8);
+  w.qh = reinterpret_cast<__half*>(take((size_t)n * w.ld_h * 2));
+  w.dh = reinterpret_cast<__half*>(take((size_t)m * w.ld_h * 2));
   w.bytes = off;
   return w;
 }
 
-// One thread per row: merge the per-column-tile partials (in ascending tile order, so the first maximum wins exactly
-// like ATen's argmax), produce lse / argmax, and reduce the loss sum and the hit count deterministically (fixed-order
-// block partials summed by the last block to arrive).
+// One warp per row: merge the per-column-tile partials (log2 domain).  Ties between tiles resolve to the lowest column
+// index, so the result is exactly ATen's first-maximum argmax.  The loss sum / hit count are reduced in a fixed order
+// (block partials summed by the last block to arrive), so results are run-to-run deterministic.
 __global__ void nce_combine_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum,
                                    const int* __restrict__ part_arg, const float* __restrict__ label_logit, int n,
                                    int n_col_tiles, int label_offset, int label_stride, float* __restrict__ lse,
                                    int* __restrict__ argmax, float* __restrict__ stats, float* __restrict__ block_part,
                                    unsigned int* __restrict__ ticket) {
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr float kLn2 = 0.6931471805599453f;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
   float loss_term = 0.f, hit = 0.f;
   if (row < n) {
     float gmax = -INFINITY;
-    int garg = 0;
-    for (int t = 0; t < n_col_tiles; ++t) {
+    int garg = 0x7fffffff;
+    for (int t = lane; t < n_col_tiles; t += 32) {
       const float mx = part_max[(size_t)t * n + row];
-      if (mx > gmax) {
+      const int ag = part_arg[(size_t)t * n + row];
+      if (mx > gmax || (mx == gmax && ag < garg)) {
         gmax = mx;
-        garg = part_arg[(size_t)t * n + row];
+        garg = ag;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, gmax, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, garg, o);
+      if (om > gmax || (om == gmax && oa < garg)) {
+        gmax = om;
+        garg = oa;
       }
     }
     float sum = 0.f;
-    for (int t = 0; t < n_col_tiles; ++t) {
-      const float mx = part_max[(size_t)t * n + row];
-      sum += part_sum[(size_t)t * n + row] * exp2f((mx - gmax) * 1.4426950408889634f);
+    for (int t = lane; t < n_col_tiles; t += 32) {
+      const float ps = part_sum[(size_t)t * n + row];
+      if (ps > 0.f) sum += ps * exp2f(part_max[(size_t)t * n + row] - gmax);  // masked-out halves carry (-inf, 0)
     }
-    const float l = gmax + logf(sum);
-    lse[row] = l;
-    argmax[row] = garg;
-    loss_term = l - label_logit[row];
-    hit = (garg == (row + label_offset) * label_stride) ? 1.f : 0.f;
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float l = (gmax + log2f(sum)) * kLn2;
+    if (lane == 0) {
+      lse[row] = l;
+      argmax[row] = garg;
+      loss_term = l - label_logit[row];
+      hit = (garg == (row + label_offset) * label_stride) ? 1.f : 0.f;
+    }
   }
   __shared__ float s_loss[32], s_hit[32];
   __shared__ bool is_last;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int o = 16; o > 0; o >>= 1) {
-    loss_term += __shfl_xor_sync(0xffffffffu, loss_term, o);
-    hit += __shfl_xor_sync(0xffffffffu, hit, o);
-  }
   if (lane == 0) {
     s_loss[warp] = loss_term;
     s_hit[warp] = hit;
@@ -105,30 +120,32 @@ __global__ void nce_combine_kernel(const float* __restrict__ part_max, const flo
     is_last = (t == gridDim.x - 1);
   }
   __syncthreads();
-  if (is_last && threadIdx.x == 0) {
+  if (is_last && warp == 0) {
     __threadfence();
     float a = 0.f, b = 0.f;
-    for (int i = 0; i < (int)gridDim.x; ++i) {
+    for (int i = lane; i < (int)gridDim.x; i += 32) {
       a += reinterpret_cast<volatile float*>(block_part)[2 * i];
       b += reinterpret_cast<volatile float*>(block_part)[2 * i + 1];
     }
-    stats[0] = a;
-    stats[1] = b;
-    *ticket = 0;  // ready for the next call on this workspace
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) {
+      stats[0] = a;
+      stats[1] = b;
+      *ticket = 0;  // ready for the next call on this workspace
+    }
   }
 }
 
+// sums the per-CTA partials (fixed order) into stats[2]
 __global__ void nce_dlogit_kernel(const float* __restrict__ part, int count, float* __restrict__ stats) {
-  __shared__ float s[1024];
+  const int lane = threadIdx.x;
   float a = 0.f;
-  for (int i = threadIdx.x; i < count; i += blockDim.x) a += part[i];
-  s[threadIdx.x] = a;
-  __syncthreads();
-  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) stats[2] = s[0];
+  for (int i = lane; i < count; i += 32) a += part[i];
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) stats[2] = a;
 }
 
 // ---------------------------------------------------------------- row utilities
@@ -150,6 +167,28 @@ __global__ void rows_to_bf16_kernel(const float* __restrict__ x, int64_t ldx, __
   if (y != nullptr) {
     __nv_bfloat16* yr = y + (size_t)row * ldy;
     for (int j = lane; j < k; j += 32) yr[j] = __float2bfloat16_rn(xr[j] * inv);
+  }
+}
+
+// bf16 -> fp16 row copy, 8 elements per thread (rows are 16-byte aligned with k % 8 == 0 on the fast path)
+__global__ void bf16_to_f16_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __half* __restrict__ y, int64_t ldy,
+                                        int rows, int k, int vec_ok) {
+  const int per_row = (k + 7) / 8;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)rows * per_row) return;
+  const int r = (int)(i / per_row), c = (int)(i % per_row) * 8;
+  const __nv_bfloat16* xr = x + (size_t)r * ldx + c;
+  __half* yr = y + (size_t)r * ldy + c;
+  if (vec_ok && c + 8 <= k) {
+    const uint4 in = *reinterpret_cast<const uint4*>(xr);
+    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&in);
+    uint4 out;
+    __half2* h2 = reinterpret_cast<__half2*>(&out);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h2[j] = __floats2half2_rn(__low2float(b2[j]), __high2float(b2[j]));
+    *reinterpret_cast<uint4*>(yr) = out;
+  } else {
+    for (int j = 0; j < 8 && c + j < k; ++j) yr[j] = __float2half_rn(__bfloat162float(xr[j]));
   }
 }
 
@@ -178,9 +217,9 @@ __global__ void l2norm_bwd_kernel(const float* __restrict__ x, int64_t ldx, cons
 
 using namespace cx;
 
-extern "C" size_t cx_infonce_workspace_bytes(int n, int m) {
-  if (n <= 0 || m <= 0) return 0;
-  return carve(nullptr, n, m).bytes + 256;
+extern "C" size_t cx_infonce_workspace_bytes(int n, int m, int k_dim) {
+  if (n <= 0 || m <= 0 || k_dim <= 0) return 0;
+  return carve(nullptr, n, m, k_dim).bytes + 256;
 }
 
 static void* align256(void* p) { return reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(p) + 255) & ~uintptr_t(255)); }
@@ -194,7 +233,7 @@ extern "C" int cx_infonce_fwd(const void* q, int64_t ldq, const void* d, int64_t
   CX_REQUIRE((long long)(n - 1 + label_offset) * label_stride < m && label_offset >= 0 && label_stride >= 1,
              "cx_infonce_fwd: labels out of range");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  NceWorkspace w = carve(align256(workspace), n, m);
+  NceWorkspace w = carve(align256(workspace), n, m, k_dim);
   GemmArgs g{};
   g.A = q; g.B = d; g.C = nullptr;
   g.M = n; g.N = m; g.K = k_dim;
@@ -210,9 +249,9 @@ extern "C" int cx_infonce_fwd(const void* q, int64_t ldq, const void* d, int64_t
   int rc = launch_gemm(g);
   if (rc) return rc;
   const int bn = gemm_block_n(m);
-  const int n_col_tiles = (m + bn - 1) / bn;
-  const int threads = 128;
-  const int blocks = (n + threads - 1) / threads;
+  const int n_col_tiles = 2 * ((m + bn - 1) / bn);  // the epilogue emits one partial per column half
+  const int threads = 256;  // 8 rows per block, one warp each
+  const int blocks = (n + 7) / 8;
   CX_REQUIRE(blocks <= kMaxCombineBlocks, "cx_infonce_fwd: n too large");
   CX_CUDA_CHECK(cudaMemsetAsync(w.ticket, 0, 4, stream));
   nce_combine_kernel<<<blocks, threads, 0, stream>>>(w.part_max, w.part_sum, w.part_arg, label_logit, n, n_col_tiles,
@@ -228,7 +267,7 @@ extern "C" int cx_infonce_bwd(const void* q, int64_t ldq, const void* d, int64_t
   CX_REQUIRE(q && d && lse && dq && dd && stats && workspace, "cx_infonce_bwd: null pointer");
   CX_REQUIRE(n > 0 && m > 0 && k_dim > 0, "cx_infonce_bwd: empty problem");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  NceWorkspace w = carve(align256(workspace), n, m);
+  NceWorkspace w = carve(align256(workspace), n, m, k_dim);
   // stage 1: dS (bf16) = coef * (softmax - onehot) [* rq_i rd_j]
   GemmArgs g{};
   g.A = q; g.B = d; g.C = w.ds;
@@ -240,32 +279,57 @@ extern "C" int cx_infonce_bwd(const void* q, int64_t ldq, const void* d, int64_t
   g.ep.scale = scale; g.ep.scale_dev = scale_dev; g.ep.rq = rq; g.ep.rd = rd;
   g.ep.label_offset = label_offset; g.ep.label_stride = label_stride;
   g.ep.lse = lse; g.ep.coef = coef; g.ep.coef_dev = coef_dev;
+  // Plain (pre-normalised) inputs: the workspace holds UNSCALED fp16 (softmax - onehot) in [-1, 1] (11-bit mantissa) and
+  // coef is folded into the contractions' alpha.  With per-row norms the values are scaled by rq*rd, whose range is
+  // the caller's, so that path keeps bf16 (fp32 exponent range) and coef in the stored value.
+  const bool f16 = (rq == nullptr && rd == nullptr);
+  g.ep.ds_f16 = f16 ? 1 : 0;
   g.ep.dlogit_part = w.dlogit_part;
   g.stream = stream;
   const int grid1 = gemm_grid(n, m, 1);
   CX_REQUIRE(grid1 <= kMaxGrid, "cx_infonce_bwd: grid too large");
   int rc = launch_gemm(g);
   if (rc) return rc;
-  nce_dlogit_kernel<<<1, 1024, 0, stream>>>(w.dlogit_part, grid1 * 128, stats);
+  nce_dlogit_kernel<<<1, 32, 0, stream>>>(w.dlogit_part, grid1, stats);
   CX_LAUNCH_CHECK();
+  const void* qB = q;
+  const void* dB = d;
+  int64_t ldqB = ldq, lddB = ldd;
+  if (f16) {
+    const int threads = 256;
+    const int64_t per_row = (k_dim + 7) / 8;
+    const int vq = (ldq % 8 == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0) ? 1 : 0;
+    const int vd = (ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(d) & 15) == 0) ? 1 : 0;
+    bf16_to_f16_rows_kernel<<<(unsigned)(((int64_t)n * per_row + threads - 1) / threads), threads, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(q), ldq, w.qh, w.ld_h, n, k_dim, vq);
+    CX_LAUNCH_CHECK();
+    bf16_to_f16_rows_kernel<<<(unsigned)(((int64_t)m * per_row + threads - 1) / threads), threads, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(d), ldd, w.dh, w.ld_h, m, k_dim, vd);
+    CX_LAUNCH_CHECK();
+    qB = w.qh; dB = w.dh; ldqB = w.ld_h; lddB = w.ld_h;
+  }
   // stage 2a: dQ[n,k] = scale * dS[n,m] (K-major A) x D[m,k] (MN-major B), split-K over m
   GemmArgs a{};
-  a.A = w.ds; a.B = d; a.C = dq;
+  a.A = w.ds; a.B = dB; a.C = dq;
   a.M = n; a.N = k_dim; a.K = m;
   a.a_mn = false; a.b_mn = true;
-  a.lda = w.ld_ds; a.ldb = ldd; a.ldc = lddq;
+  a.lda = w.ld_ds; a.ldb = lddB; a.ldc = lddq;
   a.out_f32 = true; a.accumulate = false; a.splits = 0;
-  a.mode = EPI_STORE; a.ep.alpha = scale; a.ep.alpha_dev = scale_dev; a.stream = stream;
+  a.mode = EPI_STORE; a.ep.alpha = f16 ? scale * coef : scale; a.ep.alpha_dev = scale_dev; a.ep.alpha_dev2 = f16 ? coef_dev : nullptr;
+  a.ep.ab_f16 = f16 ? 1 : 0;
+  a.stream = stream;
   rc = launch_gemm(a);
   if (rc) return rc;
   // stage 2b: dD[m,k] = scale * dS^T (MN-major A: stored [n,m]) x Q[n,k] (MN-major B)
   GemmArgs b{};
-  b.A = w.ds; b.B = q; b.C = dd;
+  b.A = w.ds; b.B = qB; b.C = dd;
   b.M = m; b.N = k_dim; b.K = n;
   b.a_mn = true; b.b_mn = true;
-  b.lda = w.ld_ds; b.ldb = ldq; b.ldc = lddd;
+  b.lda = w.ld_ds; b.ldb = ldqB; b.ldc = lddd;
   b.out_f32 = true; b.accumulate = accumulate_dd != 0; b.splits = 0;
-  b.mode = EPI_STORE; b.ep.alpha = scale; b.ep.alpha_dev = scale_dev; b.stream = stream;
+  b.mode = EPI_STORE; b.ep.alpha = f16 ? scale * coef : scale; b.ep.alpha_dev = scale_dev; b.ep.alpha_dev2 = f16 ? coef_dev : nullptr;
+  b.ep.ab_f16 = f16 ? 1 : 0;
+  b.stream = stream;
   return launch_gemm(b);
 }
 

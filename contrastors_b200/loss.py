@@ -71,7 +71,7 @@ class _FusedInfoNCE(torch.autograd.Function):
         m = d_bf.shape[0]
         dims = spec.dims or [width]
         weights = spec.weights or [1.0] * len(dims)
-        ws_buf = ops.infonce_workspace(n, m, query.device)
+        ws_buf = ops.infonce_workspace(n, m, width, query.device)
         scale_dev = scale_t.detach().contiguous()
         loss = torch.zeros((), device=query.device, dtype=torch.float32)
         saved_lse, saved_rq, saved_rd = [], [], []
@@ -107,8 +107,9 @@ class _FusedInfoNCE(torch.autograd.Function):
         n, m, width = ctx.n, ctx.m, ctx.width
         dev = q_bf.device
         coef_dev = grad_loss.detach().to(torch.float32).contiguous()
-        dq = torch.empty(n, width, device=dev, dtype=torch.float32)
-        dd = torch.empty(m, width, device=dev, dtype=torch.float32)
+        ldw = (width + 3) // 4 * 4  # fp32 rows must be 16-byte aligned for the TMA stores
+        dq = torch.empty(n, ldw, device=dev, dtype=torch.float32)[:, :width]
+        dd = torch.empty(m, ldw, device=dev, dtype=torch.float32)[:, :width]
         if spec.normalize or len(ctx.dims) > 1 or ctx.dims[0] != width:
             dq.zero_()
             dd.zero_()
@@ -120,8 +121,9 @@ class _FusedInfoNCE(torch.autograd.Function):
                 ops.infonce_bwd(q_bf, d_bf, k, 1.0, scale_dev, None, None, spec.label_offset, spec.label_stride,
                                 saved_lse[i], coef, coef_dev, dq, dd, False, stats, ctx.ws_buf)
             else:
-                gq = torch.empty(n, k, device=dev, dtype=torch.float32)
-                gd = torch.empty(m, k, device=dev, dtype=torch.float32)
+                ldk = (k + 3) // 4 * 4
+                gq = torch.empty(n, ldk, device=dev, dtype=torch.float32)[:, :k]
+                gd = torch.empty(m, ldk, device=dev, dtype=torch.float32)[:, :k]
                 ops.infonce_bwd(q_bf, d_bf, k, 1.0, scale_dev, saved_rq[i], saved_rd[i], spec.label_offset,
                                 spec.label_stride, saved_lse[i], coef, coef_dev, gq, gd, False, stats, ctx.ws_buf)
                 if spec.normalize:

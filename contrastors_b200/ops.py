@@ -75,6 +75,7 @@ def l2norm_bwd(x, g, inv_norm, k, out=None, g_prescaled=False, accumulate=False)
     if out is None:
         out = torch.zeros_like(x) if k != x.shape[1] else torch.empty_like(x)
         accumulate = False
+    assert g.stride(1) == 1 and out.stride(1) == 1 and x.stride(1) == 1
     lib = _lib.load()
     _lib.check(lib.cx_l2norm_bwd(x.data_ptr(), x.stride(0), g.data_ptr(), g.stride(0), inv_norm.data_ptr(),
                                  out.data_ptr(), out.stride(0), rows, k, int(g_prescaled), int(accumulate), _stream()),
@@ -82,8 +83,8 @@ def l2norm_bwd(x, g, inv_norm, k, out=None, g_prescaled=False, accumulate=False)
     return out
 
 
-def infonce_workspace(n, m, device):
-    nbytes = _lib.load().cx_infonce_workspace_bytes(n, m)
+def infonce_workspace(n, m, k_dim, device):
+    nbytes = _lib.load().cx_infonce_workspace_bytes(n, m, k_dim)
     return torch.empty(nbytes, device=device, dtype=torch.uint8)
 
 
@@ -113,3 +114,185 @@ def infonce_bwd(q, d, k_dim, scale, scale_dev, rq, rd, label_offset, label_strid
                                   float(coef), _ptr(coef_dev), dq.data_ptr(), dq.stride(0), dd.data_ptr(), dd.stride(0),
                                   int(accumulate_dd), stats.data_ptr(), workspace.data_ptr(), _stream()),
                "cx_infonce_bwd")
+
+
+# ------------------------------------------------------------------------------------------------ encoder ops
+def _ws_bytes(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), device=device, dtype=torch.uint8)
+
+
+def add_layernorm_fwd(a, b, gamma, beta, eps):
+    """y = LN(a + b) (b may be None); returns (y bf16 [rows,d], stats fp32 [rows,2])."""
+    _require_cuda(a, b)
+    rows, d = a.shape
+    y = torch.empty_like(a)
+    stats = torch.empty(rows, 2, device=a.device, dtype=torch.float32)
+    lib = _lib.load()
+    _lib.check(lib.cx_add_layernorm_fwd(a.data_ptr(), _ptr(b), _ptr(gamma), _ptr(beta), y.data_ptr(), stats.data_ptr(),
+                                        rows, d, float(eps), _stream()), "cx_add_layernorm_fwd")
+    return y, stats
+
+
+def add_layernorm_bwd(a, b, g1, g2, gamma, stats, dgamma, dbeta):
+    """dz (bf16) for z = a + b given upstream g1 (+ g2); ADDS into dgamma/dbeta (fp32) when given."""
+    rows, d = a.shape
+    dz = torch.empty_like(a)
+    lib = _lib.load()
+    ws = _ws_bytes(lib.cx_layernorm_bwd_workspace_bytes(d), a.device) if dgamma is not None else None
+    _lib.check(lib.cx_add_layernorm_bwd(a.data_ptr(), _ptr(b), g1.data_ptr(), _ptr(g2), _ptr(gamma), stats.data_ptr(),
+                                        dz.data_ptr(), _ptr(dgamma), _ptr(dbeta), _ptr(ws), rows, d, _stream()),
+               "cx_add_layernorm_bwd")
+    return dz
+
+
+def embed_layernorm_fwd(ids, type_ids, word_emb, type_emb, gamma, beta, eps):
+    _require_cuda(ids, word_emb)
+    rows = ids.numel()
+    d = word_emb.shape[1]
+    y = torch.empty(rows, d, device=ids.device, dtype=torch.bfloat16)
+    stats = torch.empty(rows, 2, device=ids.device, dtype=torch.float32)
+    lib = _lib.load()
+    _lib.check(lib.cx_embed_layernorm_fwd(ids.data_ptr(), _ptr(type_ids), word_emb.data_ptr(), type_emb.data_ptr(),
+                                          gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), stats.data_ptr(), rows, d,
+                                          float(eps), _stream()), "cx_embed_layernorm_fwd")
+    return y, stats
+
+
+def embed_layernorm_bwd(ids, type_ids, word_emb, type_emb, g1, g2, gamma, stats, dword, dtype_emb, dgamma, dbeta,
+                        padding_idx=-1):
+    rows = ids.numel()
+    d = word_emb.shape[1]
+    lib = _lib.load()
+    ws = _ws_bytes(lib.cx_layernorm_bwd_workspace_bytes(d), ids.device)
+    _lib.check(lib.cx_embed_layernorm_bwd(ids.data_ptr(), _ptr(type_ids), word_emb.data_ptr(), type_emb.data_ptr(),
+                                          g1.data_ptr(), _ptr(g2), gamma.data_ptr(), stats.data_ptr(), dword.data_ptr(),
+                                          dtype_emb.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), rows, d,
+                                          int(padding_idx), _stream()), "cx_embed_layernorm_bwd")
+
+
+def token_positions(cu_seqlens, total_tokens):
+    nseq = cu_seqlens.numel() - 1
+    pos = torch.empty(total_tokens, device=cu_seqlens.device, dtype=torch.int32)
+    lib = _lib.load()
+    _lib.check(lib.cx_token_positions(cu_seqlens.data_ptr(), nseq, pos.data_ptr(), 0, _stream()), "cx_token_positions")
+    return pos
+
+
+def rope_inplace(qkv, pos, cos_t, sin_t, H, Dh, backward=False, first_slot=0, num_slots=2):
+    T = qkv.shape[0]
+    lib = _lib.load()
+    _lib.check(lib.cx_rope_inplace(qkv.data_ptr(), pos.data_ptr(), cos_t.data_ptr(), sin_t.data_ptr(), T, H, Dh,
+                                   int(backward), first_slot, num_slots, _stream()), "cx_rope_inplace")
+    return qkv
+
+
+def swiglu_fwd(yg):
+    T, two_i = yg.shape
+    out = torch.empty(T, two_i // 2, device=yg.device, dtype=torch.bfloat16)
+    lib = _lib.load()
+    _lib.check(lib.cx_swiglu_fwd(yg.data_ptr(), out.data_ptr(), T, two_i // 2, _stream()), "cx_swiglu_fwd")
+    return out
+
+
+def swiglu_bwd(dout, yg):
+    T, two_i = yg.shape
+    dyg = torch.empty_like(yg)
+    lib = _lib.load()
+    _lib.check(lib.cx_swiglu_bwd(dout.data_ptr(), yg.data_ptr(), dyg.data_ptr(), T, two_i // 2, _stream()), "cx_swiglu_bwd")
+    return dyg
+
+
+def mean_pool_fwd(h, cu_seqlens):
+    nseq = cu_seqlens.numel() - 1
+    d = h.shape[1]
+    pooled = torch.empty(nseq, d, device=h.device, dtype=torch.float32)
+    lib = _lib.load()
+    _lib.check(lib.cx_mean_pool_fwd(h.data_ptr(), cu_seqlens.data_ptr(), pooled.data_ptr(), nseq, d, _stream()),
+               "cx_mean_pool_fwd")
+    return pooled
+
+
+def mean_pool_bwd(dpooled, cu_seqlens, total_tokens):
+    nseq, d = dpooled.shape
+    dh = torch.empty(total_tokens, d, device=dpooled.device, dtype=torch.bfloat16)
+    lib = _lib.load()
+    _lib.check(lib.cx_mean_pool_bwd(dpooled.data_ptr(), cu_seqlens.data_ptr(), dh.data_ptr(), nseq, d, _stream()),
+               "cx_mean_pool_bwd")
+    return dh
+
+
+def embed_head_fwd(pooled, hamming, normalize):
+    rows, d = pooled.shape
+    out = torch.empty_like(pooled)
+    save = torch.empty(rows, 3, device=pooled.device, dtype=torch.float32)
+    lib = _lib.load()
+    _lib.check(lib.cx_embed_head_fwd(pooled.data_ptr(), out.data_ptr(), save.data_ptr(), rows, d, int(hamming),
+                                     int(normalize), _stream()), "cx_embed_head_fwd")
+    return out, save
+
+
+def embed_head_bwd(pooled, gout, save, hamming, normalize):
+    rows, d = pooled.shape
+    g = torch.empty_like(pooled)
+    lib = _lib.load()
+    _lib.check(lib.cx_embed_head_bwd(pooled.data_ptr(), gout.data_ptr(), save.data_ptr(), g.data_ptr(), rows, d,
+                                     int(hamming), int(normalize), _stream()), "cx_embed_head_bwd")
+    return g
+
+
+def attn_fwd(qkv, cu_seqlens, max_seqlen, H, Dh, softmax_scale):
+    """qkv [T, 3*H*Dh] bf16 (RoPE applied) -> (out [T, H*Dh] bf16, lse [H, T] fp32)."""
+    T = qkv.shape[0]
+    nseq = cu_seqlens.numel() - 1
+    out = torch.empty(T, H * Dh, device=qkv.device, dtype=torch.bfloat16)
+    lse = torch.empty(H, T, device=qkv.device, dtype=torch.float32)
+    lib = _lib.load()
+    _lib.check(lib.cx_attn_fwd(qkv.data_ptr(), cu_seqlens.data_ptr(), out.data_ptr(), lse.data_ptr(), T, nseq,
+                               int(max_seqlen), H, Dh, float(softmax_scale), _stream()), "cx_attn_fwd")
+    return out, lse
+
+
+def attn_bwd(qkv, out, dout, lse, cu_seqlens, max_seqlen, H, Dh, softmax_scale, pos=None, cos_t=None, sin_t=None):
+    """Returns dqkv [T, 3*H*Dh] bf16; with pos/cos/sin the RoPE transpose is applied to dq and dk."""
+    T = qkv.shape[0]
+    nseq = cu_seqlens.numel() - 1
+    dqkv = torch.empty_like(qkv)
+    dq_acc = torch.zeros(T, H * Dh, device=qkv.device, dtype=torch.float32)
+    delta = torch.empty(H, T, device=qkv.device, dtype=torch.float32)
+    lib = _lib.load()
+    _lib.check(lib.cx_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), cu_seqlens.data_ptr(),
+                               dqkv.data_ptr(), dq_acc.data_ptr(), delta.data_ptr(), T, nseq, int(max_seqlen), H, Dh,
+                               float(softmax_scale), _stream()), "cx_attn_bwd")
+    if pos is not None:
+        _lib.check(lib.cx_dq_finalize_rope(dq_acc.data_ptr(), dqkv.data_ptr(), pos.data_ptr(), cos_t.data_ptr(),
+                                           sin_t.data_ptr(), T, H, Dh, _stream()), "cx_dq_finalize_rope")
+        rope_inplace(dqkv, pos, cos_t, sin_t, H, Dh, backward=True, first_slot=1, num_slots=1)  # dk
+    else:
+        _lib.check(lib.cx_dq_finalize(dq_acc.data_ptr(), dqkv.data_ptr(), T, H, Dh, _stream()), "cx_dq_finalize")
+    return dqkv
+
+
+def grad_clip_coef(grad_flat, max_norm):
+    lib = _lib.load()
+    out2 = torch.empty(2, device=grad_flat.device, dtype=torch.float32)
+    ws = _ws_bytes(lib.cx_grad_clip_workspace_bytes(), grad_flat.device)
+    _lib.check(lib.cx_grad_clip_coef(grad_flat.data_ptr(), grad_flat.numel(), float(max_norm), out2.data_ptr(),
+                                     ws.data_ptr(), _stream()), "cx_grad_clip_coef")
+    return out2
+
+
+def adamw_step(param, grad, exp_avg, exp_avg_sq, shadow, lr, beta1, beta2, eps, weight_decay, step, grad_scale_dev=None,
+               grad_scale=1.0, zero_grad=True):
+    lib = _lib.load()
+    _lib.check(lib.cx_adamw_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), _ptr(shadow),
+                                 param.numel(), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),
+                                 int(step), _ptr(grad_scale_dev), float(grad_scale), int(zero_grad), _stream()),
+               "cx_adamw_step")
+
+
+def cast_f32_bf16(x, out=None):
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    lib = _lib.load()
+    _lib.check(lib.cx_cast_f32_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "cx_cast_f32_bf16")
+    return out

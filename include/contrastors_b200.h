@@ -60,8 +60,8 @@ CX_API int cx_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int
  *   dd[m,k_dim] = scale * rd_j * sum_i dS_ij rq_i q_i   (fp32, ldd_out; accumulate_dd != 0 adds into dd)
  *   stats[2]  = sum_ij dS_ij * s_ij   (= d loss / d log(scale))
  * When rq/rd are given the caller finishes the chain rule through F.normalize (cx_l2norm_bwd, g_prescaled = 1).
- * workspace: cx_infonce_workspace_bytes(n, m) bytes of device memory, reusable across calls on one stream. */
-CX_API size_t cx_infonce_workspace_bytes(int n, int m);
+ * workspace: cx_infonce_workspace_bytes(n, m, k_dim) bytes of device memory, reusable across calls on one stream. */
+CX_API size_t cx_infonce_workspace_bytes(int n, int m, int k_dim);
 CX_API int cx_infonce_fwd(const void* q, int64_t ldq, const void* d, int64_t ldd, int n, int m, int k_dim, float scale,
                    const float* scale_dev, const float* rq, const float* rd, int label_offset, int label_stride, float* lse, int32_t* argmax,
                    float* label_logit, float* stats, void* workspace, cx_stream_t stream);
@@ -79,6 +79,74 @@ CX_API int cx_rows_to_bf16(const float* x, int64_t ldx, void* y_bf16, int64_t ld
  * g' = g * (g_prescaled ? 1 : inv_norm); accumulate != 0 adds into gx */
 CX_API int cx_l2norm_bwd(const float* x, int64_t ldx, const float* g, int64_t ldg, const float* inv_norm, float* gx,
                   int64_t ldgx, int rows, int k, int g_prescaled, int accumulate, cx_stream_t stream);
+
+/* ======================================================================================================== encoder ops
+ * Memory-bound kernels of the encoder fwd/bwd.  Activations are bf16 [rows, d] row-major (rows = packed non-pad tokens),
+ * LayerNorm parameters / statistics / parameter gradients are fp32.  d % 8 == 0, d <= 1024. */
+
+/* ---- fused (dropout-)add-LayerNorm (replaces flash-attn dropout_add_layer_norm: layers/block.py:422-431,453-462,
+ *      models/encoder/modeling_nomic_bert.py:531-535).  y = LN(a + b) * gamma + beta; b may be NULL;
+ *      stats[rows][2] = (mean, rstd) for the backward. */
+CX_API int cx_add_layernorm_fwd(const void* a, const void* b, const float* gamma, const float* beta, void* y, float* stats,
+                         int rows, int d, float eps, cx_stream_t stream);
+/* backward: z = a + b is recomputed, upstream gradient g = g1 + g2 (g2 may be NULL); writes dz (bf16, the gradient of
+ * both a and b) and ADDS the parameter gradients into dgamma/dbeta (pass both NULL to skip them).
+ * workspace: cx_layernorm_bwd_workspace_bytes(d). */
+CX_API size_t cx_layernorm_bwd_workspace_bytes(int d);
+CX_API int cx_add_layernorm_bwd(const void* a, const void* b, const void* g1, const void* g2, const float* gamma,
+                         const float* stats, void* dz, float* dgamma, float* dbeta, void* workspace, int rows, int d,
+                         cx_stream_t stream);
+/* ---- embeddings + emb_ln (layers/embedding.py:594-615 + modeling_nomic_bert.py:531-534): y = LN(word[ids] + type[type_ids]).
+ *      type_ids may be NULL (all zeros).  Backward scatters into the fp32 table gradients (atomic adds), ADDS dgamma/dbeta. */
+CX_API int cx_embed_layernorm_fwd(const int64_t* ids, const int64_t* type_ids, const void* word_emb, const void* type_emb,
+                           const float* gamma, const float* beta, void* y, float* stats, int rows, int d, float eps,
+                           cx_stream_t stream);
+CX_API int cx_embed_layernorm_bwd(const int64_t* ids, const int64_t* type_ids, const void* word_emb, const void* type_emb,
+                           const void* g1, const void* g2, const float* gamma, const float* stats, float* dword,
+                           float* dtype_emb, float* dgamma, float* dbeta, void* workspace, int rows, int d,
+                           int64_t padding_idx, cx_stream_t stream);
+/* ---- unpadded-token bookkeeping (flash-attn bert_padding: modeling_nomic_bert.py:333): pos[t] = t - cu_seqlens[seq(t)] */
+CX_API int cx_token_positions(const int32_t* cu_seqlens, int nseq, int32_t* pos, int32_t* seq_id, cx_stream_t stream);
+/* ---- rotary embedding, NeoX halves, in place on q and k of qkv [T,3,H,Dh] (layers/embedding.py:653-745);
+ *      cos/sin fp32 [max_pos, Dh/2]; backward != 0 applies the transpose rotation; slots [first_slot, first_slot +
+ *      num_slots) of {0 = q, 1 = k} are rotated. */
+CX_API int cx_rope_inplace(void* qkv, const int32_t* pos, const float* cos_t, const float* sin_t, int T, int H, int Dh,
+                    int backward, int first_slot, int num_slots, cx_stream_t stream);
+/* fp32 dQ accumulator [T,H*Dh] -> bf16 q-slot of dqkv [T,3,H,Dh] with the transpose rotation fused */
+CX_API int cx_dq_finalize_rope(const float* dq_acc, void* dqkv, const int32_t* pos, const float* cos_t, const float* sin_t,
+                        int T, int H, int Dh, cx_stream_t stream);
+/* ---- SwiGLU (layers/mlp.py:68-75): yg [T,2I] = [fc11(x) | fc12(x)];  out = y * silu(gate) */
+CX_API int cx_swiglu_fwd(const void* yg, void* out, int64_t T, int I, cx_stream_t stream);
+CX_API int cx_swiglu_bwd(const void* dout, const void* yg, void* dyg, int64_t T, int I, cx_stream_t stream);
+/* ---- MeanPooling over each packed sequence (modeling_biencoder.py:79-90) and its backward */
+CX_API int cx_mean_pool_fwd(const void* h, const int32_t* cu_seqlens, float* pooled, int nseq, int d, cx_stream_t stream);
+CX_API int cx_mean_pool_bwd(const float* dpooled, const int32_t* cu_seqlens, void* dh, int nseq, int d, cx_stream_t stream);
+/* ---- BiEncoder tail (modeling_biencoder.py:307-317): optional affine-free LN ("hamming"), cast to bf16, optional
+ *      F.normalize, fp32 out.  save[rows][3] = (mean, rstd, inv_norm). */
+CX_API int cx_embed_head_fwd(const float* pooled, float* out, float* save, int rows, int d, int hamming, int normalize,
+                      cx_stream_t stream);
+CX_API int cx_embed_head_bwd(const float* pooled, const float* gout, const float* save, float* gpooled, int rows, int d,
+                      int hamming, int normalize, cx_stream_t stream);
+/* ---- optimizer tail (optimizer.py:7-47, trainers/base.py:372-385) on flat fp32 buffers.
+ *      cx_grad_clip_coef: out2[0] = ||grad||_2, out2[1] = min(1, max_norm/(norm+1e-6)) (device scalars, no host sync).
+ *      cx_adamw_step: torch.optim.AdamW update, refreshes the bf16 shadow weights, optionally zeroes the gradient. */
+CX_API size_t cx_grad_clip_workspace_bytes(void);
+CX_API int cx_grad_clip_coef(const float* grad, int64_t n, float max_norm, float* out2, void* workspace, cx_stream_t stream);
+CX_API int cx_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, int64_t n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int step, const float* grad_scale_dev,
+                  float grad_scale, int zero_grad, cx_stream_t stream);
+CX_API int cx_cast_f32_bf16(const float* x, void* y, int64_t n, cx_stream_t stream);
+
+/* ---- varlen non-causal attention on tcgen05 (replaces flash_attn_varlen_qkvpacked_func: layers/attention.py:158-181)
+ * qkv [T,3,H,Dh] bf16 (RoPE already applied), cu_seqlens int32[nseq+1]; out [T,H,Dh] bf16; lse [H,T] fp32 (natural log).
+ * Dh == 64.  Backward: dqkv [T,3,H,Dh] bf16 (dk, dv written directly; dq through the fp32 accumulator dq_acc [T,H*Dh],
+ * which the caller zeroes and then finalises with cx_dq_finalize_rope or cx_dq_finalize). delta [H,T] fp32 scratch. */
+CX_API int cx_attn_fwd(const void* qkv, const int32_t* cu_seqlens, void* out, float* lse, int total_tokens, int nseq,
+                int max_seqlen, int H, int Dh, float softmax_scale, cx_stream_t stream);
+CX_API int cx_dq_finalize(const float* dq_acc, void* dqkv, int T, int H, int Dh, cx_stream_t stream);
+CX_API int cx_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const int32_t* cu_seqlens,
+                void* dqkv, float* dq_acc, float* delta, int total_tokens, int nseq, int max_seqlen, int H, int Dh,
+                float softmax_scale, cx_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -83,9 +83,10 @@ def clip_loss_fwd_bwd(query, document, scale: float, rank: int = 0, world_size: 
     dq = scale * (ds @ d)
     dd = scale * (ds.T @ q)
     dlogit = float(np.sum(ds * s))
+    dlogit_abs = float(np.sum(np.abs(ds * s)))  # scale of the cancelling sum (tolerance reference for tests)
     argmax = s.argmax(axis=1).astype(np.int64)  # first max wins, as ATen
     return dict(loss=loss, lse=lse, argmax=argmax, labels=labels,
-                accuracy=float(np.mean(argmax == labels)), dq=dq, dd=dd, dlogit=dlogit)
+                accuracy=float(np.mean(argmax == labels)), dq=dq, dd=dd, dlogit=dlogit, dlogit_abs=dlogit_abs)
 
 
 def clip_loss_multirank(queries, documents, scale: float, bidirectional: bool = False):

@@ -18,8 +18,8 @@ def test_exports_every_declared_symbol(lib):
 
 
 def test_workspace_size_is_pure_host_math(lib):
-    small = lib.cx_infonce_workspace_bytes(128, 128)
-    big = lib.cx_infonce_workspace_bytes(2048, 16384)
+    small = lib.cx_infonce_workspace_bytes(128, 128, 64)
+    big = lib.cx_infonce_workspace_bytes(2048, 16384, 768)
     assert 0 < small < big
     assert big >= 2048 * 16384 * 2
 
@@ -45,3 +45,13 @@ def test_cpu_tensors_are_rejected_not_emulated():
             clip_loss(q, q, lambda x: x)
     finally:
         dist.destroy_process_group()
+
+
+def test_library_is_not_stale():
+    """The in-tree .so (which is what travels to the GPU box) must be newer than every source it is built from."""
+    import os
+    from contrastors_b200 import build
+    lib_m = os.path.getmtime(_lib.LIB_PATH)
+    srcs = [os.path.join(build.CSRC, f) for f in os.listdir(build.CSRC)] + [_lib.HEADER]
+    stale = [s for s in srcs if os.path.getmtime(s) > lib_m]
+    assert not stale, f"rebuild with `python -m contrastors_b200.build`: {stale}"

