@@ -40,32 +40,47 @@ struct BF8 {  // 8 bf16 = 16 bytes
 
 constexpr int kLnMaxVec = 4;  // up to d = 32 lanes * 8 * 4 = 1024 columns per row
 
+__device__ __forceinline__ void load8f(const float* __restrict__ p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
 // ---------------------------------------------------------------------------------------------- LayerNorm forward
 // z = a (+ b) ; y = (z - mean) * rstd * gamma + beta.  EMBED: a-row = word_emb[ids[r]] + type_emb[type_ids[r]].
-template <bool EMBED>
-__global__ void add_layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
-                                         const int64_t* __restrict__ ids, const int64_t* __restrict__ type_ids,
-                                         const __nv_bfloat16* __restrict__ type_emb, const float* __restrict__ gamma,
-                                         const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
-                                         float* __restrict__ stats, int rows, int d, float eps) {
+// One warp per row; NV = ceil(d / 256) 16-byte vectors per lane, all loads issued before any math.
+template <bool EMBED, int NV>
+__global__ void __launch_bounds__(256)
+add_layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                         const int64_t* __restrict__ ids, const int64_t* __restrict__ type_ids,
+                         const __nv_bfloat16* __restrict__ type_emb, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ stats, int rows,
+                         int d, float eps) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const __nv_bfloat16* ar = EMBED ? a + (size_t)ids[row] * d : a + (size_t)row * d;
   const __nv_bfloat16* br = EMBED ? type_emb + (size_t)(type_ids ? type_ids[row] : 0) * d : (b ? b + (size_t)row * d : nullptr);
-  float z[kLnMaxVec][8];
-  float sum = 0.f;
+  BF8 ra[NV], rb[NV];
 #pragma unroll
-  for (int c = 0; c < kLnMaxVec; ++c) {
+  for (int c = 0; c < NV; ++c) {
     const int col = (c * 32 + lane) * 8;
     if (col < d) {
-      BF8 va, vb;
-      va.raw = *reinterpret_cast<const uint4*>(ar + col);
-      va.unpack(z[c]);
+      ra[c].raw = *reinterpret_cast<const uint4*>(ar + col);
+      if (br != nullptr) rb[c].raw = *reinterpret_cast<const uint4*>(br + col);
+    }
+  }
+  float z[NV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    if (col < d) {
+      ra[c].unpack(z[c]);
       if (br != nullptr) {
         float t[8];
-        vb.raw = *reinterpret_cast<const uint4*>(br + col);
-        vb.unpack(t);
+        rb[c].unpack(t);
 #pragma unroll
         for (int i = 0; i < 8; ++i) z[c][i] += t[i];
       }
@@ -76,7 +91,7 @@ __global__ void add_layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ a, co
   const float mean = warp_sum(sum) / d;
   float var = 0.f;
 #pragma unroll
-  for (int c = 0; c < kLnMaxVec; ++c) {
+  for (int c = 0; c < NV; ++c) {
     const int col = (c * 32 + lane) * 8;
     if (col < d) {
 #pragma unroll
@@ -92,14 +107,18 @@ __global__ void add_layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ a, co
     stats[2 * (size_t)row + 1] = rstd;
   }
 #pragma unroll
-  for (int c = 0; c < kLnMaxVec; ++c) {
+  for (int c = 0; c < NV; ++c) {
     const int col = (c * 32 + lane) * 8;
     if (col < d) {
-      float o[8];
+      float o[8], gm[8], bt[8];
+      if (gamma != nullptr) {
+        load8f(gamma + col, gm);
+        load8f(beta + col, bt);
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float v = (z[c][i] - mean) * rstd;
-        if (gamma != nullptr) v = fmaf(v, gamma[col + i], beta[col + i]);
+        if (gamma != nullptr) v = fmaf(v, gm[i], bt[i]);
         o[i] = v;
       }
       BF8 vo;
@@ -110,57 +129,76 @@ __global__ void add_layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ a, co
 }
 
 // ---------------------------------------------------------------------------------------------- LayerNorm backward
-// g = g1 (+ g2); dz = rstd * (g*gamma - mean_d(g*gamma) - xhat * mean_d(g*gamma*xhat)); per-CTA dgamma/dbeta partials.
-// EMBED: z is recomputed from the embedding tables and dz is scattered (atomicAdd fp32) into the table gradients.
-template <bool EMBED>
-__global__ void add_layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
-                                         const int64_t* __restrict__ ids, const int64_t* __restrict__ type_ids,
-                                         const __nv_bfloat16* __restrict__ type_emb, const __nv_bfloat16* __restrict__ g1,
-                                         const __nv_bfloat16* __restrict__ g2, const float* __restrict__ gamma,
-                                         const float* __restrict__ stats, __nv_bfloat16* __restrict__ dz,
-                                         float* __restrict__ dword, float* __restrict__ dtype_emb,
-                                         float* __restrict__ partials, int rows, int d, int64_t padding_idx) {
-  extern __shared__ float sh[];  // [warps][2][d]
+// g = g1 (+ g2); dz = rstd * (g*gamma - mean_d(g*gamma) - xhat * mean_d(g*gamma*xhat)); per-CTA partials of
+// dgamma / dbeta (and, EMBED with type_ids == NULL, of the type-0 embedding row gradient) in a fixed order.
+// EMBED: z is recomputed from the tables and dz is scattered (red.add fp32) into the word-embedding gradient.
+template <bool EMBED, int NV>
+__global__ void __launch_bounds__(256)
+add_layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                         const int64_t* __restrict__ ids, const int64_t* __restrict__ type_ids,
+                         const __nv_bfloat16* __restrict__ type_emb, const __nv_bfloat16* __restrict__ g1,
+                         const __nv_bfloat16* __restrict__ g2, const float* __restrict__ gamma,
+                         const float* __restrict__ stats, __nv_bfloat16* __restrict__ dz, float* __restrict__ dword,
+                         float* __restrict__ dtype_emb, float* __restrict__ partials, int rows, int d, int64_t padding_idx) {
+  extern __shared__ float sh[];  // [warps][NP][d]
+  constexpr int NP = EMBED ? 3 : 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  float dg[kLnMaxVec][8], db[kLnMaxVec][8];
+  float dg[NV][8], db[NV][8], dt[EMBED ? NV : 1][8];
 #pragma unroll
-  for (int c = 0; c < kLnMaxVec; ++c)
+  for (int c = 0; c < NV; ++c)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) dg[c][i] = db[c][i] = 0.f;
+    for (int i = 0; i < 8; ++i) {
+      dg[c][i] = db[c][i] = 0.f;
+      if (EMBED) dt[c][i] = 0.f;
+    }
+  float gm[NV][8];
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+    const int col = (c * 32 + lane) * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) gm[c][i] = 1.f;
+    if (col < d && gamma != nullptr) load8f(gamma + col, gm[c]);
+  }
 
   for (int row = blockIdx.x * nwarps + warp; row < rows; row += gridDim.x * nwarps) {
     const __nv_bfloat16* ar = EMBED ? a + (size_t)ids[row] * d : a + (size_t)row * d;
     const int64_t tid = EMBED ? (type_ids ? type_ids[row] : 0) : 0;
     const __nv_bfloat16* br = EMBED ? type_emb + (size_t)tid * d : (b ? b + (size_t)row * d : nullptr);
     const float mean = stats[2 * (size_t)row], rstd = stats[2 * (size_t)row + 1];
-    float xh[kLnMaxVec][8], wg[kLnMaxVec][8];
-    float s1 = 0.f, s2 = 0.f;
+    BF8 ra[NV], rb[NV], rg1[NV], rg2[NV];
 #pragma unroll
-    for (int c = 0; c < kLnMaxVec; ++c) {
+    for (int c = 0; c < NV; ++c) {
       const int col = (c * 32 + lane) * 8;
       if (col < d) {
-        BF8 v;
+        ra[c].raw = *reinterpret_cast<const uint4*>(ar + col);
+        if (br != nullptr) rb[c].raw = *reinterpret_cast<const uint4*>(br + col);
+        rg1[c].raw = *reinterpret_cast<const uint4*>(g1 + (size_t)row * d + col);
+        if (g2 != nullptr) rg2[c].raw = *reinterpret_cast<const uint4*>(g2 + (size_t)row * d + col);
+      }
+    }
+    float xh[NV][8], wg[NV][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < d) {
         float z[8], t[8], g[8];
-        v.raw = *reinterpret_cast<const uint4*>(ar + col);
-        v.unpack(z);
+        ra[c].unpack(z);
         if (br != nullptr) {
-          v.raw = *reinterpret_cast<const uint4*>(br + col);
-          v.unpack(t);
+          rb[c].unpack(t);
 #pragma unroll
           for (int i = 0; i < 8; ++i) z[i] += t[i];
         }
-        v.raw = *reinterpret_cast<const uint4*>(g1 + (size_t)row * d + col);
-        v.unpack(g);
+        rg1[c].unpack(g);
         if (g2 != nullptr) {
-          v.raw = *reinterpret_cast<const uint4*>(g2 + (size_t)row * d + col);
-          v.unpack(t);
+          rg2[c].unpack(t);
 #pragma unroll
           for (int i = 0; i < 8; ++i) g[i] += t[i];
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float x = (z[i] - mean) * rstd;
-          const float w = g[i] * (gamma != nullptr ? gamma[col + i] : 1.f);
+          const float w = g[i] * gm[c][i];
           xh[c][i] = x;
           wg[c][i] = w;
           s1 += w;
@@ -173,7 +211,7 @@ __global__ void add_layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ a, co
     s1 = warp_sum(s1) / d;
     s2 = warp_sum(s2) / d;
 #pragma unroll
-    for (int c = 0; c < kLnMaxVec; ++c) {
+    for (int c = 0; c < NV; ++c) {
       const int col = (c * 32 + lane) * 8;
       if (col < d) {
         float o[8];
@@ -181,12 +219,12 @@ __global__ void add_layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ a, co
         for (int i = 0; i < 8; ++i) o[i] = (wg[c][i] - s1 - xh[c][i] * s2) * rstd;
         if (EMBED) {
           float* dw = dword + (size_t)ids[row] * d + col;
-          float* dt = dtype_emb + (size_t)tid * d + col;
           const bool pad = ids[row] == padding_idx;  // nn.Embedding(padding_idx=...) never receives a gradient there
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             if (!pad) atomicAdd(dw + i, o[i]);
-            atomicAdd(dt + i, o[i]);
+            if (type_ids == nullptr) dt[c][i] += o[i];  // all tokens are type 0: column sum, reduced below
+            else atomicAdd(dtype_emb + (size_t)tid * d + col + i, o[i]);
           }
         } else {
           BF8 vo;
@@ -197,35 +235,38 @@ __global__ void add_layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ a, co
     }
   }
   if (partials == nullptr) return;
-  // CTA reduction of dgamma/dbeta partials (fixed order => deterministic)
+  // CTA reduction of the column-sum partials (fixed order => deterministic)
 #pragma unroll
-  for (int c = 0; c < kLnMaxVec; ++c) {
+  for (int c = 0; c < NV; ++c) {
     const int col = (c * 32 + lane) * 8;
     if (col < d) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        sh[(warp * 2 + 0) * d + col + i] = dg[c][i];
-        sh[(warp * 2 + 1) * d + col + i] = db[c][i];
+        sh[(warp * NP + 0) * d + col + i] = dg[c][i];
+        sh[(warp * NP + 1) * d + col + i] = db[c][i];
+        if (EMBED) sh[(warp * NP + 2) * d + col + i] = dt[c][i];
       }
     }
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < 2 * d; j += blockDim.x) {
+  for (int j = threadIdx.x; j < NP * d; j += blockDim.x) {
     const int which = j / d, col = j % d;
     float acc = 0.f;
-    for (int w = 0; w < nwarps; ++w) acc += sh[(w * 2 + which) * d + col];
-    partials[(size_t)blockIdx.x * 2 * d + j] = acc;
+    for (int w = 0; w < nwarps; ++w) acc += sh[(w * NP + which) * d + col];
+    partials[(size_t)blockIdx.x * NP * d + j] = acc;
   }
 }
 
-__global__ void ln_param_grad_reduce_kernel(const float* __restrict__ partials, int nblocks, int d, float* __restrict__ dgamma,
-                                            float* __restrict__ dbeta) {
+// out_k[j] += sum over blocks of partials[b][k][j], k < np (dgamma, dbeta, and optionally the type-0 embedding row)
+__global__ void ln_param_grad_reduce_kernel(const float* __restrict__ partials, int nblocks, int d, int np, float* __restrict__ o0,
+                                            float* __restrict__ o1, float* __restrict__ o2) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= 2 * d) return;
+  if (j >= np * d) return;
   float acc = 0.f;
-  for (int b = 0; b < nblocks; ++b) acc += partials[(size_t)b * 2 * d + j];
-  if (j < d) dgamma[j] += acc;
-  else dbeta[j - d] += acc;
+  for (int b = 0; b < nblocks; ++b) acc += partials[(size_t)b * np * d + j];
+  const int which = j / d, col = j % d;
+  float* dst = which == 0 ? o0 : (which == 1 ? o1 : o2);
+  if (dst != nullptr) dst[col] += acc;
 }
 
 // ---------------------------------------------------------------------------------------------- token bookkeeping
@@ -556,8 +597,16 @@ extern "C" int cx_add_layernorm_fwd(const void* a, const void* b, const float* g
   CX_REQUIRE(a && y, "cx_add_layernorm_fwd: null pointer");
   CX_REQUIRE(d % 8 == 0 && d <= 256 * kLnMaxVec, "cx_add_layernorm_fwd: d must be a multiple of 8 and <= 1024");
   if (rows <= 0) return 0;
-  add_layernorm_fwd_kernel<false><<<ln_rows_grid(rows, 8), 256, 0, STREAM>>>(
-      (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, nullptr, nullptr, nullptr, gamma, beta, (__nv_bfloat16*)y, stats, rows, d, eps);
+#define CX_LN_FWD(NV_)                                                                                              \
+  add_layernorm_fwd_kernel<false, NV_><<<ln_rows_grid(rows, 8), 256, 0, STREAM>>>(                                  \
+      (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, nullptr, nullptr, nullptr, gamma, beta, (__nv_bfloat16*)y, stats, rows, d, eps)
+  switch ((d + 255) / 256) {
+    case 1: CX_LN_FWD(1); break;
+    case 2: CX_LN_FWD(2); break;
+    case 3: CX_LN_FWD(3); break;
+    default: CX_LN_FWD(4); break;
+  }
+#undef CX_LN_FWD
   CX_LAUNCH_CHECK();
   return 0;
 }
@@ -568,9 +617,17 @@ extern "C" int cx_embed_layernorm_fwd(const int64_t* ids, const int64_t* type_id
   CX_REQUIRE(ids && word_emb && type_emb && y, "cx_embed_layernorm_fwd: null pointer");
   CX_REQUIRE(d % 8 == 0 && d <= 256 * kLnMaxVec, "cx_embed_layernorm_fwd: d must be a multiple of 8 and <= 1024");
   if (rows <= 0) return 0;
-  add_layernorm_fwd_kernel<true><<<ln_rows_grid(rows, 8), 256, 0, STREAM>>>(
-      (const __nv_bfloat16*)word_emb, nullptr, ids, type_ids, (const __nv_bfloat16*)type_emb, gamma, beta, (__nv_bfloat16*)y,
-      stats, rows, d, eps);
+#define CX_LN_FWD(NV_)                                                                                              \
+  add_layernorm_fwd_kernel<true, NV_><<<ln_rows_grid(rows, 8), 256, 0, STREAM>>>(                                   \
+      (const __nv_bfloat16*)word_emb, nullptr, ids, type_ids, (const __nv_bfloat16*)type_emb, gamma, beta, (__nv_bfloat16*)y, \
+      stats, rows, d, eps)
+  switch ((d + 255) / 256) {
+    case 1: CX_LN_FWD(1); break;
+    case 2: CX_LN_FWD(2); break;
+    case 3: CX_LN_FWD(3); break;
+    default: CX_LN_FWD(4); break;
+  }
+#undef CX_LN_FWD
   CX_LAUNCH_CHECK();
   return 0;
 }
@@ -581,7 +638,32 @@ static int ln_bwd_grid(int rows) {
   return g < cap ? (g < 1 ? 1 : g) : cap;
 }
 
-extern "C" size_t cx_layernorm_bwd_workspace_bytes(int d) { return (size_t)2 * sm_count() * 2 * d * sizeof(float); }
+extern "C" size_t cx_layernorm_bwd_workspace_bytes(int d) { return (size_t)2 * sm_count() * 3 * d * sizeof(float); }
+
+template <bool EMBED, int NV>
+static int ln_bwd_launch(int grid, size_t smem, cudaStream_t st, const __nv_bfloat16* a, const __nv_bfloat16* b, const int64_t* ids,
+                         const int64_t* type_ids, const __nv_bfloat16* type_emb, const __nv_bfloat16* g1, const __nv_bfloat16* g2,
+                         const float* gamma, const float* stats, __nv_bfloat16* dz, float* dword, float* dtype_emb, float* partials,
+                         int rows, int d, int64_t padding_idx) {
+  static bool configured = false;
+  if (!configured) {
+    CX_CUDA_CHECK(cudaFuncSetAttribute(add_layernorm_bwd_kernel<EMBED, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4));
+    configured = true;
+  }
+  add_layernorm_bwd_kernel<EMBED, NV><<<grid, 256, smem, st>>>(a, b, ids, type_ids, type_emb, g1, g2, gamma, stats, dz, dword, dtype_emb,
+                                                               partials, rows, d, padding_idx);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+template <bool EMBED, typename... Args>
+static int ln_bwd_dispatch(int d, Args... args) {
+  switch ((d + 255) / 256) {
+    case 1: return ln_bwd_launch<EMBED, 1>(args...);
+    case 2: return ln_bwd_launch<EMBED, 2>(args...);
+    case 3: return ln_bwd_launch<EMBED, 3>(args...);
+    default: return ln_bwd_launch<EMBED, 4>(args...);
+  }
+}
 
 extern "C" int cx_add_layernorm_bwd(const void* a, const void* b, const void* g1, const void* g2, const float* gamma,
                                     const float* stats, void* dz, float* dgamma, float* dbeta, void* workspace, int rows, int d,
@@ -593,18 +675,13 @@ extern "C" int cx_add_layernorm_bwd(const void* a, const void* b, const void* g1
   if (rows <= 0) return 0;
   const int grid = ln_bwd_grid(rows);
   const size_t smem = (size_t)8 * 2 * d * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    CX_CUDA_CHECK(cudaFuncSetAttribute(add_layernorm_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4));
-    CX_CUDA_CHECK(cudaFuncSetAttribute(add_layernorm_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4));
-    configured = true;
-  }
-  add_layernorm_bwd_kernel<false><<<grid, 256, smem, STREAM>>>(
-      (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, nullptr, nullptr, nullptr, (const __nv_bfloat16*)g1,
-      (const __nv_bfloat16*)g2, gamma, stats, (__nv_bfloat16*)dz, nullptr, nullptr, dgamma ? (float*)workspace : nullptr, rows, d, -1);
-  CX_LAUNCH_CHECK();
+  int rc = ln_bwd_dispatch<false>(d, grid, smem, STREAM, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (const int64_t*)nullptr,
+                                  (const int64_t*)nullptr, (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)g1,
+                                  (const __nv_bfloat16*)g2, gamma, stats, (__nv_bfloat16*)dz, (float*)nullptr, (float*)nullptr,
+                                  dgamma ? (float*)workspace : (float*)nullptr, rows, d, (int64_t)-1);
+  if (rc) return rc;
   if (dgamma) {
-    ln_param_grad_reduce_kernel<<<(2 * d + 255) / 256, 256, 0, STREAM>>>((const float*)workspace, grid, d, dgamma, dbeta);
+    ln_param_grad_reduce_kernel<<<(2 * d + 255) / 256, 256, 0, STREAM>>>((const float*)workspace, grid, d, 2, dgamma, dbeta, nullptr);
     CX_LAUNCH_CHECK();
   }
   return 0;
@@ -619,17 +696,14 @@ extern "C" int cx_embed_layernorm_bwd(const int64_t* ids, const int64_t* type_id
   CX_REQUIRE(d % 8 == 0 && d <= 256 * kLnMaxVec, "cx_embed_layernorm_bwd: d must be a multiple of 8 and <= 1024");
   if (rows <= 0) return 0;
   const int grid = ln_bwd_grid(rows);
-  const size_t smem = (size_t)8 * 2 * d * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    CX_CUDA_CHECK(cudaFuncSetAttribute(add_layernorm_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4));
-    configured = true;
-  }
-  add_layernorm_bwd_kernel<true><<<grid, 256, smem, STREAM>>>(
-      (const __nv_bfloat16*)word_emb, nullptr, ids, type_ids, (const __nv_bfloat16*)type_emb, (const __nv_bfloat16*)g1,
-      (const __nv_bfloat16*)g2, gamma, stats, nullptr, dword, dtype_emb, (float*)workspace, rows, d, padding_idx);
-  CX_LAUNCH_CHECK();
-  ln_param_grad_reduce_kernel<<<(2 * d + 255) / 256, 256, 0, STREAM>>>((const float*)workspace, grid, d, dgamma, dbeta);
+  const size_t smem = (size_t)8 * 3 * d * sizeof(float);
+  int rc = ln_bwd_dispatch<true>(d, grid, smem, STREAM, (const __nv_bfloat16*)word_emb, (const __nv_bfloat16*)nullptr, ids, type_ids,
+                                 (const __nv_bfloat16*)type_emb, (const __nv_bfloat16*)g1, (const __nv_bfloat16*)g2, gamma, stats,
+                                 (__nv_bfloat16*)nullptr, dword, dtype_emb, (float*)workspace, rows, d, padding_idx);
+  if (rc) return rc;
+  // type_ids == NULL: every token is type 0, its embedding-row gradient is the third column-sum partial
+  ln_param_grad_reduce_kernel<<<(3 * d + 255) / 256, 256, 0, STREAM>>>((const float*)workspace, grid, d, 3, dgamma, dbeta,
+                                                                       type_ids == nullptr ? dtype_emb : nullptr);
   CX_LAUNCH_CHECK();
   return 0;
 }

@@ -5,15 +5,16 @@ namespace cx {
 
 int gemm_block_n(int N) { return (N % 256 == 0) ? 256 : 128; }
 
-int gemm_grid(int M, int N, int splits) {
-  const int bn = gemm_block_n(N);
+int gemm_grid(int M, int N, int splits, int tile_n) {
+  const int bn = tile_n > 0 ? tile_n : gemm_block_n(N);
   const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + bn - 1) / bn) * splits;
   const int sms = sm_count();
   return tiles < sms ? tiles : sms;
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int MODE, bool OUT_F32, bool ACCUM>
-static int launch_one(const GemmArgs& g, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC) {
+static int launch_one(const GemmArgs& g, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                      const CUtensorMap& tmD) {
   auto kern = gemm_kernel<BLOCK_N, A_MN, B_MN, MODE, OUT_F32, ACCUM>;
   constexpr int smem = GemmSmem<BLOCK_N>::kTotal;
   static bool configured = false;  // per instantiation
@@ -21,36 +22,40 @@ static int launch_one(const GemmArgs& g, const CUtensorMap& tmA, const CUtensorM
     CX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  const int grid = gemm_grid(g.M, g.N, g.splits);
-  kern<<<grid, kGemmThreads, smem, g.stream>>>(tmA, tmB, tmC, g.M, g.N, g.K, g.splits, g.ep);
+  const int grid = gemm_grid(g.M, g.N, g.splits, MODE == EPI_SWIGLU ? BLOCK_N / 2 : 0);
+  kern<<<grid, kGemmThreads, smem, g.stream>>>(tmA, tmB, tmC, tmD, g.M, g.N, g.K, g.splits, g.ep);
   CX_LAUNCH_CHECK();
   return 0;
 }
 
 template <int BLOCK_N, int MODE, bool OUT_F32, bool ACCUM>
-static int launch_majors(const GemmArgs& g, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c) {
-  if (MODE != EPI_STORE) {  // InfoNCE epilogues only exist for K-major operands
-    if (g.a_mn || g.b_mn) return fail(CX_ERR_UNSUPPORTED, "InfoNCE epilogues need K-major operands");
-    return launch_one<BLOCK_N, false, false, MODE, OUT_F32, ACCUM>(g, a, b, c);
+static int launch_majors(const GemmArgs& g, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
+                         const CUtensorMap& d) {
+  if (MODE != EPI_STORE) {  // the fused epilogues only exist for K-major operands
+    if (g.a_mn || g.b_mn) return fail(CX_ERR_UNSUPPORTED, "fused epilogues need K-major operands");
+    return launch_one<BLOCK_N, false, false, MODE, OUT_F32, ACCUM>(g, a, b, c, d);
   } else {
-    if (!g.a_mn && !g.b_mn) return launch_one<BLOCK_N, false, false, EPI_STORE, OUT_F32, ACCUM>(g, a, b, c);
-    if (!g.a_mn && g.b_mn) return launch_one<BLOCK_N, false, true, EPI_STORE, OUT_F32, ACCUM>(g, a, b, c);
-    if (g.a_mn && !g.b_mn) return launch_one<BLOCK_N, true, false, EPI_STORE, OUT_F32, ACCUM>(g, a, b, c);
-    return launch_one<BLOCK_N, true, true, EPI_STORE, OUT_F32, ACCUM>(g, a, b, c);
+    if (!g.a_mn && !g.b_mn) return launch_one<BLOCK_N, false, false, EPI_STORE, OUT_F32, ACCUM>(g, a, b, c, d);
+    if (!g.a_mn && g.b_mn) return launch_one<BLOCK_N, false, true, EPI_STORE, OUT_F32, ACCUM>(g, a, b, c, d);
+    if (g.a_mn && !g.b_mn) return launch_one<BLOCK_N, true, false, EPI_STORE, OUT_F32, ACCUM>(g, a, b, c, d);
+    return launch_one<BLOCK_N, true, true, EPI_STORE, OUT_F32, ACCUM>(g, a, b, c, d);
   }
 }
 
 template <int BLOCK_N>
-static int launch_bn(const GemmArgs& g, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c) {
+static int launch_bn(const GemmArgs& g, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const CUtensorMap& d) {
   switch (g.mode) {
     case EPI_NCE_STATS:
-      return launch_majors<BLOCK_N, EPI_NCE_STATS, false, false>(g, a, b, c);
+      return launch_majors<BLOCK_N, EPI_NCE_STATS, false, false>(g, a, b, c, d);
     case EPI_NCE_DS:
-      return launch_majors<BLOCK_N, EPI_NCE_DS, false, false>(g, a, b, c);
+      return launch_majors<BLOCK_N, EPI_NCE_DS, false, false>(g, a, b, c, d);
+    case EPI_SWIGLU:
+      if (BLOCK_N != 256) return fail(CX_ERR_INVALID, "swiglu epilogue uses 256-column accumulators");
+      return launch_majors<256, EPI_SWIGLU, false, false>(g, a, b, c, d);
     case EPI_STORE:
-      if (!g.out_f32) return launch_majors<BLOCK_N, EPI_STORE, false, false>(g, a, b, c);
-      if (!g.accumulate) return launch_majors<BLOCK_N, EPI_STORE, true, false>(g, a, b, c);
-      return launch_majors<BLOCK_N, EPI_STORE, true, true>(g, a, b, c);
+      if (!g.out_f32) return launch_majors<BLOCK_N, EPI_STORE, false, false>(g, a, b, c, d);
+      if (!g.accumulate) return launch_majors<BLOCK_N, EPI_STORE, true, false>(g, a, b, c, d);
+      return launch_majors<BLOCK_N, EPI_STORE, true, true>(g, a, b, c, d);
   }
   return fail(CX_ERR_INVALID, "bad epilogue mode");
 }
@@ -59,7 +64,7 @@ int launch_gemm(const GemmArgs& g_in) {
   GemmArgs g = g_in;
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return fail(CX_ERR_INVALID, "gemm: empty problem");
   if (g.accumulate && !g.out_f32) return fail(CX_ERR_INVALID, "gemm: accumulate needs an fp32 output");
-  const int bn = gemm_block_n(g.N);
+  const int bn = (g.mode == EPI_SWIGLU) ? 256 : gemm_block_n(g.N);
   {
     // split-K: fp32 outputs only (partials are combined by TMA reduce-add at L2)
     const int tiles = ((g.M + kBlockM - 1) / kBlockM) * ((g.N + bn - 1) / bn);
@@ -88,10 +93,17 @@ int launch_gemm(const GemmArgs& g_in) {
   if (!g.a_mn) rc = make_tmap_2d(&tmA, BF, 2, g.A, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)g.lda * 2, kBlockK, kBlockM, SW);
   else rc = make_tmap_2d(&tmA, BF, 2, g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda * 2, 64, kBlockK, SW);
   if (rc) return rc;
-  if (!g.b_mn) rc = make_tmap_2d(&tmB, BF, 2, g.B, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb * 2, kBlockK, (uint32_t)bn, SW);
+  if (g.mode == EPI_SWIGLU) rc = make_tmap_2d(&tmB, BF, 2, g.B, (uint64_t)g.K, (uint64_t)2 * g.N, (uint64_t)g.ldb * 2, kBlockK, 128, SW);
+  else if (!g.b_mn) rc = make_tmap_2d(&tmB, BF, 2, g.B, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb * 2, kBlockK, (uint32_t)bn, SW);
   else rc = make_tmap_2d(&tmB, BF, 2, g.B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb * 2, 64, kBlockK, SW);
   if (rc) return rc;
-  if (g.mode == EPI_NCE_STATS) {
+  CUtensorMap tmD;
+  if (g.mode == EPI_SWIGLU) {
+    rc = make_tmap_2d(&tmC, BF, 2, g.ep.act_out, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ep.ld_act * 2, 64, kBlockM, SW);
+    if (rc) return rc;
+    if (g.ep.yg_out != nullptr)
+      rc = make_tmap_2d(&tmD, BF, 2, g.ep.yg_out, (uint64_t)2 * g.N, (uint64_t)g.M, (uint64_t)g.ep.ld_yg * 2, 64, kBlockM, SW);
+  } else if (g.mode == EPI_NCE_STATS) {
     tmC = tmA;
   } else if (g.out_f32) {
     rc = make_tmap_2d(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.C, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldc * 4, 32, kBlockM, SW);
@@ -99,7 +111,8 @@ int launch_gemm(const GemmArgs& g_in) {
     rc = make_tmap_2d(&tmC, BF, 2, g.C, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldc * 2, 64, kBlockM, SW);
   }
   if (rc) return rc;
-  return bn == 256 ? launch_bn<256>(g, tmA, tmB, tmC) : launch_bn<128>(g, tmA, tmB, tmC);
+  if (g.mode != EPI_SWIGLU || g.ep.yg_out == nullptr) tmD = tmC;
+  return bn == 256 ? launch_bn<256>(g, tmA, tmB, tmC, tmD) : launch_bn<128>(g, tmA, tmB, tmC, tmD);
 }
 
 }  // namespace cx
@@ -119,6 +132,26 @@ extern "C" int cx_gemm_bf16(const void* A, const void* B, void* C, int M, int N,
   g.accumulate = accumulate != 0;
   g.mode = cx::EPI_STORE;
   g.ep.alpha = alpha;
+  g.stream = static_cast<cudaStream_t>(stream);
+  return cx::launch_gemm(g);
+}
+
+extern "C" int cx_gemm_swiglu(const void* x, const void* w1, void* act_out, void* yg_out, int M, int I, int K, int64_t ldx,
+                              int64_t ldw, int64_t ld_act, int64_t ld_yg, cx_stream_t stream) {
+  CX_REQUIRE(x && w1 && act_out, "cx_gemm_swiglu: null pointer");
+  CX_REQUIRE(I % 128 == 0, "cx_gemm_swiglu: the gated width must be a multiple of 128");
+  CX_REQUIRE(ld_act % 8 == 0 && (yg_out == nullptr || ld_yg % 8 == 0), "cx_gemm_swiglu: output rows must be 16-byte aligned");
+  cx::GemmArgs g{};
+  g.A = x; g.B = w1; g.C = act_out;
+  g.M = M; g.N = I; g.K = K;
+  g.a_mn = false; g.b_mn = false;
+  g.lda = ldx; g.ldb = ldw; g.ldc = ld_act;
+  g.out_f32 = false; g.accumulate = false; g.splits = 1;
+  g.mode = cx::EPI_SWIGLU;
+  g.ep.act_out = reinterpret_cast<__nv_bfloat16*>(act_out);
+  g.ep.ld_act = ld_act;
+  g.ep.yg_out = reinterpret_cast<__nv_bfloat16*>(yg_out);
+  g.ep.ld_yg = ld_yg;
   g.stream = static_cast<cudaStream_t>(stream);
   return cx::launch_gemm(g);
 }

@@ -15,6 +15,8 @@
 // Epilogue modes:
 //   EPI_STORE      C = alpha * acc  as bf16 or fp32 through a swizzled smem stage + TMA store (or TMA reduce-add)
 //   EPI_NCE_STATS  InfoNCE forward: per-row (max, sum-exp, first-argmax, label logit) partials per column tile
+//   EPI_SWIGLU     gated MLP first layer: B tile = 128 rows of fc11 (y) + the matching 128 rows of fc12 (gate);
+//                  epilogue writes out = y * silu(gate) (bf16 [M, N]) and optionally the pre-activations [y | gate]
 //   EPI_NCE_DS     InfoNCE backward stage 1: dS = coef * (softmax - onehot) (x rq_i rd_j) stored as bf16, plus
 //                  per-thread partial of sum dS*s (the logit-scale gradient)
 #pragma once
@@ -23,7 +25,7 @@
 
 namespace cx {
 
-enum EpiMode { EPI_STORE = 0, EPI_NCE_STATS = 1, EPI_NCE_DS = 2 };
+enum EpiMode { EPI_STORE = 0, EPI_NCE_STATS = 1, EPI_NCE_DS = 2, EPI_SWIGLU = 3 };
 
 struct EpiParams {
   float alpha = 1.f;
@@ -44,6 +46,11 @@ struct EpiParams {
   int* part_arg = nullptr;     // [2 * n_col_tiles][M]
   float* label_logit = nullptr;  // [M]
   float* dlogit_part = nullptr;  // [gridDim.x]
+  // EPI_SWIGLU (direct global stores; N = number of gated output columns)
+  __nv_bfloat16* act_out = nullptr;  // [M, N]
+  int64_t ld_act = 0;
+  __nv_bfloat16* yg_out = nullptr;   // [M, 2N] = [y | gate], nullptr = do not keep the pre-activations
+  int64_t ld_yg = 0;
   int ab_f16 = 0;  // A and B operands hold IEEE fp16 instead of bf16 (kind::f16 wants one input type): fp16 dS path
   int ds_f16 = 0;  // EPI_NCE_DS: store (softmax - onehot) UNSCALED as fp16 (11-bit mantissa) instead of coef*(...) as bf16
 };
@@ -67,7 +74,8 @@ struct GemmSmem {
 template <int BLOCK_N, bool A_MN, bool B_MN, int MODE, bool OUT_F32, bool ACCUM>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ CUtensorMap tmC, int M, int N, int K, int splits, EpiParams ep) {
+            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD, int M, int N, int K,
+            int splits, EpiParams ep) {
   using S = GemmSmem<BLOCK_N>;
   constexpr int kStages = S::kStages;
   constexpr uint32_t kTmemCols = 2 * BLOCK_N;
@@ -86,7 +94,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int m_tiles = (M + kBlockM - 1) / kBlockM;
-  const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+  constexpr int TILE_N = (MODE == EPI_SWIGLU) ? BLOCK_N / 2 : BLOCK_N;  // output columns per tile
+  const int n_tiles = (N + TILE_N - 1) / TILE_N;
   const int num_tiles = m_tiles * n_tiles * splits;  // split-K slices are separate work items (reduce-add epilogue)
   const int num_kb = (K + kBlockK - 1) / kBlockK;
 
@@ -94,6 +103,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (MODE != EPI_NCE_STATS) tma_prefetch_desc(&tmC);
+    if (MODE == EPI_SWIGLU) tma_prefetch_desc(&tmD);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -120,7 +130,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mn = tile / splits, ks = tile % splits;
         const int m0 = (mn / n_tiles) * kBlockM;
-        const int n0 = (mn % n_tiles) * BLOCK_N;
+        const int n0 = (mn % n_tiles) * TILE_N;
         const int kb0 = (int)((long long)ks * num_kb / splits), kb1 = (int)((long long)(ks + 1) * num_kb / splits);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -133,7 +143,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int i = 0; i < kBlockM / 64; ++i) tma_load_2d(sA + i * 8192, &tmA, &full_bar[stage], m0 + i * 64, kb * kBlockK);
           }
-          if (!B_MN) {
+          if (MODE == EPI_SWIGLU) {  // rows [n0, n0+128) of fc11 and of fc12 (stored N rows further down)
+            tma_load_2d(sB, &tmB, &full_bar[stage], kb * kBlockK, n0);
+            tma_load_2d(sB + (BLOCK_N / 2) * 128, &tmB, &full_bar[stage], kb * kBlockK, N + n0);
+          } else if (!B_MN) {
             tma_load_2d(sB, &tmB, &full_bar[stage], kb * kBlockK, n0);
           } else {
 #pragma unroll
@@ -204,7 +217,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t acc_phase = (it >> 1) & 1;
       const int mn = tile / splits;
       const int mt = mn / n_tiles, nt = mn % n_tiles;
-      const int m0 = mt * kBlockM, n0 = nt * BLOCK_N + hf * HALF_N;
+      const int m0 = mt * kBlockM, n0 = (MODE == EPI_SWIGLU) ? nt * TILE_N + hf * (TILE_N / 2) : nt * BLOCK_N + hf * HALF_N;
       const int row = m0 + row_in_tile;
       const bool row_ok = row < M;
       // fast path: no column masks and no per-column scale anywhere in this tile
@@ -229,6 +242,55 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N + hf * HALF_N;
 
+      if (MODE == EPI_SWIGLU) {
+        // this group owns output columns [n0, n0 + 64): y at TMEM cols hf*64 + .., gate at 128 + hf*64 + ..
+        // Three passes over the same TMEM columns (act, then y, then gate when the pre-activations are kept); each
+        // pass packs one 128 x 64 bf16 tile into this group's swizzled staging buffer and TMA-stores it.
+        const uint32_t ty = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N + hf * (TILE_N / 2);
+        const int npass = (ep.yg_out != nullptr) ? 3 : 1;
+#pragma unroll 1
+        for (int pass = 0; pass < npass; ++pass) {
+          if (etid == 0) tma_store_wait_read<0>();
+          named_bar_sync(1 + hf, 128);
+          uint8_t* dst = stage_c + row_in_tile * 128;
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t vy[32], vg[32];
+            if (pass != 2) tmem_ld_32x32(ty + c * 32, vy);
+            if (pass != 1) tmem_ld_32x32(ty + TILE_N + c * 32, vg);
+            tmem_ld_wait();
+            uint32_t pk[16];
+            if (pass == 0) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float y0 = __uint_as_float(vy[2 * j]), y1 = __uint_as_float(vy[2 * j + 1]);
+                const float g0 = __uint_as_float(vg[2 * j]), g1 = __uint_as_float(vg[2 * j + 1]);
+                pk[j] = pack_bf16x2(y0 * __fdividef(g0, 1.f + fast_exp2(-g0 * kLog2e)),
+                                    y1 * __fdividef(g1, 1.f + fast_exp2(-g1 * kLog2e)));
+              }
+            } else if (pass == 1) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(vy[2 * j]), __uint_as_float(vy[2 * j + 1]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(vg[2 * j]), __uint_as_float(vg[2 * j + 1]));
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int chunk = c * 4 + q;
+              *reinterpret_cast<uint4*>(dst + ((chunk ^ (row_in_tile & 7)) << 4)) =
+                  make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1 + hf, 128);
+          if (etid == 0) {
+            if (pass == 0) tma_store_2d(&tmC, stage_c, n0, m0);
+            else tma_store_2d(&tmD, stage_c, (pass == 2 ? N : 0) + n0, m0);
+            tma_store_commit();
+          }
+        }
+      } else
 #pragma unroll 1
       for (int c = 0; c < NC; ++c) {
         uint32_t v[32];
@@ -433,7 +495,7 @@ struct GemmArgs {
 
 int launch_gemm(const GemmArgs& g);
 // number of CTAs launch_gemm will use for (M, N): needed to size dlogit_part
-int gemm_grid(int M, int N, int splits = 1);
+int gemm_grid(int M, int N, int splits = 1, int tile_n = 0);
 int gemm_block_n(int N);
 
 }  // namespace cx

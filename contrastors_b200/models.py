@@ -310,12 +310,15 @@ class _TrunkFn(torch.autograd.Function):
             o = ops.gemm(attn, v(W, p + "attn.out_proj.weight"))
             h1, st1 = ops.add_layernorm_fwd(o, h, v(P, p + "norm1.weight"), v(P, p + "norm1.bias"), eps)
             w1 = _w1(model, W, i)
-            yg = ops.gemm(h1, w1)
-            a = ops.swiglu_fwd(yg)
+            if cfg.n_inner % 128 == 0:
+                a, yg = ops.gemm_swiglu(h1, w1, keep_preact=need_grad)  # SwiGLU fused into the GEMM epilogue
+            else:
+                yg = ops.gemm(h1, w1)
+                a = ops.swiglu_fwd(yg)
             m = ops.gemm(a, v(W, p + "mlp.fc2.weight"))
             h2, st2 = ops.add_layernorm_fwd(m, h1, v(P, p + "norm2.weight"), v(P, p + "norm2.bias"), eps)
             if need_grad:
-                saved.append((h, qkv, attn, lse, o, st1, h1, yg, m, st2))
+                saved.append((h, qkv, attn, lse, o, st1, h1, yg, a, m, st2))
             h = h2
         ctx.model, ctx.packed, ctx.head = model, packed, head
         ctx.saved, ctx.st0 = saved, st0
@@ -345,11 +348,10 @@ class _TrunkFn(torch.autograd.Function):
         f32 = torch.float32
         for i in reversed(range(cfg.n_layer)):
             p = f"encoder.layers.{i}."
-            h, qkv, attn, lse, o, st1, h1, yg, m, st2 = ctx.saved[i]
+            h, qkv, attn, lse, o, st1, h1, yg, a, m, st2 = ctx.saved[i]
             ctx.saved[i] = None
             dz2 = ops.add_layernorm_bwd(m, h1, g_a, g_b, v(P, p + "norm2.weight"), st2, v(G, p + "norm2.weight"),
                                         v(G, p + "norm2.bias"))
-            a = ops.swiglu_fwd(yg)  # recomputed instead of stored
             da = ops.gemm(dz2, v(W, p + "mlp.fc2.weight"), b_major=MAJOR_MN)
             ops.gemm(dz2, a, a_major=MAJOR_MN, b_major=MAJOR_MN, out=v(G, p + "mlp.fc2.weight"), accumulate=True)
             dyg = ops.swiglu_bwd(da, yg)

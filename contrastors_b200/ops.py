@@ -9,6 +9,49 @@ MAJOR_K, MAJOR_MN = 0, 1
 _DT = {torch.bfloat16: 0, torch.float32: 1}
 
 
+class KernelTimer:
+    """CUDA-event timing of individual launches on the launching stream (bench.py's live roofline numbers).
+    ``sample_every`` = record one launch in N per kind, so the timed region is not perturbed."""
+
+    def __init__(self, sample_every=1):
+        self.sample_every = max(1, int(sample_every))
+        self.records = []  # (kind, work, start_event, end_event)
+        self.counts = {}
+
+    def begin(self, kind):
+        c = self.counts.get(kind, 0)
+        self.counts[kind] = c + 1
+        if c % self.sample_every:
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return ev
+
+    def end(self, kind, work, ev):
+        if ev is None:
+            return
+        e2 = torch.cuda.Event(enable_timing=True)
+        e2.record()
+        self.records.append((kind, work, ev, e2))
+
+    def summary(self):
+        """{kind: dict(launches, sampled, ms_avg, work_avg)} -- call after a device synchronize."""
+        out = {}
+        for kind, work, a, b in self.records:
+            d = out.setdefault(kind, dict(sampled=0, ms=0.0, work=0.0))
+            d["sampled"] += 1
+            d["ms"] += a.elapsed_time(b)
+            d["work"] += work
+        for kind, d in out.items():
+            d["launches"] = self.counts.get(kind, 0)
+            d["ms_avg"] = d["ms"] / d["sampled"]
+            d["work_avg"] = d["work"] / d["sampled"]
+        return out
+
+
+TIMER = None  # set to a KernelTimer to time launches
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -37,10 +80,29 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_major=MAJOR_K, b_major=MAJOR_K, 
         out = torch.empty(M, N, device=a.device, dtype=out_dtype)
     assert out.shape == (M, N) and out.stride(1) == 1
     lib = _lib.load()
+    ev = TIMER.begin("gemm") if TIMER is not None else None
     _lib.check(lib.cx_gemm_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, a_major, b_major, a.stride(0),
                                 b.stride(0), out.stride(0), _DT[out.dtype], int(accumulate), float(alpha), _stream()),
                "cx_gemm_bf16")
+    if ev is not None:
+        TIMER.end("gemm", 2.0 * M * N * K, ev)
     return out
+
+
+def gemm_swiglu(x, w1, keep_preact=True):
+    """(x fc11^T) * silu(x fc12^T) with w1 = [fc11; fc12]; returns (act [M,I], yg [M,2I] or None)."""
+    _require_cuda(x, w1)
+    M, K = x.shape
+    I = w1.shape[0] // 2
+    act = torch.empty(M, I, device=x.device, dtype=torch.bfloat16)
+    yg = torch.empty(M, 2 * I, device=x.device, dtype=torch.bfloat16) if keep_preact else None
+    lib = _lib.load()
+    ev = TIMER.begin("gemm") if TIMER is not None else None
+    _lib.check(lib.cx_gemm_swiglu(x.data_ptr(), w1.data_ptr(), act.data_ptr(), _ptr(yg), M, I, K, x.stride(0), w1.stride(0),
+                                  act.stride(0), 2 * I, _stream()), "cx_gemm_swiglu")
+    if ev is not None:
+        TIMER.end("gemm", 2.0 * M * 2 * I * K, ev)
+    return act, yg
 
 
 def rows_to_bf16(x: torch.Tensor, k=None, normalize=False, want_inv_norm=False):
@@ -98,10 +160,13 @@ def infonce_fwd(q, d, k_dim, scale, scale_dev, rq, rd, label_offset, label_strid
     label_logit = torch.empty(n, device=dev, dtype=torch.float32)
     stats = torch.zeros(4, device=dev, dtype=torch.float32)
     lib = _lib.load()
+    ev = TIMER.begin("infonce_fwd") if TIMER is not None else None
     _lib.check(lib.cx_infonce_fwd(q.data_ptr(), q.stride(0), d.data_ptr(), d.stride(0), n, m, k_dim, float(scale),
                                   _ptr(scale_dev), _ptr(rq), _ptr(rd), label_offset, label_stride, lse.data_ptr(),
                                   argmax.data_ptr(), label_logit.data_ptr(), stats.data_ptr(), workspace.data_ptr(),
                                   _stream()), "cx_infonce_fwd")
+    if ev is not None:
+        TIMER.end("infonce_fwd", 2.0 * n * m * k_dim, ev)
     return lse, argmax, label_logit, stats
 
 
@@ -109,11 +174,14 @@ def infonce_bwd(q, d, k_dim, scale, scale_dev, rq, rd, label_offset, label_strid
                 accumulate_dd, stats, workspace):
     lib = _lib.load()
     n, m = q.shape[0], d.shape[0]
+    ev = TIMER.begin("infonce_bwd") if TIMER is not None else None
     _lib.check(lib.cx_infonce_bwd(q.data_ptr(), q.stride(0), d.data_ptr(), d.stride(0), n, m, k_dim, float(scale),
                                   _ptr(scale_dev), _ptr(rq), _ptr(rd), label_offset, label_stride, lse.data_ptr(),
                                   float(coef), _ptr(coef_dev), dq.data_ptr(), dq.stride(0), dd.data_ptr(), dd.stride(0),
                                   int(accumulate_dd), stats.data_ptr(), workspace.data_ptr(), _stream()),
                "cx_infonce_bwd")
+    if ev is not None:
+        TIMER.end("infonce_bwd", 4.0 * n * m * k_dim, ev)
 
 
 # ------------------------------------------------------------------------------------------------ encoder ops
@@ -247,8 +315,11 @@ def attn_fwd(qkv, cu_seqlens, max_seqlen, H, Dh, softmax_scale):
     out = torch.empty(T, H * Dh, device=qkv.device, dtype=torch.bfloat16)
     lse = torch.empty(H, T, device=qkv.device, dtype=torch.float32)
     lib = _lib.load()
+    ev = TIMER.begin("attn_fwd") if TIMER is not None else None
     _lib.check(lib.cx_attn_fwd(qkv.data_ptr(), cu_seqlens.data_ptr(), out.data_ptr(), lse.data_ptr(), T, nseq,
                                int(max_seqlen), H, Dh, float(softmax_scale), _stream()), "cx_attn_fwd")
+    if ev is not None:  # dense estimate 4*S*d per token; exact for full-length sequences
+        TIMER.end("attn_fwd", 4.0 * T * max_seqlen * H * Dh, ev)
     return out, lse
 
 
@@ -260,6 +331,7 @@ def attn_bwd(qkv, out, dout, lse, cu_seqlens, max_seqlen, H, Dh, softmax_scale, 
     dq_acc = torch.zeros(T, H * Dh, device=qkv.device, dtype=torch.float32)
     delta = torch.empty(H, T, device=qkv.device, dtype=torch.float32)
     lib = _lib.load()
+    ev = TIMER.begin("attn_bwd") if TIMER is not None else None
     _lib.check(lib.cx_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), cu_seqlens.data_ptr(),
                                dqkv.data_ptr(), dq_acc.data_ptr(), delta.data_ptr(), T, nseq, int(max_seqlen), H, Dh,
                                float(softmax_scale), _stream()), "cx_attn_bwd")
@@ -269,6 +341,8 @@ def attn_bwd(qkv, out, dout, lse, cu_seqlens, max_seqlen, H, Dh, softmax_scale, 
         rope_inplace(dqkv, pos, cos_t, sin_t, H, Dh, backward=True, first_slot=1, num_slots=1)  # dk
     else:
         _lib.check(lib.cx_dq_finalize(dq_acc.data_ptr(), dqkv.data_ptr(), T, H, Dh, _stream()), "cx_dq_finalize")
+    if ev is not None:
+        TIMER.end("attn_bwd", 10.0 * T * max_seqlen * H * Dh, ev)
     return dqkv
 
 

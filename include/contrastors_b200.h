@@ -46,6 +46,12 @@ CX_API unsigned long long cx_launch_count(void);
 CX_API int cx_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int a_major, int b_major, int64_t lda,
                  int64_t ldb, int64_t ldc, int c_dtype, int accumulate, float alpha, cx_stream_t stream);
 
+/* ---- gated-MLP first layer with the SwiGLU fused into the GEMM epilogue (layers/mlp.py:68-75: fc11, fc12, swiglu)
+ * w1 [2I, K] = [fc11; fc12] (nn.Linear layout); act_out[M, I] = (x fc11^T) * silu(x fc12^T), bf16;
+ * yg_out [M, 2I] = [x fc11^T | x fc12^T] kept for the backward, or NULL (no-grad forward). I % 128 == 0. */
+CX_API int cx_gemm_swiglu(const void* x, const void* w1, void* act_out, void* yg_out, int M, int I, int K, int64_t ldx,
+                   int64_t ldw, int64_t ld_act, int64_t ld_yg, cx_stream_t stream);
+
 /* ---- fused InfoNCE (replaces loss.py:105-130 = matmul + LogitScale + F.cross_entropy + argmax, and its autograd
  *      backward; modeling_dual_encoder.py:54-65; the Matryoshka loop text_text.py:352-369 via k_dim/row scales)
  * q [n, ldq] bf16, d [m, ldd] bf16 (first k_dim columns are used), logits s_ij = scale*rq_i*rd_j*<q_i,d_j>,

@@ -53,3 +53,20 @@ def test_gemm_strided_operands():
     c = ops.gemm(a, b, out_dtype=torch.float32)
     ref = a.float() @ b.float().t()
     assert (c - ref).abs().max().item() <= 1e-3
+
+
+@pytest.mark.parametrize("M,I,K", [(256, 128, 64), (1000, 3072, 768), (130, 256, 128)])
+def test_gemm_swiglu_epilogue(M, I, K):
+    """fc11/fc12 GEMM with the SwiGLU fused into the epilogue (layers/mlp.py:68-75) vs fp32 torch."""
+    import torch.nn.functional as F
+    from contrastors_b200 import ops
+    torch.manual_seed(3)
+    x = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    w1 = (torch.randn(2 * I, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
+    act, yg = ops.gemm_swiglu(x, w1, keep_preact=True)
+    ref_yg = x.float() @ w1.float().t()
+    ref = ref_yg[:, :I] * F.silu(ref_yg[:, I:])
+    assert (yg.float() - ref_yg).abs().max().item() <= 2.0 ** -8 * ref_yg.abs().max().item() + 1e-3
+    assert (act.float() - ref).abs().max().item() <= 2.0 ** -7 * ref.abs().max().item() + 1e-3
+    act2, none = ops.gemm_swiglu(x, w1, keep_preact=False)
+    assert none is None and torch.equal(act, act2)
