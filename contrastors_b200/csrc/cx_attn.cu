@@ -24,40 +24,42 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
 // ============================================================================================== forward
-constexpr int kFwdThreads = 384;
+// One CTA = (sequence, head, 128 query rows); two CTAs are co-resident per SM (112 KB smem, 256 TMEM columns each), so
+// one CTA's softmax overlaps the other's MMAs and prologue.
+constexpr int kFwdThreads = 256;
 struct FwdSmem {
   static constexpr int kTile = 128 * kDh * 2;      // 16 KB: 128 rows x 128 B
-  static constexpr int kQ = 0;                     // 2 tiles
-  static constexpr int kK = kQ + 2 * kTile;        // 2 stages
+  static constexpr int kQ = 0;
+  static constexpr int kK = kQ + kTile;            // 2 stages
   static constexpr int kV = kK + 2 * kTile;        // 2 stages
-  static constexpr int kP = kV + 2 * kTile;        // 2 query tiles x 32 KB
-  static constexpr int kBars = kP + 2 * 32768;
-  static constexpr int kTotal = kBars + 256 + 1024;  // + alignment slack
+  static constexpr int kP = kV + 2 * kTile;        // 32 KB
+  static constexpr int kBars = kP + 32768;
+  static constexpr int kTotal = kBars + 128;       // 114,816 B: two CTAs fit in one SM's 228 KB
 };
 
-__global__ void __launch_bounds__(kFwdThreads, 1)
+__global__ void __launch_bounds__(kFwdThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __restrict__ cu_seqlens,
                 __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int T, int H, float scale2) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::kBars);
   uint64_t* q_full = bars;          // [1]
   uint64_t* k_full = bars + 1;      // [2]
   uint64_t* k_empty = bars + 3;     // [2]
   uint64_t* v_full = bars + 5;      // [2]
   uint64_t* v_empty = bars + 7;     // [2]
-  uint64_t* s_full = bars + 9;      // [2] per query tile
-  uint64_t* p_full = bars + 11;     // [2]
-  uint64_t* o_full = bars + 13;     // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* s_full = bars + 9;      // [1]
+  uint64_t* p_full = bars + 10;     // [1]
+  uint64_t* o_full = bars + 11;     // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int seq = blockIdx.z, head = blockIdx.y;
   const int seq_begin = cu_seqlens[seq];
   const int len = cu_seqlens[seq + 1] - seq_begin;
-  const int q0 = blockIdx.x * 256;
+  const int q0 = blockIdx.x * 128;
   if (q0 >= len) return;  // uniform per CTA, before any barrier/TMEM use
   const int nk = (len + 127) / 128;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // the swizzled tiles need a 1024-byte aligned base
 
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tmQKV);
   if (warp == 1 && lane == 0) {
@@ -67,25 +69,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __restrict
       mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
-      mbar_init(&o_full[i], 1);
     }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<512>(tmem_ptr);
+  if (warp == 2) tmem_alloc<256>(tmem_ptr);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = *tmem_ptr;  // S: columns [0,128), O: [128,192)
 
   const int col_q = (0 * H + head) * kDh, col_k = (1 * H + head) * kDh, col_v = (2 * H + head) * kDh;
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, 2 * FwdSmem::kTile);
+      mbar_arrive_expect_tx(q_full, FwdSmem::kTile);
       tma_load_2d(smem + FwdSmem::kQ, &tmQKV, q_full, col_q, seq_begin + q0);
-      tma_load_2d(smem + FwdSmem::kQ + FwdSmem::kTile, &tmQKV, q_full, col_q, seq_begin + q0 + 128);
       for (int j = 0; j < nk; ++j) {
         const int st = j & 1;
         const uint32_t ph = (j >> 1) & 1;
@@ -103,88 +104,79 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __restrict
       constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);   // O = P V  : A K-major, B (V) MN-major
       const uint32_t q_addr = smem_u32(smem + FwdSmem::kQ), k_addr = smem_u32(smem + FwdSmem::kK);
       const uint32_t v_addr = smem_u32(smem + FwdSmem::kV), p_addr = smem_u32(smem + FwdSmem::kP);
-      auto issue_s = [&](int qt, int st) {
+      auto issue_s = [&](int st) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          umma_f16_ss(tmem_base + qt * 192, make_smem_desc_sw128(q_addr + qt * FwdSmem::kTile + kk * 32, 0, 1024),
+          umma_f16_ss(tmem_base, make_smem_desc_sw128(q_addr + kk * 32, 0, 1024),
                       make_smem_desc_sw128(k_addr + st * FwdSmem::kTile + kk * 32, 0, 1024), idesc_s, kk > 0 ? 1u : 0u);
       };
-      auto issue_pv = [&](int qt, int st, bool accumulate) {
+      auto issue_pv = [&](int st, bool accumulate) {
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma_f16_ss(tmem_base + qt * 192 + 128,
-                      make_smem_desc_sw128(p_addr + qt * 32768 + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024),
+          umma_f16_ss(tmem_base + 128, make_smem_desc_sw128(p_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024),
                       make_smem_desc_sw128(v_addr + st * FwdSmem::kTile + kk * 2048, 8192, 1024), idesc_o,
                       (accumulate || kk > 0) ? 1u : 0u);
       };
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
-      issue_s(0, 0);
-      umma_commit(&s_full[0]);
-      issue_s(1, 0);
-      umma_commit(&s_full[1]);
+      issue_s(0);
+      umma_commit(s_full);
       umma_commit(&k_empty[0]);
       for (int j = 0; j < nk; ++j) {
         const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1, pj = j & 1;
-        const bool more = (j + 1 < nk);
-        mbar_wait(&v_full[st], ph);
-        mbar_wait(&p_full[0], pj);
+        mbar_wait(&v_full[st], (j >> 1) & 1);
+        mbar_wait(p_full, j & 1);
         tc_fence_after();
-        issue_pv(0, st, j > 0);
-        if (more) {
-          mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
-          tc_fence_after();
-          issue_s(0, (j + 1) & 1);
-          umma_commit(&s_full[0]);
-        } else {
-          umma_commit(&o_full[0]);
-        }
-        mbar_wait(&p_full[1], pj);
-        tc_fence_after();
-        issue_pv(1, st, j > 0);
+        issue_pv(st, j > 0);
         umma_commit(&v_empty[st]);
-        if (more) {
-          issue_s(1, (j + 1) & 1);
-          umma_commit(&s_full[1]);
-          umma_commit(&k_empty[(j + 1) & 1]);
+        if (j + 1 < nk) {
+          const int ns = (j + 1) & 1;
+          mbar_wait(&k_full[ns], ((j + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_s(ns);
+          umma_commit(s_full);
+          umma_commit(&k_empty[ns]);
         } else {
-          umma_commit(&o_full[1]);
+          umma_commit(o_full);
         }
       }
     }
   } else if (warp >= 4) {
-    // ---------------------------------------------------------------- softmax groups
-    const int qt = (warp - 4) >> 2;
+    // ---------------------------------------------------------------- softmax warps (thread = query row)
     const int ew = warp & 3;
     const int r = ew * 32 + lane;                // row within the query tile
-    const int q_row = q0 + qt * 128 + r;         // row within the sequence
-    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + qt * 192;
+    const int q_row = q0 + r;                    // row within the sequence
+    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
     const uint32_t t_o = t_s + 128;
-    uint8_t* p_smem = smem + FwdSmem::kP + qt * 32768;
+    uint8_t* p_smem = smem + FwdSmem::kP;
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < nk; ++j) {
-      mbar_wait(&s_full[qt], j & 1);
+      mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int kv_valid = min(128, len - j * 128);  // columns >= kv_valid are padding / another sequence
-      // pass 1: row maximum
+      const bool full = kv_valid == 128;             // CTA-uniform: only the last key tile of a ragged sequence masks
+      // pass 1: row maximum (FMNMX3: two columns per instruction)
       float mx = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(t_s + c * 32, v);
         tmem_ld_wait();
+        if (!full) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= kv_valid) v[i] = 0xff800000u;  // -inf
+        }
         float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const int cb = c * 32 + i;
-          a0 = fmaxf(a0, cb < kv_valid ? __uint_as_float(v[i]) : -INFINITY);
-          a1 = fmaxf(a1, cb + 1 < kv_valid ? __uint_as_float(v[i + 1]) : -INFINITY);
-          a2 = fmaxf(a2, cb + 2 < kv_valid ? __uint_as_float(v[i + 2]) : -INFINITY);
-          a3 = fmaxf(a3, cb + 3 < kv_valid ? __uint_as_float(v[i + 3]) : -INFINITY);
+        for (int i = 0; i < 32; i += 8) {
+          a0 = fmax3(a0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+          a1 = fmax3(a1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+          a2 = fmax3(a2, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+          a3 = fmax3(a3, __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
         }
-        mx = fmaxf(mx, fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)));
+        mx = fmax3(mx, fmaxf(a0, a1), fmaxf(a2, a3));
       }
       const float m_new = fmaxf(m_run, mx * scale2);
       const float alpha = fast_exp2(m_run - m_new);  // 0 on the first tile (m_run = -inf)
@@ -195,27 +187,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __restrict
         uint32_t v[32];
         tmem_ld_32x32(t_s + c * 32, v);
         tmem_ld_wait();
-        float p[32];
+        if (!full) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const int cb = c * 32 + i;
-          p[i] = cb < kv_valid ? fast_exp2(fmaf(__uint_as_float(v[i]), scale2, -m_new)) : 0.f;
-          p[i + 1] = cb + 1 < kv_valid ? fast_exp2(fmaf(__uint_as_float(v[i + 1]), scale2, -m_new)) : 0.f;
-          p[i + 2] = cb + 2 < kv_valid ? fast_exp2(fmaf(__uint_as_float(v[i + 2]), scale2, -m_new)) : 0.f;
-          p[i + 3] = cb + 3 < kv_valid ? fast_exp2(fmaf(__uint_as_float(v[i + 3]), scale2, -m_new)) : 0.f;
-          rs0 += p[i];
-          rs1 += p[i + 1];
-          rs2 += p[i + 2];
-          rs3 += p[i + 3];
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= kv_valid) v[i] = 0xff800000u;  // exp2(-inf) = 0
         }
         uint8_t* dst = p_smem + (c >> 1) * 16384 + r * 128;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
+          float p[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) p[i] = fast_exp2(fmaf(__uint_as_float(v[8 * q + i]), scale2, -m_new));
+          rs0 += p[0] + p[4];
+          rs1 += p[1] + p[5];
+          rs2 += p[2] + p[6];
+          rs3 += p[3] + p[7];
           uint4 w;
-          w.x = pack_bf16x2(p[8 * q + 0], p[8 * q + 1]);
-          w.y = pack_bf16x2(p[8 * q + 2], p[8 * q + 3]);
-          w.z = pack_bf16x2(p[8 * q + 4], p[8 * q + 5]);
-          w.w = pack_bf16x2(p[8 * q + 6], p[8 * q + 7]);
+          w.x = pack_bf16x2(p[0], p[1]);
+          w.y = pack_bf16x2(p[2], p[3]);
+          w.z = pack_bf16x2(p[4], p[5]);
+          w.w = pack_bf16x2(p[6], p[7]);
           const int chunk = (c & 1) * 4 + q;
           *reinterpret_cast<uint4*>(dst + ((chunk ^ (r & 7)) << 4)) = w;
         }
@@ -237,10 +228,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __restrict
       }
       fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core's async proxy
       tc_fence_before();
-      mbar_arrive(&p_full[qt]);
+      mbar_arrive(p_full);
     }
     // epilogue: O / l -> bf16, lse
-    mbar_wait(&o_full[qt], 0);
+    mbar_wait(o_full, 0);
     tc_fence_after();
     const float inv_l = 1.f / l_run;
     const bool row_ok = q_row < len;
@@ -269,7 +260,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __restrict
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc<256>(tmem_base);
   }
 }
 
@@ -290,7 +281,7 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __n
   if (lane == 0) delta[(size_t)h * T + t] = s;
 }
 
-constexpr int kBwdThreads = 256;
+constexpr int kBwdThreads = 384;  // 4 control warps + 2 x 4 worker warps (each group owns 64 of the 128 key columns)
 struct BwdSmem {
   static constexpr int kTile = 128 * kDh * 2;   // 16 KB
   static constexpr int kK = 0;                  // K_j  (B of S, B of dQ as MN-major)
@@ -344,9 +335,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       mbar_init(&q_empty[i], 1);
     }
     mbar_init(sdp_full, 1);
-    mbar_init(pds_full, 128);
+    mbar_init(pds_full, 256);
     mbar_init(dq_full, 1);
-    mbar_init(dq_free, 128);
+    mbar_init(dq_free, 256);
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -423,13 +414,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     }
   } else if (warp >= 4) {
     const int ew = warp & 3;
-    const int r = ew * 32 + lane;  // query row within the tile (S/dP/dQ) or key row within the tile (dK/dV)
-    const int etid = threadIdx.x - 128;
+    const int grp = (warp - 4) >> 2;  // column group: keys [grp*64, grp*64+64) of the tile; dQ columns [grp*32, +32)
+    const int r = ew * 32 + lane;     // query row within the tile (S/dP/dQ) or key row within the tile (dK/dV)
+    const int etid = (threadIdx.x - 128) & 127;
     const uint32_t lane_base = static_cast<uint32_t>(ew * 32) << 16;
     const int kv_valid = min(128, len - k0);
-    uint8_t* p_smem = smem + BwdSmem::kP;
-    uint8_t* ds_smem = smem + BwdSmem::kDS;
-    uint8_t* dq_smem = smem + BwdSmem::kDQ;
+    const bool full = kv_valid == 128;
+    uint8_t* p_smem = smem + BwdSmem::kP + grp * 16384;    // this group's 64-key block of P / dS
+    uint8_t* ds_smem = smem + BwdSmem::kDS + grp * 16384;
+    uint8_t* dq_smem = smem + BwdSmem::kDQ + grp * 16384;
     for (int i = 0; i < nq; ++i) {
       const int q_row = i * 128 + r;
       const bool row_ok = q_row < len;
@@ -438,33 +431,36 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       mbar_wait(sdp_full, i & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t vs[32], vd[32];
-        tmem_ld_32x32(tmem_base + lane_base + c * 32, vs);
-        tmem_ld_32x32(tmem_base + lane_base + 128 + c * 32, vd);
+        tmem_ld_32x32(tmem_base + lane_base + grp * 64 + c * 32, vs);
+        tmem_ld_32x32(tmem_base + lane_base + 128 + grp * 64 + c * 32, vd);
         tmem_ld_wait();
-        float p[32], ds[32];
+        if (!full) {
 #pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          const bool ok = (c * 32 + t) < kv_valid;
-          const float pv = ok ? fast_exp2(fmaf(__uint_as_float(vs[t]), scale2, -lse2)) : 0.f;
-          p[t] = pv;
-          ds[t] = pv * (__uint_as_float(vd[t]) - dl) * softmax_scale;
+          for (int t = 0; t < 32; ++t)
+            if (grp * 64 + c * 32 + t >= kv_valid) vs[t] = 0xff800000u;  // -inf => P = 0
         }
-        uint8_t* dp = p_smem + (c >> 1) * 16384 + r * 128;
-        uint8_t* dd = ds_smem + (c >> 1) * 16384 + r * 128;
+        uint8_t* dp = p_smem + r * 128;
+        uint8_t* dd = ds_smem + r * 128;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
+          float p[8], ds[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            p[t] = fast_exp2(fmaf(__uint_as_float(vs[8 * q + t]), scale2, -lse2));
+            ds[t] = p[t] * (__uint_as_float(vd[8 * q + t]) - dl) * softmax_scale;
+          }
           uint4 w, x;
-          w.x = pack_bf16x2(p[8 * q + 0], p[8 * q + 1]);
-          w.y = pack_bf16x2(p[8 * q + 2], p[8 * q + 3]);
-          w.z = pack_bf16x2(p[8 * q + 4], p[8 * q + 5]);
-          w.w = pack_bf16x2(p[8 * q + 6], p[8 * q + 7]);
-          x.x = pack_bf16x2(ds[8 * q + 0], ds[8 * q + 1]);
-          x.y = pack_bf16x2(ds[8 * q + 2], ds[8 * q + 3]);
-          x.z = pack_bf16x2(ds[8 * q + 4], ds[8 * q + 5]);
-          x.w = pack_bf16x2(ds[8 * q + 6], ds[8 * q + 7]);
-          const int chunk = (c & 1) * 4 + q;
+          w.x = pack_bf16x2(p[0], p[1]);
+          w.y = pack_bf16x2(p[2], p[3]);
+          w.z = pack_bf16x2(p[4], p[5]);
+          w.w = pack_bf16x2(p[6], p[7]);
+          x.x = pack_bf16x2(ds[0], ds[1]);
+          x.y = pack_bf16x2(ds[2], ds[3]);
+          x.z = pack_bf16x2(ds[4], ds[5]);
+          x.w = pack_bf16x2(ds[6], ds[7]);
+          const int chunk = c * 4 + q;
           *reinterpret_cast<uint4*>(dp + ((chunk ^ (r & 7)) << 4)) = w;
           *reinterpret_cast<uint4*>(dd + ((chunk ^ (r & 7)) << 4)) = x;
         }
@@ -472,17 +468,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(pds_full);
-      // drain this tile's dQ partial: TMEM -> fp32 smem stage -> TMA reduce-add into dq_acc [T, H*Dh]
+      // drain this tile's dQ partial (this group's 32 columns): TMEM -> fp32 smem stage -> TMA reduce-add into dq_acc
       mbar_wait(dq_full, i & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
+      {
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + lane_base + 384 + c * 32, v);
+        tmem_ld_32x32(tmem_base + lane_base + 384 + grp * 32, v);
         tmem_ld_wait();
-        if (etid == 0) tma_store_wait_read<1>();
-        named_bar_sync(1, 128);
-        uint8_t* dst = dq_smem + c * 16384 + r * 128;
+        if (etid == 0) tma_store_wait_read<0>();
+        named_bar_sync(1 + grp, 128);
+        uint8_t* dst = dq_smem + r * 128;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           uint4 w = make_uint4(row_ok ? v[4 * q] : 0u, row_ok ? v[4 * q + 1] : 0u, row_ok ? v[4 * q + 2] : 0u,
@@ -490,40 +485,35 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           *reinterpret_cast<uint4*>(dst + ((q ^ (r & 7)) << 4)) = w;
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
+        named_bar_sync(1 + grp, 128);
         if (etid == 0) {
-          tma_reduce_add_2d(&tmDQ, dq_smem + c * 16384, col_o + c * 32, seq_begin + i * 128);
+          tma_reduce_add_2d(&tmDQ, dq_smem, col_o + grp * 32, seq_begin + i * 128);
           tma_store_commit();
         }
       }
       tc_fence_before();
       mbar_arrive(dq_free);
     }
-    // dK / dV: TMEM -> bf16 -> dqkv rows of this key tile
+    // dV (group 0) / dK (group 1): TMEM -> bf16 -> dqkv rows of this key tile
     mbar_wait(acc_full, 0);
     tc_fence_after();
     const int k_row = k0 + r;
     const bool krow_ok = k_row < len;
-    __nv_bfloat16* dk_row = dqkv + ((size_t)(seq_begin + k_row) * 3 + 1) * H * kDh + (size_t)head * kDh;
-    __nv_bfloat16* dv_row = dqkv + ((size_t)(seq_begin + k_row) * 3 + 2) * H * kDh + (size_t)head * kDh;
+    __nv_bfloat16* dst = dqkv + ((size_t)(seq_begin + k_row) * 3 + (grp == 0 ? 2 : 1)) * H * kDh + (size_t)head * kDh;
 #pragma unroll 1
-    for (int which = 0; which < 2; ++which) {
-      __nv_bfloat16* dst = which == 0 ? dv_row : dk_row;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + lane_base + 256 + which * 64 + c * 32, v);
-        tmem_ld_wait();
-        if (krow_ok) {
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + lane_base + 256 + grp * 64 + c * 32, v);
+      tmem_ld_wait();
+      if (krow_ok) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 w;
-            w.x = pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
-            w.y = pack_bf16x2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
-            w.z = pack_bf16x2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
-            w.w = pack_bf16x2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
-            *reinterpret_cast<uint4*>(dst + c * 32 + q * 8) = w;
-          }
+        for (int q = 0; q < 4; ++q) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
+          w.y = pack_bf16x2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
+          w.z = pack_bf16x2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
+          w.w = pack_bf16x2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
+          *reinterpret_cast<uint4*>(dst + c * 32 + q * 8) = w;
         }
       }
     }
@@ -573,7 +563,7 @@ extern "C" int cx_attn_fwd(const void* qkv, const int32_t* cu_seqlens, void* out
     CX_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::kTotal));
     configured = true;
   }
-  dim3 grid((max_seqlen + 255) / 256, H, nseq);
+  dim3 grid((max_seqlen + 127) / 128, H, nseq);
   attn_fwd_kernel<<<grid, kFwdThreads, FwdSmem::kTotal, stream>>>(tm, cu_seqlens, (__nv_bfloat16*)out, lse, total_tokens, H,
                                                                  softmax_scale * kLog2e);
   CX_LAUNCH_CHECK();
