@@ -257,13 +257,19 @@ add_layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat1
   }
 }
 
-// out_k[j] += sum over blocks of partials[b][k][j], k < np (dgamma, dbeta, and optionally the type-0 embedding row)
+// out_k[j] += sum over blocks of partials[b][k][j], k < np (dgamma, dbeta, and optionally the type-0 embedding row).
+// 8 threads per column split the blocks (fixed assignment + fixed shuffle tree => deterministic).
 __global__ void ln_param_grad_reduce_kernel(const float* __restrict__ partials, int nblocks, int d, int np, float* __restrict__ o0,
                                             float* __restrict__ o1, float* __restrict__ o2) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= np * d) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = t >> 3, sub = t & 7;
   float acc = 0.f;
-  for (int b = 0; b < nblocks; ++b) acc += partials[(size_t)b * np * d + j];
+  if (j < np * d)
+    for (int b = sub; b < nblocks; b += 8) acc += partials[(size_t)b * np * d + j];
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  if (j >= np * d || sub != 0) return;
   const int which = j / d, col = j % d;
   float* dst = which == 0 ? o0 : (which == 1 ? o1 : o2);
   if (dst != nullptr) dst[col] += acc;
@@ -681,7 +687,7 @@ extern "C" int cx_add_layernorm_bwd(const void* a, const void* b, const void* g1
                                   dgamma ? (float*)workspace : (float*)nullptr, rows, d, (int64_t)-1);
   if (rc) return rc;
   if (dgamma) {
-    ln_param_grad_reduce_kernel<<<(2 * d + 255) / 256, 256, 0, STREAM>>>((const float*)workspace, grid, d, 2, dgamma, dbeta, nullptr);
+    ln_param_grad_reduce_kernel<<<(2 * d * 8 + 255) / 256, 256, 0, STREAM>>>((const float*)workspace, grid, d, 2, dgamma, dbeta, nullptr);
     CX_LAUNCH_CHECK();
   }
   return 0;
@@ -702,7 +708,7 @@ extern "C" int cx_embed_layernorm_bwd(const int64_t* ids, const int64_t* type_id
                                  (__nv_bfloat16*)nullptr, dword, dtype_emb, (float*)workspace, rows, d, padding_idx);
   if (rc) return rc;
   // type_ids == NULL: every token is type 0, its embedding-row gradient is the third column-sum partial
-  ln_param_grad_reduce_kernel<<<(3 * d + 255) / 256, 256, 0, STREAM>>>((const float*)workspace, grid, d, 3, dgamma, dbeta,
+  ln_param_grad_reduce_kernel<<<(3 * d * 8 + 255) / 256, 256, 0, STREAM>>>((const float*)workspace, grid, d, 3, dgamma, dbeta,
                                                                        type_ids == nullptr ? dtype_emb : nullptr);
   CX_LAUNCH_CHECK();
   return 0;

@@ -46,7 +46,13 @@ struct EpiParams {
   int* part_arg = nullptr;     // [2 * n_col_tiles][M]
   float* label_logit = nullptr;  // [M]
   float* dlogit_part = nullptr;  // [gridDim.x]
-  // EPI_SWIGLU (direct global stores; N = number of gated output columns)
+  // EPI_STORE bf16 with rotary embedding fused (QKV projection): columns [0, rope_cols) are heads of 64 whose halves
+  // (x1 = first 32, x2 = last 32) are rotated by cos/sin[rope_pos[row]][0..32)   (layers/embedding.py:685-706)
+  const int* rope_pos = nullptr;
+  const float* rope_cos = nullptr;
+  const float* rope_sin = nullptr;
+  int rope_cols = 0;
+  // EPI_SWIGLU (N = number of gated output columns)
   __nv_bfloat16* act_out = nullptr;  // [M, N]
   int64_t ld_act = 0;
   __nv_bfloat16* yg_out = nullptr;   // [M, 2N] = [y | gate], nullptr = do not keep the pre-activations
@@ -287,6 +293,57 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (etid == 0) {
             if (pass == 0) tma_store_2d(&tmC, stage_c, n0, m0);
             else tma_store_2d(&tmD, stage_c, (pass == 2 ? N : 0) + n0, m0);
+            tma_store_commit();
+          }
+        }
+      } else if (MODE == EPI_STORE && !OUT_F32) {
+        // bf16 store path: one staging row (128 B) = 64 columns = two TMEM chunks = one attention head when RoPE is on
+        const float* cs = nullptr;
+        const float* sn = nullptr;
+        if (ep.rope_pos != nullptr && row_ok) {
+          const int ps = ep.rope_pos[row];
+          cs = ep.rope_cos + (size_t)ps * 32;
+          sn = ep.rope_sin + (size_t)ps * 32;
+        }
+#pragma unroll 1
+        for (int pr = 0; pr < NC / 2; ++pr) {
+          uint32_t v1[32], v2[32];
+          tmem_ld_32x32(taddr + pr * 64, v1);
+          tmem_ld_32x32(taddr + pr * 64 + 32, v2);
+          tmem_ld_wait();
+          const int col0 = n0 + pr * 64;
+          uint32_t pk1[16], pk2[16];
+          if (cs != nullptr && col0 < ep.rope_cols) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 c2 = *reinterpret_cast<const float2*>(cs + 2 * j);
+              const float2 s2 = *reinterpret_cast<const float2*>(sn + 2 * j);
+              const float a0 = __uint_as_float(v1[2 * j]) * ep_alpha, a1 = __uint_as_float(v1[2 * j + 1]) * ep_alpha;
+              const float b0 = __uint_as_float(v2[2 * j]) * ep_alpha, b1 = __uint_as_float(v2[2 * j + 1]) * ep_alpha;
+              pk1[j] = pack_bf16x2(a0 * c2.x - b0 * s2.x, a1 * c2.y - b1 * s2.y);
+              pk2[j] = pack_bf16x2(b0 * c2.x + a0 * s2.x, b1 * c2.y + a1 * s2.y);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              pk1[j] = pack_bf16x2(__uint_as_float(v1[2 * j]) * ep_alpha, __uint_as_float(v1[2 * j + 1]) * ep_alpha);
+              pk2[j] = pack_bf16x2(__uint_as_float(v2[2 * j]) * ep_alpha, __uint_as_float(v2[2 * j + 1]) * ep_alpha);
+            }
+          }
+          if (etid == 0) tma_store_wait_read<0>();
+          named_bar_sync(1 + hf, 128);
+          uint8_t* dst = stage_c + row_in_tile * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            *reinterpret_cast<uint4*>(dst + ((q ^ (row_in_tile & 7)) << 4)) =
+                make_uint4(pk1[4 * q], pk1[4 * q + 1], pk1[4 * q + 2], pk1[4 * q + 3]);
+            *reinterpret_cast<uint4*>(dst + (((4 + q) ^ (row_in_tile & 7)) << 4)) =
+                make_uint4(pk2[4 * q], pk2[4 * q + 1], pk2[4 * q + 2], pk2[4 * q + 3]);
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1 + hf, 128);
+          if (etid == 0) {
+            tma_store_2d(&tmC, stage_c, col0, m0);
             tma_store_commit();
           }
         }

@@ -89,6 +89,22 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_major=MAJOR_K, b_major=MAJOR_K, 
     return out
 
 
+def gemm_qkv_rope(x, w, pos, cos_t, sin_t, rope_cols):
+    """qkv = x w^T with RoPE applied to the q and k heads in the GEMM epilogue."""
+    _require_cuda(x, w)
+    T, K = x.shape
+    n_out = w.shape[0]
+    out = torch.empty(T, n_out, device=x.device, dtype=torch.bfloat16)
+    lib = _lib.load()
+    ev = TIMER.begin("gemm") if TIMER is not None else None
+    _lib.check(lib.cx_gemm_qkv_rope(x.data_ptr(), w.data_ptr(), out.data_ptr(), T, n_out, K, x.stride(0), w.stride(0),
+                                    out.stride(0), pos.data_ptr(), cos_t.data_ptr(), sin_t.data_ptr(), rope_cols, _stream()),
+               "cx_gemm_qkv_rope")
+    if ev is not None:
+        TIMER.end("gemm", 2.0 * T * n_out * K, ev)
+    return out
+
+
 def gemm_swiglu(x, w1, keep_preact=True):
     """(x fc11^T) * silu(x fc12^T) with w1 = [fc11; fc12]; returns (act [M,I], yg [M,2I] or None)."""
     _require_cuda(x, w1)

@@ -46,6 +46,13 @@ CX_API unsigned long long cx_launch_count(void);
 CX_API int cx_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int a_major, int b_major, int64_t lda,
                  int64_t ldb, int64_t ldc, int c_dtype, int accumulate, float alpha, cx_stream_t stream);
 
+/* ---- QKV projection with the rotary embedding fused into the GEMM epilogue (layers/attention.py:112-133 =
+ * Wqkv GEMM + apply_rotary_emb x2 + torch.stack): qkv[T, n_out] = x w^T; heads (64 columns) inside [0, rope_cols) are
+ * rotated NeoX-style by cos/sin[pos[t]] (fp32 tables [max_pos, 32]). */
+CX_API int cx_gemm_qkv_rope(const void* x, const void* w, void* qkv, int T, int n_out, int K, int64_t ldx, int64_t ldw,
+                     int64_t ldo, const int32_t* pos, const float* cos_t, const float* sin_t, int rope_cols,
+                     cx_stream_t stream);
+
 /* ---- gated-MLP first layer with the SwiGLU fused into the GEMM epilogue (layers/mlp.py:68-75: fc11, fc12, swiglu)
  * w1 [2I, K] = [fc11; fc12] (nn.Linear layout); act_out[M, I] = (x fc11^T) * silu(x fc12^T), bf16;
  * yg_out [M, 2I] = [x fc11^T | x fc12^T] kept for the backward, or NULL (no-grad forward). I % 128 == 0. */

@@ -2,7 +2,6 @@
 set -x
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-# forward GEMMs of layer 0 in the grad-mode forward: skip the 48 no-grad forward GEMMs first
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 48 -c 4 -o gpurun_out/prof_gemm python tools/profile_chunk.py 1 > gpurun_out/prof_gemm.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_fwd -s 12 -c 1 -o gpurun_out/prof_attn_fwd python tools/profile_chunk.py 1 >> gpurun_out/prof_gemm.log 2>&1
-tail -3 gpurun_out/prof_gemm.log
+timeout 900 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_encoder_ops.py tests/test_gpu_encoder.py tests/test_gpu_infonce.py -x -q -m gpu 2>&1 | tail -15 | tee gpurun_out/tests.log
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_chunk.csv python tools/profile_chunk.py 2 > gpurun_out/prof_chunk.log 2>&1
+tail -3 gpurun_out/prof_chunk.log

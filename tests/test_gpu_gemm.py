@@ -70,3 +70,31 @@ def test_gemm_swiglu_epilogue(M, I, K):
     assert (act.float() - ref).abs().max().item() <= 2.0 ** -7 * ref.abs().max().item() + 1e-3
     act2, none = ops.gemm_swiglu(x, w1, keep_preact=False)
     assert none is None and torch.equal(act, act2)
+
+
+def test_gemm_qkv_rope_epilogue_matches_gemm_then_rope():
+    """RoPE fused into the QKV GEMM epilogue == plain GEMM followed by the standalone rotary kernel (bitwise up to the
+    single bf16 rounding the fusion removes), and both match an fp32 torch reference."""
+    from contrastors_b200 import ops
+    torch.manual_seed(4)
+    H, Dh, d = 3, 64, 192
+    lens = [200, 56]
+    T = sum(lens)
+    cu = torch.tensor([0, 200, 256], dtype=torch.int32, device="cuda")
+    pos = ops.token_positions(cu, T)
+    inv = 1.0 / (1000.0 ** (torch.arange(0, Dh, 2, dtype=torch.float32) / Dh))
+    fr = torch.outer(torch.arange(256, dtype=torch.float32), inv)
+    cos_t, sin_t = torch.cos(fr).cuda(), torch.sin(fr).cuda()
+    x = torch.randn(T, d, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(3 * d, d, device="cuda") / d ** 0.5).to(torch.bfloat16)
+    fused = ops.gemm_qkv_rope(x, w, pos, cos_t, sin_t, 2 * d)
+    ref = (x.float() @ w.float().t()).view(T, 3, H, Dh)
+    c = cos_t[pos.long()][:, None, :]
+    s = sin_t[pos.long()][:, None, :]
+    for slot in (0, 1):
+        x1, x2 = ref[:, slot, :, :32].clone(), ref[:, slot, :, 32:].clone()
+        ref[:, slot, :, :32] = x1 * c - x2 * s
+        ref[:, slot, :, 32:] = x2 * c + x1 * s
+    assert (fused.float().view(T, 3, H, Dh) - ref).abs().max().item() <= 2.0 ** -7 * ref.abs().max().item()
+    two_step = ops.rope_inplace(ops.gemm(x, w), pos, cos_t, sin_t, H, Dh)
+    assert (fused.float() - two_step.float()).abs().max().item() <= 2.0 ** -6 * ref.abs().max().item()
