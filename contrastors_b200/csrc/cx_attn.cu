@@ -24,17 +24,19 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
 // ============================================================================================== forward
-// One CTA = (sequence, head, 128 query rows); two CTAs are co-resident per SM (112 KB smem, 256 TMEM columns each), so
-// one CTA's softmax overlaps the other's MMAs and prologue.
-constexpr int kFwdThreads = 256;
+// One CTA = (sequence, head, 128 query rows); two CTAs are co-resident per SM (112.6 KB smem, 256 TMEM columns each), so
+// one CTA's softmax overlaps the other's MMAs and prologue.  Softmax: 8 warps, two threads per query row (64 key columns
+// each); the row maximum is agreed through a 512-byte bf16 exchange (rounded up, so it is a valid stabiliser for both).
+constexpr int kFwdThreads = 384;
 struct FwdSmem {
   static constexpr int kTile = 128 * kDh * 2;      // 16 KB: 128 rows x 128 B
   static constexpr int kQ = 0;
   static constexpr int kK = kQ + kTile;            // 2 stages
   static constexpr int kV = kK + 2 * kTile;        // 2 stages
   static constexpr int kP = kV + 2 * kTile;        // 32 KB
-  static constexpr int kBars = kP + 32768;
-  static constexpr int kTotal = kBars + 128;       // 114,816 B: two CTAs fit in one SM's 228 KB
+  static constexpr int kSmax = kP + 32768;         // [2 groups][128 rows] bf16
+  static constexpr int kBars = kSmax + 512;
+  static constexpr int kTotal = kBars + 112;       // 115,312 B <= 115,712: two CTAs fit in one SM's 228 KB
 };
 
 __global__ void __launch_bounds__(kFwdThreads, 2)
@@ -71,7 +73,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __restrict
       mbar_init(&v_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 256);
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
@@ -143,103 +145,104 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __restrict
       }
     }
   } else if (warp >= 4) {
-    // ---------------------------------------------------------------- softmax warps (thread = query row)
+    // ---------------------------------------------------------------- softmax warps (two threads per query row)
     const int ew = warp & 3;
+    const int grp = (warp - 4) >> 2;             // key columns [grp*64, grp*64+64) of each tile; O columns [grp*32, +32)
     const int r = ew * 32 + lane;                // row within the query tile
     const int q_row = q0 + r;                    // row within the sequence
-    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
-    const uint32_t t_o = t_s + 128;
-    uint8_t* p_smem = smem + FwdSmem::kP;
-    float m_run = -INFINITY, l_run = 0.f;
+    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + grp * 64;
+    const uint32_t t_o = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + 128 + grp * 32;
+    uint8_t* p_smem = smem + FwdSmem::kP + grp * 16384;
+    __nv_bfloat16* smax = reinterpret_cast<__nv_bfloat16*>(smem + FwdSmem::kSmax);
+    float m_run = -INFINITY, l_run = 0.f;        // l_run: this thread's 64-column share of the row sum
     for (int j = 0; j < nk; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      const int kv_valid = min(128, len - j * 128);  // columns >= kv_valid are padding / another sequence
-      const bool full = kv_valid == 128;             // CTA-uniform: only the last key tile of a ragged sequence masks
-      // pass 1: row maximum (FMNMX3: two columns per instruction)
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_s + c * 32, v);
-        tmem_ld_wait();
-        if (!full) {
+      const int kv_valid = min(128, len - j * 128) - grp * 64;  // valid columns among this thread's 64
+      const bool full = kv_valid >= 64;
+      // one TMEM read of this thread's 64 scores, kept in registers for both the maximum and the exponentials
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32(t_s, va);
+      tmem_ld_32x32(t_s + 32, vb);
+      tmem_ld_wait();
+      if (!full) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i >= kv_valid) v[i] = 0xff800000u;  // -inf
+        for (int i = 0; i < 32; ++i) {
+          if (i >= kv_valid) va[i] = 0xff800000u;       // -inf: never the maximum, exp2 -> 0
+          if (32 + i >= kv_valid) vb[i] = 0xff800000u;
         }
-        float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          a0 = fmax3(a0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-          a1 = fmax3(a1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
-          a2 = fmax3(a2, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
-          a3 = fmax3(a3, __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
-        }
-        mx = fmax3(mx, fmaxf(a0, a1), fmaxf(a2, a3));
       }
-      const float m_new = fmaxf(m_run, mx * scale2);
+      float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        a0 = fmax3(a0, __uint_as_float(va[i]), __uint_as_float(va[i + 1]));
+        a1 = fmax3(a1, __uint_as_float(va[i + 2]), __uint_as_float(va[i + 3]));
+        a2 = fmax3(a2, __uint_as_float(va[i + 4]), __uint_as_float(va[i + 5]));
+        a3 = fmax3(a3, __uint_as_float(va[i + 6]), __uint_as_float(va[i + 7]));
+        a0 = fmax3(a0, __uint_as_float(vb[i]), __uint_as_float(vb[i + 1]));
+        a1 = fmax3(a1, __uint_as_float(vb[i + 2]), __uint_as_float(vb[i + 3]));
+        a2 = fmax3(a2, __uint_as_float(vb[i + 4]), __uint_as_float(vb[i + 5]));
+        a3 = fmax3(a3, __uint_as_float(vb[i + 6]), __uint_as_float(vb[i + 7]));
+      }
+      const float mx = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+      // agree on the row maximum with the thread that owns the other 64 columns (values rounded UP to bf16, so the
+      // agreed stabiliser is >= the true maximum and identical in both threads)
+      const __nv_bfloat16 mine = __float2bfloat16_ru(mx * scale2);
+      smax[grp * 128 + r] = mine;
+      named_bar_sync(2, 256);
+      const float m_new = fmax3(m_run, __bfloat162float(mine), __bfloat162float(smax[(grp ^ 1) * 128 + r]));
       const float alpha = fast_exp2(m_run - m_new);  // 0 on the first tile (m_run = -inf)
-      // pass 2: P = exp2(s*scale2 - m_new) -> bf16 smem (K-major, two 64-column swizzled blocks), row sum
+      // P = exp2(s*scale2 - m_new) -> bf16 smem (this group's 64-column swizzled block), row-sum share
       float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_s + c * 32, v);
-        tmem_ld_wait();
-        if (!full) {
+      uint8_t* dst = p_smem + r * 128;
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i >= kv_valid) v[i] = 0xff800000u;  // exp2(-inf) = 0
+      for (int q = 0; q < 8; ++q) {
+        float p[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t raw = (q < 4) ? va[8 * q + i] : vb[8 * (q - 4) + i];
+          p[i] = fast_exp2(fmaf(__uint_as_float(raw), scale2, -m_new));
         }
-        uint8_t* dst = p_smem + (c >> 1) * 16384 + r * 128;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float p[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) p[i] = fast_exp2(fmaf(__uint_as_float(v[8 * q + i]), scale2, -m_new));
-          rs0 += p[0] + p[4];
-          rs1 += p[1] + p[5];
-          rs2 += p[2] + p[6];
-          rs3 += p[3] + p[7];
-          uint4 w;
-          w.x = pack_bf16x2(p[0], p[1]);
-          w.y = pack_bf16x2(p[2], p[3]);
-          w.z = pack_bf16x2(p[4], p[5]);
-          w.w = pack_bf16x2(p[6], p[7]);
-          const int chunk = (c & 1) * 4 + q;
-          *reinterpret_cast<uint4*>(dst + ((chunk ^ (r & 7)) << 4)) = w;
-        }
+        rs0 += p[0] + p[4];
+        rs1 += p[1] + p[5];
+        rs2 += p[2] + p[6];
+        rs3 += p[3] + p[7];
+        uint4 w;
+        w.x = pack_bf16x2(p[0], p[1]);
+        w.y = pack_bf16x2(p[2], p[3]);
+        w.z = pack_bf16x2(p[4], p[5]);
+        w.w = pack_bf16x2(p[6], p[7]);
+        *reinterpret_cast<uint4*>(dst + ((q ^ (r & 7)) << 4)) = w;
       }
       l_run = l_run * alpha + ((rs0 + rs1) + (rs2 + rs3));
       m_run = m_new;
-      // rescale the running output only if some row of this warp moved its maximum
+      // rescale this thread's 32 output columns only if some row of the warp moved its maximum
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(t_o + c * 32, v);
-          tmem_ld_wait();
+        uint32_t v[32];
+        tmem_ld_32x32(t_o, v);
+        tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-          tmem_st_32x32(t_o + c * 32, v);
-        }
+        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+        tmem_st_32x32(t_o, v);
         tmem_st_wait();
       }
       fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core's async proxy
       tc_fence_before();
       mbar_arrive(p_full);
     }
-    // epilogue: O / l -> bf16, lse
+    // epilogue: combine the two row-sum shares, O / l -> bf16 (this thread's 32 columns), lse
     mbar_wait(o_full, 0);
     tc_fence_after();
-    const float inv_l = 1.f / l_run;
+    float* lsum = reinterpret_cast<float*>(smem + FwdSmem::kP);  // P is dead once o_full fired
+    lsum[grp * 128 + r] = l_run;
+    named_bar_sync(2, 256);
+    const float l_tot = l_run + lsum[(grp ^ 1) * 128 + r];
+    const float inv_l = 1.f / l_tot;
     const bool row_ok = q_row < len;
-    __nv_bfloat16* orow = out + ((size_t)(seq_begin + q_row) * H + head) * kDh;
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
+    __nv_bfloat16* orow = out + ((size_t)(seq_begin + q_row) * H + head) * kDh + grp * 32;
+    {
       uint32_t v[32];
-      tmem_ld_32x32(t_o + c * 32, v);
+      tmem_ld_32x32(t_o, v);
       tmem_ld_wait();
       if (row_ok) {
 #pragma unroll
@@ -249,11 +252,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __restrict
           w.y = pack_bf16x2(__uint_as_float(v[8 * q + 2]) * inv_l, __uint_as_float(v[8 * q + 3]) * inv_l);
           w.z = pack_bf16x2(__uint_as_float(v[8 * q + 4]) * inv_l, __uint_as_float(v[8 * q + 5]) * inv_l);
           w.w = pack_bf16x2(__uint_as_float(v[8 * q + 6]) * inv_l, __uint_as_float(v[8 * q + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(orow + c * 32 + q * 8) = w;
+          *reinterpret_cast<uint4*>(orow + q * 8) = w;
         }
       }
     }
-    if (row_ok) lse[(size_t)head * T + seq_begin + q_row] = (m_run + log2f(l_run)) * kLn2;
+    if (row_ok && grp == 0) lse[(size_t)head * T + seq_begin + q_row] = (m_run + log2f(l_tot)) * kLn2;
   }
 
   tc_fence_before();

@@ -45,6 +45,7 @@ class _NceSpec:
     dims: Optional[List[int]] = None  # Matryoshka prefix dims (None = full width)
     weights: Optional[List[float]] = None
     normalize: bool = False          # L2-normalise each prefix inside the kernel (rq / rd epilogue scales)
+    pregathered: Optional[torch.Tensor] = None  # bf16 [ws*N, ld] documents already gathered (GradCache stream overlap)
     out: dict = field(default_factory=dict)  # per-dim stats tensors for logging (accuracy), filled by forward
 
 
@@ -66,8 +67,11 @@ class _FusedInfoNCE(torch.autograd.Function):
                                "the CPU restatement lives in oracle/ and is test infrastructure only")
         n, width = query.shape
         q_bf = _as_bf16_rows(query.detach())
-        d_loc = _as_bf16_rows(document.detach())
-        d_bf = all_gather_rows(d_loc) if spec.gather else d_loc
+        if spec.pregathered is not None:
+            d_bf = spec.pregathered  # gathered chunk by chunk on the side stream while the encoder was still running
+        else:
+            d_loc = _as_bf16_rows(document.detach())
+            d_bf = all_gather_rows(d_loc) if spec.gather else d_loc
         m = d_bf.shape[0]
         dims = spec.dims or [width]
         weights = spec.weights or [1.0] * len(dims)
@@ -147,7 +151,7 @@ def _fused_infonce(query, document, logit_scale, spec: _NceSpec):
 
 
 def clip_loss(query, document, logit_scale, step=None, gather_enabled=False, tracker=None, dataset="",
-              bidirectional=False):
+              bidirectional=False, _pregathered=None):
     """InfoNCE for N queries against M >= N documents (reference loss.py:76-132, same signature).
 
     ``logit_scale`` is a callable x -> x * e^p (``LogitScale`` or a DDP-wrapped one).  Returns a 0-dim fp32 tensor
@@ -169,7 +173,8 @@ def clip_loss(query, document, logit_scale, step=None, gather_enabled=False, tra
         loss = loss + _fused_infonce(doc_full, query, logit_scale, spec_d)
         spec = spec_q
     else:
-        spec = _NceSpec(label_offset=rank * n, label_stride=stride, mult=float(ws), gather=gather)
+        spec = _NceSpec(label_offset=rank * n, label_stride=stride, mult=float(ws), gather=gather,
+                        pregathered=_pregathered if gather else None)
         loss = _fused_infonce(query, document, logit_scale, spec)
     if tracker is not None:
         # per-rank top-1 accuracy, as the reference (loss.py:127-130); the hit count came out of the same kernel
@@ -231,6 +236,51 @@ def get_chunked_embeddings(model, chunks):
     return torch.concat(embeddings, dim=0), rand_states
 
 
+_COMM_STREAMS = {}
+
+
+def _comm_stream(device):
+    key = (device.type, device.index)
+    if key not in _COMM_STREAMS:
+        _COMM_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _COMM_STREAMS[key]
+
+
+def _chunked_embeddings_with_gather(model, chunks, n_local):
+    """Pass 1 for the document tower with the cross-rank gather overlapped (north_star: "GradCache loop driven from CUDA
+    streams so encoder compute overlaps the gather"): as each chunk's embeddings land they are cast to bf16 into this
+    rank's slice and all-gathered on a side stream straight into their final rows of the InfoNCE K operand, while the
+    main stream is already running the next chunk's forward.  Returns (fp32 embeddings, rand states, gathered bf16)."""
+    ws, rank = dist.get_world_size(), dist.get_rank()
+    embeddings, rand_states = [], []
+    gathered = None
+    comm = None
+    row = 0
+    with torch.no_grad():
+        for chunk in chunks:
+            rand_states.append(RandContext(chunk))
+            with _autocast_for(chunk):
+                emb = model(**chunk)["embedding"]
+            embeddings.append(emb)
+            e32 = emb.float().contiguous()
+            b, width = e32.shape
+            if gathered is None:
+                ld = (width + 7) // 8 * 8
+                gathered = torch.zeros(ws * n_local, ld, device=e32.device, dtype=torch.bfloat16)
+                comm = _comm_stream(e32.device)
+            mine = gathered[rank * n_local + row: rank * n_local + row + b]
+            ops.rows_to_bf16_into(e32, mine)
+            ready = torch.cuda.Event()
+            ready.record()
+            outs = [gathered[r * n_local + row: r * n_local + row + b] for r in range(ws)]
+            with torch.cuda.stream(comm):
+                comm.wait_event(ready)
+                dist.all_gather(outs, mine)
+            row += b
+    torch.cuda.current_stream().wait_stream(comm)
+    return torch.concat(embeddings, dim=0), rand_states, gathered
+
+
 def accumulate_gradients(model, inputs, cache, rand_states, router_aux_coeff):
     """Pass 2 of GradCache (reference loss.py:149-161): re-forward each chunk with its RNG replayed and back-propagate
     <embedding, cached gradient>; DDP gradient sync only on the last chunk."""
@@ -248,12 +298,13 @@ def accumulate_gradients(model, inputs, cache, rand_states, router_aux_coeff):
             surrogate.backward()
 
 
-def cache_loss(tower1, tower2, query_embeddings, document_embeddings, logit_scale, bidirectional=False):
+def cache_loss(tower1, tower2, query_embeddings, document_embeddings, logit_scale, bidirectional=False, _pregathered=None):
     """Loss on the cached embeddings and its gradients w.r.t. them (reference loss.py:164-184).
     Returns (dQ, dD, loss.detach()).  tower1/tower2 are unused, as in the reference (Appendix A.6)."""
     query_embs = query_embeddings.detach().requires_grad_()
     document_embs = document_embeddings.detach().requires_grad_()
-    loss = clip_loss(query_embs, document_embs, logit_scale, gather_enabled=True, bidirectional=bidirectional)
+    loss = clip_loss(query_embs, document_embs, logit_scale, gather_enabled=True, bidirectional=bidirectional,
+                     _pregathered=None if bidirectional else _pregathered)
     loss.backward()
     return query_embs.grad, document_embs.grad, loss.detach()
 
@@ -270,10 +321,16 @@ def grad_cache_loss(tower1, t1_inputs, tower2, t2_inputs, chunk_size, logit_scal
         chunked_documents.append({k: v[start:start + chunk_size] for k, v in t2_inputs.items()})
 
     query_embs, query_rand_states = get_chunked_embeddings(tower1, chunked_queries)
-    document_embs, doc_rand_states = get_chunked_embeddings(tower2, chunked_documents)
+    pregathered = None
+    if (dist.is_initialized() and dist.get_world_size() > 1 and dist.get_backend() == "nccl"
+            and t2_inputs["input_ids"].is_cuda and total_bs % chunk_size == 0):
+        # the document gather runs chunk by chunk on a side stream while the next chunk's encoder forward computes
+        document_embs, doc_rand_states, pregathered = _chunked_embeddings_with_gather(tower2, chunked_documents, total_bs)
+    else:
+        document_embs, doc_rand_states = get_chunked_embeddings(tower2, chunked_documents)
 
     query_cache, document_cache, loss = cache_loss(tower1, tower2, query_embs, document_embs, logit_scale,
-                                                   bidirectional=bidirectional)
+                                                   bidirectional=bidirectional, _pregathered=pregathered)
 
     accumulate_gradients(tower1, chunked_queries, query_cache.split(chunk_size), query_rand_states,
                          router_aux_coeff=router_aux_coeff)

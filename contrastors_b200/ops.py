@@ -138,6 +138,16 @@ def rows_to_bf16(x: torch.Tensor, k=None, normalize=False, want_inv_norm=False):
     return y, inv
 
 
+def rows_to_bf16_into(x: torch.Tensor, y: torch.Tensor):
+    """bf16 copy of fp32 rows into an existing (possibly strided-row) bf16 buffer."""
+    _require_cuda(x, y)
+    assert x.dtype == torch.float32 and y.dtype == torch.bfloat16 and x.stride(1) == 1 and y.stride(1) == 1
+    lib = _lib.load()
+    _lib.check(lib.cx_rows_to_bf16(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), 0, x.shape[0], x.shape[1], 0,
+                                   _stream()), "cx_rows_to_bf16")
+    return y
+
+
 def row_inv_norms(x: torch.Tensor, k: int):
     _require_cuda(x)
     inv = torch.empty(x.shape[0], device=x.device, dtype=torch.float32)

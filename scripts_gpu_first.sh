@@ -2,6 +2,5 @@
 set -x
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_encoder_ops.py tests/test_gpu_encoder.py tests/test_gpu_infonce.py -x -q -m gpu 2>&1 | tail -15 | tee gpurun_out/tests.log
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_chunk.csv python tools/profile_chunk.py 2 > gpurun_out/prof_chunk.log 2>&1
-tail -3 gpurun_out/prof_chunk.log
+timeout 1200 python bench.py 2>&1 | tail -2 | tee gpurun_out/bench_default.log
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1 | tee gpurun_out/bench_reference.log

@@ -76,3 +76,49 @@ def test_clip_loss_two_ranks(name, tmp_path):
         if name != "unsat":
             z = golden(f"infonce_{name}.npz")
             assert abs(got["loss"] - float(z[f"r{r}_loss"])) <= 5e-2 * max(float(z[f"r{r}_loss"]), 0.05)
+
+
+def _gc_worker(rank, ws, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=ws)
+    import contrastors_b200 as cb
+    from contrastors_b200.parallel import allreduce_gradients
+    cfg = cb.NomicBertConfig(vocab_size=256, n_embd=128, n_head=2, n_inner=256, n_layer=2)
+    model = cb.BiEncoder(cb.BiEncoderConfig(encoder=cfg)).cuda()
+    model.trunk.reset_parameters(seed=3)
+    ls = cb.LogitScale(logit_scale=20.0).cuda()
+    g = torch.Generator().manual_seed(10 + rank)
+    n, S = 12, 40
+    q = {"input_ids": torch.randint(0, 256, (n, S), generator=g).cuda(), "attention_mask": torch.ones(n, S, dtype=torch.long).cuda()}
+    d = {"input_ids": torch.randint(0, 256, (n, S), generator=g).cuda(), "attention_mask": torch.ones(n, S, dtype=torch.long).cuda()}
+    # GradCache step with the gather overlapped on the side stream (chunk 4 -> 3 chunks per tower)
+    loss_gc = cb.grad_cache_loss(model, q, model, d, 4, ls)
+    allreduce_gradients(model)
+    g_gc = model.trunk.flat_grad().clone()
+    model.trunk.flat_grad().zero_()
+    # plain step on the same weights (reference text_text.py:324-378 path)
+    eq = model(**q)["embedding"]
+    ed = model(**d)["embedding"]
+    loss_plain = cb.clip_loss(eq, ed, ls, gather_enabled=True)
+    loss_plain.backward()
+    allreduce_gradients(model)
+    g_plain = model.trunk.flat_grad().clone()
+    torch.cuda.synchronize()
+    np.savez(os.path.join(out_dir, f"gc{rank}.npz"), loss_gc=loss_gc.item(), loss_plain=loss_plain.item(),
+             g_gc=g_gc.cpu().numpy(), g_plain=g_plain.cpu().numpy())
+    dist.destroy_process_group()
+
+
+def test_grad_cache_two_ranks_matches_plain_step(tmp_path):
+    """GradCache == plain step on the same weights; here across 2 ranks with the overlapped gather."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    mp.spawn(_gc_worker, args=(2, 29631, str(tmp_path)), nprocs=2, join=True)
+    z0, z1 = np.load(tmp_path / "gc0.npz"), np.load(tmp_path / "gc1.npz")
+    for z in (z0, z1):
+        assert abs(z["loss_gc"] - z["loss_plain"]) <= 2e-3 * abs(z["loss_plain"])
+        scale = np.abs(z["g_plain"]).max()
+        assert np.abs(z["g_gc"] - z["g_plain"]).max() <= 3e-2 * scale  # bf16 backward, different chunking
+    assert np.array_equal(z0["g_gc"], z1["g_gc"])  # both ranks hold the same averaged gradient
