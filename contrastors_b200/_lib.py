@@ -31,9 +31,9 @@ SIGNATURES = {
                             _i64, _i, _vp, _vp, _vp]),
     "cx_rows_to_bf16": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _i, _i, _vp]),
     "cx_l2norm_bwd": (_i, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
-    "cx_add_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "cx_add_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp]),
     "cx_layernorm_bwd_workspace_bytes": (_sz, [_i]),
-    "cx_add_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "cx_add_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "cx_embed_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "cx_embed_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _vp]),
     "cx_token_positions": (_i, [_vp, _i, _vp, _vp, _vp]),
@@ -50,6 +50,15 @@ SIGNATURES = {
     "cx_grad_clip_coef": (_i, [_vp, _i64, _f, _vp, _vp, _vp]),
     "cx_adamw_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _vp, _f, _i, _vp]),
     "cx_cast_f32_bf16": (_i, [_vp, _vp, _i64, _vp]),
+    "cx_linear_bias_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _vp]),
+    "cx_colsum_bf16": (_i, [_vp, _i64, _i, _vp, _vp]),
+    "cx_act_fwd": (_i, [_vp, _vp, _i64, _i, _vp]),
+    "cx_act_bwd": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
+    "cx_patchify": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "cx_vit_assemble_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "cx_vit_assemble_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "cx_cls_select_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "cx_cls_select_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "cx_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "cx_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
 }

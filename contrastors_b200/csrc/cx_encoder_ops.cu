@@ -56,7 +56,7 @@ add_layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat1
                          const int64_t* __restrict__ ids, const int64_t* __restrict__ type_ids,
                          const __nv_bfloat16* __restrict__ type_emb, const float* __restrict__ gamma,
                          const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ stats, int rows,
-                         int d, float eps) {
+                         int d, float eps, __nv_bfloat16* __restrict__ z_out) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -86,6 +86,11 @@ add_layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat1
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) sum += z[c][i];
+      if (z_out != nullptr) {  // pre-norm blocks carry the residual stream z = a + b forward (layers/block.py:293-388)
+        BF8 vz;
+        vz.pack(z[c]);
+        *reinterpret_cast<uint4*>(z_out + (size_t)row * d + col) = vz.raw;
+      }
     }
   }
   const float mean = warp_sum(sum) / d;
@@ -139,7 +144,8 @@ add_layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat1
                          const __nv_bfloat16* __restrict__ type_emb, const __nv_bfloat16* __restrict__ g1,
                          const __nv_bfloat16* __restrict__ g2, const float* __restrict__ gamma,
                          const float* __restrict__ stats, __nv_bfloat16* __restrict__ dz, float* __restrict__ dword,
-                         float* __restrict__ dtype_emb, float* __restrict__ partials, int rows, int d, int64_t padding_idx) {
+                         float* __restrict__ dtype_emb, float* __restrict__ partials, int rows, int d, int64_t padding_idx,
+                         const __nv_bfloat16* __restrict__ gres) {
   extern __shared__ float sh[];  // [warps][NP][d]
   constexpr int NP = EMBED ? 3 : 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -227,6 +233,14 @@ add_layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat1
             else atomicAdd(dtype_emb + (size_t)tid * d + col + i, o[i]);
           }
         } else {
+          if (gres != nullptr) {  // pre-norm: z also feeds the residual stream, whose gradient adds here
+            BF8 vr;
+            float t[8];
+            vr.raw = *reinterpret_cast<const uint4*>(gres + (size_t)row * d + col);
+            vr.unpack(t);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] += t[i];
+          }
           BF8 vo;
           vo.pack(o);
           *reinterpret_cast<uint4*>(dz + (size_t)row * d + col) = vo.raw;
@@ -591,6 +605,133 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16*
   }
 }
 
+// ---------------------------------------------------------------------------------------------- ViT pieces
+// out[j] (+)= sum_t x[t, j]   (bias gradients of FusedDense); grid.y slabs of rows, fp32 atomics into out
+__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, int64_t T, int N, float* __restrict__ out, int rows_per_block) {
+  const int col = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (col >= N) return;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = min(T, r0 + rows_per_block);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int64_t r = r0; r < r1; ++r) {
+    BF8 v;
+    float f[8];
+    v.raw = *reinterpret_cast<const uint4*>(x + r * N + col);
+    v.unpack(f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += f[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) atomicAdd(out + col + i, acc[i]);
+}
+
+// kind 0: gelu (erf), 1: quick_gelu x*sigmoid(1.702x) (layers/activations.py), elementwise over bf16
+__device__ __forceinline__ float act_fwd(float x, int kind) {
+  if (kind == 1) return x / (1.f + __expf(-1.702f * x));
+  return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+}
+__device__ __forceinline__ float act_grad(float x, int kind) {
+  if (kind == 1) {
+    const float s = 1.f / (1.f + __expf(-1.702f * x));
+    return s * (1.f + 1.702f * x * (1.f - s));
+  }
+  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+__global__ void act_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n8, int kind) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  BF8 v, o;
+  float f[8], g[8];
+  v.raw = *reinterpret_cast<const uint4*>(x + i * 8);
+  v.unpack(f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) g[k] = act_fwd(f[k], kind);
+  o.pack(g);
+  *reinterpret_cast<uint4*>(y + i * 8) = o.raw;
+}
+__global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ dx,
+                               int64_t n8, int kind) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  BF8 v, w, o;
+  float f[8], g[8], r[8];
+  v.raw = *reinterpret_cast<const uint4*>(x + i * 8);
+  w.raw = *reinterpret_cast<const uint4*>(dy + i * 8);
+  v.unpack(f);
+  w.unpack(g);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) r[k] = g[k] * act_grad(f[k], kind);
+  o.pack(r);
+  *reinterpret_cast<uint4*>(dx + i * 8) = o.raw;
+}
+
+// pixels [B, C, Himg, Wimg] fp32 -> patch matrix [B*gh*gw, C*p*p] bf16, column order (c p1 p2) (embedding.py:465-476)
+__global__ void patchify_kernel(const float* __restrict__ px, __nv_bfloat16* __restrict__ out, int B, int C, int Himg, int Wimg, int p) {
+  const int gw = Wimg / p, gh = Himg / p;
+  const int K = C * p * p;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * gh * gw * K) return;
+  const int k = (int)(i % K);
+  const int64_t row = i / K;
+  const int c = k / (p * p), p1 = (k / p) % p, p2 = k % p;
+  const int b = (int)(row / (gh * gw)), hw = (int)(row % (gh * gw));
+  const int h = hw / gw, w = hw % gw;
+  out[i] = __float2bfloat16_rn(px[(((size_t)b * C + c) * Himg + h * p + p1) * Wimg + w * p + p2]);
+}
+
+// z[b, 0] = cls + pos[0];  z[b, 1+i] = proj[b*nP + i] + pos[1+i]   (cls token + learned position embedding)
+__global__ void vit_assemble_fwd_kernel(const __nv_bfloat16* __restrict__ proj, const float* __restrict__ cls, const float* __restrict__ pos,
+                                        __nv_bfloat16* __restrict__ z, int B, int nP, int d) {
+  const int per_row = d / 8;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * (nP + 1) * per_row) return;
+  const int64_t row = i / per_row;
+  const int col = (int)(i % per_row) * 8;
+  const int b = (int)(row / (nP + 1)), tok = (int)(row % (nP + 1));
+  float f[8];
+  if (tok == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = cls[col + k];
+  } else {
+    BF8 v;
+    v.raw = *reinterpret_cast<const uint4*>(proj + ((size_t)b * nP + tok - 1) * d + col);
+    v.unpack(f);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) f[k] += pos[(size_t)tok * d + col + k];
+  BF8 o;
+  o.pack(f);
+  *reinterpret_cast<uint4*>(z + row * d + col) = o.raw;
+}
+// dproj rows = dz rows of the patch tokens (bf16 copy); dcls += sum_b dz[b,0]; dpos[tok] += sum_b dz[b,tok]
+__global__ void vit_assemble_bwd_kernel(const __nv_bfloat16* __restrict__ dz, __nv_bfloat16* __restrict__ dproj, float* __restrict__ dcls,
+                                        float* __restrict__ dpos, int B, int nP, int d) {
+  const int tok = blockIdx.x;  // one block per token position
+  for (int col = threadIdx.x; col < d; col += blockDim.x) {
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const __nv_bfloat16 v = dz[((size_t)b * (nP + 1) + tok) * d + col];
+      acc += __bfloat162float(v);
+      if (tok > 0) dproj[((size_t)b * nP + tok - 1) * d + col] = v;
+    }
+    dpos[(size_t)tok * d + col] += acc;
+    if (tok == 0) dcls[col] += acc;
+  }
+}
+// CLS selector: out[b, :] = h[b*S, :] (fp32), and its backward (zeros elsewhere)
+__global__ void cls_select_fwd_kernel(const __nv_bfloat16* __restrict__ h, float* __restrict__ out, int B, int S, int d) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * d) return;
+  out[i] = __bfloat162float(h[(size_t)(i / d) * S * d + (i % d)]);
+}
+__global__ void cls_select_bwd_kernel(const float* __restrict__ g, __nv_bfloat16* __restrict__ dh, int B, int S, int d) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * S * d) return;
+  const int64_t row = i / d;
+  const int b = (int)(row / S), tok = (int)(row % S);
+  dh[i] = tok == 0 ? __float2bfloat16_rn(g[(size_t)b * d + (i % d)]) : __float2bfloat16_rn(0.f);
+}
+
 }  // namespace cx
 
 using namespace cx;
@@ -599,13 +740,14 @@ using namespace cx;
 static int ln_rows_grid(int rows, int warps) { return (rows + warps - 1) / warps; }
 
 extern "C" int cx_add_layernorm_fwd(const void* a, const void* b, const float* gamma, const float* beta, void* y, float* stats,
-                                    int rows, int d, float eps, cx_stream_t stream) {
+                                    int rows, int d, float eps, void* z_out, cx_stream_t stream) {
   CX_REQUIRE(a && y, "cx_add_layernorm_fwd: null pointer");
   CX_REQUIRE(d % 8 == 0 && d <= 256 * kLnMaxVec, "cx_add_layernorm_fwd: d must be a multiple of 8 and <= 1024");
   if (rows <= 0) return 0;
 #define CX_LN_FWD(NV_)                                                                                              \
   add_layernorm_fwd_kernel<false, NV_><<<ln_rows_grid(rows, 8), 256, 0, STREAM>>>(                                  \
-      (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, nullptr, nullptr, nullptr, gamma, beta, (__nv_bfloat16*)y, stats, rows, d, eps)
+      (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, nullptr, nullptr, nullptr, gamma, beta, (__nv_bfloat16*)y, stats, rows, d, eps, \
+      (__nv_bfloat16*)z_out)
   switch ((d + 255) / 256) {
     case 1: CX_LN_FWD(1); break;
     case 2: CX_LN_FWD(2); break;
@@ -626,7 +768,7 @@ extern "C" int cx_embed_layernorm_fwd(const int64_t* ids, const int64_t* type_id
 #define CX_LN_FWD(NV_)                                                                                              \
   add_layernorm_fwd_kernel<true, NV_><<<ln_rows_grid(rows, 8), 256, 0, STREAM>>>(                                   \
       (const __nv_bfloat16*)word_emb, nullptr, ids, type_ids, (const __nv_bfloat16*)type_emb, gamma, beta, (__nv_bfloat16*)y, \
-      stats, rows, d, eps)
+      stats, rows, d, eps, nullptr)
   switch ((d + 255) / 256) {
     case 1: CX_LN_FWD(1); break;
     case 2: CX_LN_FWD(2); break;
@@ -650,14 +792,14 @@ template <bool EMBED, int NV>
 static int ln_bwd_launch(int grid, size_t smem, cudaStream_t st, const __nv_bfloat16* a, const __nv_bfloat16* b, const int64_t* ids,
                          const int64_t* type_ids, const __nv_bfloat16* type_emb, const __nv_bfloat16* g1, const __nv_bfloat16* g2,
                          const float* gamma, const float* stats, __nv_bfloat16* dz, float* dword, float* dtype_emb, float* partials,
-                         int rows, int d, int64_t padding_idx) {
+                         int rows, int d, int64_t padding_idx, const __nv_bfloat16* gres) {
   static bool configured = false;
   if (!configured) {
     CX_CUDA_CHECK(cudaFuncSetAttribute(add_layernorm_bwd_kernel<EMBED, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4));
     configured = true;
   }
   add_layernorm_bwd_kernel<EMBED, NV><<<grid, 256, smem, st>>>(a, b, ids, type_ids, type_emb, g1, g2, gamma, stats, dz, dword, dtype_emb,
-                                                               partials, rows, d, padding_idx);
+                                                               partials, rows, d, padding_idx, gres);
   CX_LAUNCH_CHECK();
   return 0;
 }
@@ -673,7 +815,7 @@ static int ln_bwd_dispatch(int d, Args... args) {
 
 extern "C" int cx_add_layernorm_bwd(const void* a, const void* b, const void* g1, const void* g2, const float* gamma,
                                     const float* stats, void* dz, float* dgamma, float* dbeta, void* workspace, int rows, int d,
-                                    cx_stream_t stream) {
+                                    const void* gres, cx_stream_t stream) {
   CX_REQUIRE(a && g1 && stats && dz, "cx_add_layernorm_bwd: null pointer");
   CX_REQUIRE(d % 8 == 0 && d <= 256 * kLnMaxVec, "cx_add_layernorm_bwd: d must be a multiple of 8 and <= 1024");
   CX_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "cx_add_layernorm_bwd: dgamma/dbeta go together");
@@ -684,7 +826,7 @@ extern "C" int cx_add_layernorm_bwd(const void* a, const void* b, const void* g1
   int rc = ln_bwd_dispatch<false>(d, grid, smem, STREAM, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (const int64_t*)nullptr,
                                   (const int64_t*)nullptr, (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)g1,
                                   (const __nv_bfloat16*)g2, gamma, stats, (__nv_bfloat16*)dz, (float*)nullptr, (float*)nullptr,
-                                  dgamma ? (float*)workspace : (float*)nullptr, rows, d, (int64_t)-1);
+                                  dgamma ? (float*)workspace : (float*)nullptr, rows, d, (int64_t)-1, (const __nv_bfloat16*)gres);
   if (rc) return rc;
   if (dgamma) {
     ln_param_grad_reduce_kernel<<<(2 * d * 8 + 255) / 256, 256, 0, STREAM>>>((const float*)workspace, grid, d, 2, dgamma, dbeta, nullptr);
@@ -705,7 +847,8 @@ extern "C" int cx_embed_layernorm_bwd(const int64_t* ids, const int64_t* type_id
   const size_t smem = (size_t)8 * 3 * d * sizeof(float);
   int rc = ln_bwd_dispatch<true>(d, grid, smem, STREAM, (const __nv_bfloat16*)word_emb, (const __nv_bfloat16*)nullptr, ids, type_ids,
                                  (const __nv_bfloat16*)type_emb, (const __nv_bfloat16*)g1, (const __nv_bfloat16*)g2, gamma, stats,
-                                 (__nv_bfloat16*)nullptr, dword, dtype_emb, (float*)workspace, rows, d, padding_idx);
+                                 (__nv_bfloat16*)nullptr, dword, dtype_emb, (float*)workspace, rows, d, padding_idx,
+                                 (const __nv_bfloat16*)nullptr);
   if (rc) return rc;
   // type_ids == NULL: every token is type 0, its embedding-row gradient is the third column-sum partial
   ln_param_grad_reduce_kernel<<<(3 * d * 8 + 255) / 256, 256, 0, STREAM>>>((const float*)workspace, grid, d, 3, dgamma, dbeta,
@@ -832,6 +975,74 @@ extern "C" int cx_cast_f32_bf16(const float* x, void* y, int64_t n, cx_stream_t 
   CX_REQUIRE(x && y, "cx_cast_f32_bf16: null pointer");
   if (n <= 0) return 0;
   cast_f32_bf16_kernel<<<8 * sm_count(), 256, 0, STREAM>>>(x, (__nv_bfloat16*)y, n);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cx_colsum_bf16(const void* x, int64_t T, int N, float* out, cx_stream_t stream) {
+  CX_REQUIRE(x && out, "cx_colsum_bf16: null pointer");
+  CX_REQUIRE(N % 8 == 0, "cx_colsum_bf16: N must be a multiple of 8");
+  if (T <= 0) return 0;
+  const int rows_per_block = 256;
+  dim3 grid((N / 8 + 127) / 128, (unsigned)((T + rows_per_block - 1) / rows_per_block));
+  colsum_kernel<<<grid, 128, 0, STREAM>>>((const __nv_bfloat16*)x, T, N, out, rows_per_block);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int cx_act_fwd(const void* x, void* y, int64_t n, int kind, cx_stream_t stream) {
+  CX_REQUIRE(x && y, "cx_act_fwd: null pointer");
+  CX_REQUIRE(n % 8 == 0 && (kind == 0 || kind == 1), "cx_act_fwd: n % 8 == 0, kind in {0 gelu, 1 quick_gelu}");
+  if (n <= 0) return 0;
+  act_fwd_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, STREAM>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n / 8, kind);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int cx_act_bwd(const void* dy, const void* x, void* dx, int64_t n, int kind, cx_stream_t stream) {
+  CX_REQUIRE(dy && x && dx, "cx_act_bwd: null pointer");
+  CX_REQUIRE(n % 8 == 0 && (kind == 0 || kind == 1), "cx_act_bwd: n % 8 == 0, kind in {0 gelu, 1 quick_gelu}");
+  if (n <= 0) return 0;
+  act_bwd_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, STREAM>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx, n / 8, kind);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int cx_patchify(const float* pixels, void* out, int B, int C, int Himg, int Wimg, int patch, cx_stream_t stream) {
+  CX_REQUIRE(pixels && out, "cx_patchify: null pointer");
+  CX_REQUIRE(Himg % patch == 0 && Wimg % patch == 0, "cx_patchify: image size must be a multiple of the patch size");
+  const int64_t n = (int64_t)B * C * Himg * Wimg;
+  if (n <= 0) return 0;
+  patchify_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>(pixels, (__nv_bfloat16*)out, B, C, Himg, Wimg, patch);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int cx_vit_assemble_fwd(const void* proj, const float* cls, const float* pos, void* z, int B, int nP, int d, cx_stream_t stream) {
+  CX_REQUIRE(proj && cls && pos && z, "cx_vit_assemble_fwd: null pointer");
+  CX_REQUIRE(d % 8 == 0, "cx_vit_assemble_fwd: d must be a multiple of 8");
+  const int64_t n = (int64_t)B * (nP + 1) * (d / 8);
+  if (n <= 0) return 0;
+  vit_assemble_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>((const __nv_bfloat16*)proj, cls, pos, (__nv_bfloat16*)z, B, nP, d);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int cx_vit_assemble_bwd(const void* dz, void* dproj, float* dcls, float* dpos, int B, int nP, int d, cx_stream_t stream) {
+  CX_REQUIRE(dz && dproj && dcls && dpos, "cx_vit_assemble_bwd: null pointer");
+  if (B <= 0) return 0;
+  vit_assemble_bwd_kernel<<<nP + 1, 256, 0, STREAM>>>((const __nv_bfloat16*)dz, (__nv_bfloat16*)dproj, dcls, dpos, B, nP, d);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int cx_cls_select_fwd(const void* h, float* out, int B, int S, int d, cx_stream_t stream) {
+  CX_REQUIRE(h && out, "cx_cls_select_fwd: null pointer");
+  const int64_t n = (int64_t)B * d;
+  if (n <= 0) return 0;
+  cls_select_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>((const __nv_bfloat16*)h, out, B, S, d);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int cx_cls_select_bwd(const float* g, void* dh, int B, int S, int d, cx_stream_t stream) {
+  CX_REQUIRE(g && dh, "cx_cls_select_bwd: null pointer");
+  const int64_t n = (int64_t)B * S * d;
+  if (n <= 0) return 0;
+  cls_select_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>(g, (__nv_bfloat16*)dh, B, S, d);
   CX_LAUNCH_CHECK();
   return 0;
 }

@@ -175,3 +175,20 @@ extern "C" int cx_gemm_qkv_rope(const void* x, const void* w, void* qkv, int T, 
   g.stream = static_cast<cudaStream_t>(stream);
   return cx::launch_gemm(g);
 }
+
+// y[M,N] = x[M,K] w[N,K]^T + bias[N]  (bf16 in/out, fp32 bias added in the epilogue; replaces flash-attn FusedDense)
+extern "C" int cx_linear_bias_bf16(const void* x, const void* w, const float* bias, void* y, int M, int N, int K, int64_t ldx,
+                                   int64_t ldw, int64_t ldy, cx_stream_t stream) {
+  CX_REQUIRE(x && w && y, "cx_linear_bias_bf16: null pointer");
+  cx::GemmArgs g{};
+  g.A = x; g.B = w; g.C = y;
+  g.M = M; g.N = N; g.K = K;
+  g.a_mn = false; g.b_mn = false;
+  g.lda = ldx; g.ldb = ldw; g.ldc = ldy;
+  g.out_f32 = false; g.accumulate = false; g.splits = 1;
+  g.mode = cx::EPI_STORE;
+  g.ep.alpha = 1.f;
+  g.ep.bias = bias;
+  g.stream = static_cast<cudaStream_t>(stream);
+  return cx::launch_gemm(g);
+}

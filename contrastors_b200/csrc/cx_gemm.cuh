@@ -48,6 +48,7 @@ struct EpiParams {
   float* dlogit_part = nullptr;  // [gridDim.x]
   // EPI_STORE bf16 with rotary embedding fused (QKV projection): columns [0, rope_cols) are heads of 64 whose halves
   // (x1 = first 32, x2 = last 32) are rotated by cos/sin[rope_pos[row]][0..32)   (layers/embedding.py:685-706)
+  const float* bias = nullptr;  // EPI_STORE bf16: out = alpha * acc + bias[col]  (FusedDense: layers/attention.py:82-85, mlp.py:24)
   const int* rope_pos = nullptr;
   const float* rope_cos = nullptr;
   const float* rope_sin = nullptr;
@@ -322,6 +323,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const float b0 = __uint_as_float(v2[2 * j]) * ep_alpha, b1 = __uint_as_float(v2[2 * j + 1]) * ep_alpha;
               pk1[j] = pack_bf16x2(a0 * c2.x - b0 * s2.x, a1 * c2.y - b1 * s2.y);
               pk2[j] = pack_bf16x2(b0 * c2.x + a0 * s2.x, b1 * c2.y + a1 * s2.y);
+            }
+          } else if (ep.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {  // every thread reads the same addresses: one broadcast wavefront per load
+              const int c1 = col0 + 2 * j, c2 = c1 + 32;
+              const float b10 = c1 < N ? ep.bias[c1] : 0.f, b11 = c1 + 1 < N ? ep.bias[c1 + 1] : 0.f;
+              const float b20 = c2 < N ? ep.bias[c2] : 0.f, b21 = c2 + 1 < N ? ep.bias[c2 + 1] : 0.f;
+              pk1[j] = pack_bf16x2(fmaf(__uint_as_float(v1[2 * j]), ep_alpha, b10), fmaf(__uint_as_float(v1[2 * j + 1]), ep_alpha, b11));
+              pk2[j] = pack_bf16x2(fmaf(__uint_as_float(v2[2 * j]), ep_alpha, b20), fmaf(__uint_as_float(v2[2 * j + 1]), ep_alpha, b21));
             }
           } else {
 #pragma unroll

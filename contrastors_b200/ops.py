@@ -215,26 +215,27 @@ def _ws_bytes(nbytes, device):
     return torch.empty(max(int(nbytes), 16), device=device, dtype=torch.uint8)
 
 
-def add_layernorm_fwd(a, b, gamma, beta, eps):
-    """y = LN(a + b) (b may be None); returns (y bf16 [rows,d], stats fp32 [rows,2])."""
+def add_layernorm_fwd(a, b, gamma, beta, eps, want_z=False):
+    """y = LN(a + b) (b may be None); returns (y bf16 [rows,d], stats fp32 [rows,2]) (+ z = a + b when want_z)."""
     _require_cuda(a, b)
     rows, d = a.shape
     y = torch.empty_like(a)
+    z = torch.empty_like(a) if want_z else None
     stats = torch.empty(rows, 2, device=a.device, dtype=torch.float32)
     lib = _lib.load()
     _lib.check(lib.cx_add_layernorm_fwd(a.data_ptr(), _ptr(b), _ptr(gamma), _ptr(beta), y.data_ptr(), stats.data_ptr(),
-                                        rows, d, float(eps), _stream()), "cx_add_layernorm_fwd")
-    return y, stats
+                                        rows, d, float(eps), _ptr(z), _stream()), "cx_add_layernorm_fwd")
+    return (y, stats, z) if want_z else (y, stats)
 
 
-def add_layernorm_bwd(a, b, g1, g2, gamma, stats, dgamma, dbeta):
-    """dz (bf16) for z = a + b given upstream g1 (+ g2); ADDS into dgamma/dbeta (fp32) when given."""
+def add_layernorm_bwd(a, b, g1, g2, gamma, stats, dgamma, dbeta, gres=None):
+    """dz (bf16) for z = a + b given upstream g1 (+ g2) (+ gres on the residual stream); ADDS into dgamma/dbeta."""
     rows, d = a.shape
     dz = torch.empty_like(a)
     lib = _lib.load()
     ws = _ws_bytes(lib.cx_layernorm_bwd_workspace_bytes(d), a.device) if dgamma is not None else None
     _lib.check(lib.cx_add_layernorm_bwd(a.data_ptr(), _ptr(b), g1.data_ptr(), _ptr(g2), _ptr(gamma), stats.data_ptr(),
-                                        dz.data_ptr(), _ptr(dgamma), _ptr(dbeta), _ptr(ws), rows, d, _stream()),
+                                        dz.data_ptr(), _ptr(dgamma), _ptr(dbeta), _ptr(ws), rows, d, _ptr(gres), _stream()),
                "cx_add_layernorm_bwd")
     return dz
 
@@ -396,3 +397,87 @@ def cast_f32_bf16(x, out=None):
     lib = _lib.load()
     _lib.check(lib.cx_cast_f32_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "cx_cast_f32_bf16")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ ViT ops
+ACT_GELU, ACT_QUICK_GELU = 0, 1
+
+
+def linear_bias(x, w, bias):
+    """y = x w^T + bias (bias fp32 or None) on the tcgen05 GEMM."""
+    if bias is None:
+        return gemm(x, w)
+    _require_cuda(x, w, bias)
+    M, K = x.shape
+    N = w.shape[0]
+    y = torch.empty(M, N, device=x.device, dtype=torch.bfloat16)
+    lib = _lib.load()
+    ev = TIMER.begin("gemm") if TIMER is not None else None
+    _lib.check(lib.cx_linear_bias_bf16(x.data_ptr(), w.data_ptr(), bias.data_ptr(), y.data_ptr(), M, N, K, x.stride(0),
+                                       w.stride(0), y.stride(0), _stream()), "cx_linear_bias_bf16")
+    if ev is not None:
+        TIMER.end("gemm", 2.0 * M * N * K, ev)
+    return y
+
+
+def colsum_into(x, out):
+    lib = _lib.load()
+    _lib.check(lib.cx_colsum_bf16(x.data_ptr(), x.shape[0], x.shape[1], out.data_ptr(), _stream()), "cx_colsum_bf16")
+
+
+def act_fwd(x, kind):
+    y = torch.empty_like(x)
+    _lib.check(_lib.load().cx_act_fwd(x.data_ptr(), y.data_ptr(), x.numel(), kind, _stream()), "cx_act_fwd")
+    return y
+
+
+def act_bwd(dy, x, kind):
+    dx = torch.empty_like(x)
+    _lib.check(_lib.load().cx_act_bwd(dy.data_ptr(), x.data_ptr(), dx.data_ptr(), x.numel(), kind, _stream()), "cx_act_bwd")
+    return dx
+
+
+def patchify(pixels, patch):
+    B, C, H, W = pixels.shape
+    px = pixels.float().contiguous()
+    K = C * patch * patch
+    rows = B * (H // patch) * (W // patch)
+    if K % 8 == 0:
+        out = torch.empty(rows, K, device=px.device, dtype=torch.bfloat16)
+        _lib.check(_lib.load().cx_patchify(px.data_ptr(), out.data_ptr(), B, C, H, W, patch, _stream()), "cx_patchify")
+        return out
+    tmp = torch.empty(rows, K, device=px.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().cx_patchify(px.data_ptr(), tmp.data_ptr(), B, C, H, W, patch, _stream()), "cx_patchify")
+    out = torch.zeros(rows, (K + 7) // 8 * 8, device=px.device, dtype=torch.bfloat16)
+    out[:, :K] = tmp
+    return out[:, :K]
+
+
+def vit_assemble_fwd(proj, cls, pos, B, nP):
+    d = proj.shape[1]
+    z = torch.empty(B * (nP + 1), d, device=proj.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().cx_vit_assemble_fwd(proj.data_ptr(), cls.data_ptr(), pos.data_ptr(), z.data_ptr(), B, nP, d, _stream()),
+               "cx_vit_assemble_fwd")
+    return z
+
+
+def vit_assemble_bwd(dz, dcls, dpos, B, nP):
+    d = dz.shape[1]
+    dproj = torch.empty(B * nP, d, device=dz.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().cx_vit_assemble_bwd(dz.data_ptr(), dproj.data_ptr(), dcls.data_ptr(), dpos.data_ptr(), B, nP, d,
+                                               _stream()), "cx_vit_assemble_bwd")
+    return dproj
+
+
+def cls_select_fwd(h, B, S):
+    d = h.shape[1]
+    out = torch.empty(B, d, device=h.device, dtype=torch.float32)
+    _lib.check(_lib.load().cx_cls_select_fwd(h.data_ptr(), out.data_ptr(), B, S, d, _stream()), "cx_cls_select_fwd")
+    return out
+
+
+def cls_select_bwd(g, B, S):
+    d = g.shape[1]
+    dh = torch.empty(B * S, d, device=g.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().cx_cls_select_bwd(g.data_ptr(), dh.data_ptr(), B, S, d, _stream()), "cx_cls_select_bwd")
+    return dh

@@ -99,16 +99,18 @@ CX_API int cx_l2norm_bwd(const float* x, int64_t ldx, const float* g, int64_t ld
 
 /* ---- fused (dropout-)add-LayerNorm (replaces flash-attn dropout_add_layer_norm: layers/block.py:422-431,453-462,
  *      models/encoder/modeling_nomic_bert.py:531-535).  y = LN(a + b) * gamma + beta; b may be NULL;
- *      stats[rows][2] = (mean, rstd) for the backward. */
+ *      stats[rows][2] = (mean, rstd) for the backward; z_out (bf16, may be NULL) receives z = a + b, the residual
+ *      stream of the pre-norm blocks (layers/block.py:293-388, ViT). */
 CX_API int cx_add_layernorm_fwd(const void* a, const void* b, const float* gamma, const float* beta, void* y, float* stats,
-                         int rows, int d, float eps, cx_stream_t stream);
+                         int rows, int d, float eps, void* z_out, cx_stream_t stream);
 /* backward: z = a + b is recomputed, upstream gradient g = g1 + g2 (g2 may be NULL); writes dz (bf16, the gradient of
  * both a and b) and ADDS the parameter gradients into dgamma/dbeta (pass both NULL to skip them).
- * workspace: cx_layernorm_bwd_workspace_bytes(d). */
+ * workspace: cx_layernorm_bwd_workspace_bytes(d).  gres (bf16, may be NULL): gradient arriving on the residual stream
+ * z itself (pre-norm blocks), added to dz. */
 CX_API size_t cx_layernorm_bwd_workspace_bytes(int d);
 CX_API int cx_add_layernorm_bwd(const void* a, const void* b, const void* g1, const void* g2, const float* gamma,
                          const float* stats, void* dz, float* dgamma, float* dbeta, void* workspace, int rows, int d,
-                         cx_stream_t stream);
+                         const void* gres, cx_stream_t stream);
 /* ---- embeddings + emb_ln (layers/embedding.py:594-615 + modeling_nomic_bert.py:531-534): y = LN(word[ids] + type[type_ids]).
  *      type_ids may be NULL (all zeros).  Backward scatters into the fp32 table gradients (atomic adds), ADDS dgamma/dbeta. */
 CX_API int cx_embed_layernorm_fwd(const int64_t* ids, const int64_t* type_ids, const void* word_emb, const void* type_emb,
@@ -149,6 +151,21 @@ CX_API int cx_adamw_step(float* param, float* grad, float* exp_avg, float* exp_a
                   float beta1, float beta2, float eps, float weight_decay, int step, const float* grad_scale_dev,
                   float grad_scale, int zero_grad, cx_stream_t stream);
 CX_API int cx_cast_f32_bf16(const float* x, void* y, int64_t n, cx_stream_t stream);
+
+/* ---- ViT tower pieces (models/vit/vit.py:176-276, layers/embedding.py:465-516, layers/mlp.py:8-34)
+ * cx_linear_bias_bf16: y = x w^T + bias (FusedDense); cx_colsum_bf16: out[N] += column sums (bias gradients);
+ * cx_act_*: kind 0 = gelu(erf), 1 = quick_gelu; cx_patchify: pixels [B,C,H,W] fp32 -> patch rows [B*gh*gw, C*p*p] bf16;
+ * cx_vit_assemble_*: cls token + learned position embedding; cx_cls_select_*: ClsSelector (modeling_biencoder.py:44-49). */
+CX_API int cx_linear_bias_bf16(const void* x, const void* w, const float* bias, void* y, int M, int N, int K, int64_t ldx,
+                        int64_t ldw, int64_t ldy, cx_stream_t stream);
+CX_API int cx_colsum_bf16(const void* x, int64_t T, int N, float* out, cx_stream_t stream);
+CX_API int cx_act_fwd(const void* x, void* y, int64_t n, int kind, cx_stream_t stream);
+CX_API int cx_act_bwd(const void* dy, const void* x, void* dx, int64_t n, int kind, cx_stream_t stream);
+CX_API int cx_patchify(const float* pixels, void* out, int B, int C, int Himg, int Wimg, int patch, cx_stream_t stream);
+CX_API int cx_vit_assemble_fwd(const void* proj, const float* cls, const float* pos, void* z, int B, int nP, int d, cx_stream_t stream);
+CX_API int cx_vit_assemble_bwd(const void* dz, void* dproj, float* dcls, float* dpos, int B, int nP, int d, cx_stream_t stream);
+CX_API int cx_cls_select_fwd(const void* h, float* out, int B, int S, int d, cx_stream_t stream);
+CX_API int cx_cls_select_bwd(const float* g, void* dh, int B, int S, int d, cx_stream_t stream);
 
 /* ---- varlen non-causal attention on tcgen05 (replaces flash_attn_varlen_qkvpacked_func: layers/attention.py:158-181)
  * qkv [T,3,H,Dh] bf16 (RoPE already applied), cu_seqlens int32[nseq+1]; out [T,H,Dh] bf16; lse [H,T] fp32 (natural log).

@@ -33,6 +33,10 @@ ENCODER_CASES = {
     "tiny3": dict(vocab=512, n_embd=192, n_head=3, n_inner=512, n_layer=3, seq=130, batch=2, wseed=6, seed=42,
                   rope_base=10000.0, lens=[130, 77]),
 }
+VIT_CASES = {
+    "tiny": dict(n_embd=128, n_head=2, n_inner=256, n_layer=2, img=64, patch=16, act="quick_gelu", batch=3, wseed=8, seed=61),
+    "tiny_gelu": dict(n_embd=192, n_head=3, n_inner=384, n_layer=2, img=96, patch=32, act="gelu", batch=2, wseed=9, seed=62),
+}
 GRADCACHE_CASE = dict(n=8, chunk=3, din=16, dout=32, scale=20.0, seed=51)
 
 
@@ -96,3 +100,16 @@ class TinyTower(torch.nn.Module):
     def forward(self, input_ids):
         h = torch.tanh(self.fc1(input_ids))
         return {"embedding": torch.nn.functional.normalize(self.fc2(h), dim=-1)}
+
+
+def vit_cfg(case):
+    from oracle.vit import ViTConfig
+    return ViTConfig(n_embd=case["n_embd"], n_head=case["n_head"], n_inner=case["n_inner"], n_layer=case["n_layer"],
+                     img_size=case["img"], patch_size=case["patch"], activation_function=case["act"])
+
+
+def make_vit_inputs(case):
+    rs = np.random.RandomState(case["seed"])
+    px = rs.randn(case["batch"], 3, case["img"], case["img"]).astype(np.float32)
+    g = rs.randn(case["batch"], case["n_embd"]).astype(np.float32)
+    return px, g

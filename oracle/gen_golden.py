@@ -228,6 +228,66 @@ def gen_encoder():
         print("encoder", name, "emb[0,:4]", emb[0, :4].tolist())
 
 
+def gen_vit():
+    """transformers.CLIPVisionModel (the reference's own ViT oracle, tests/test_flash_openclip.py:20-57) on weights that
+    map to our reference-named state dict through the reference's remap_state_dict_hf_clip (models/vit/clip.py:56-173)."""
+    import importlib
+    from transformers import CLIPVisionConfig, CLIPVisionModel
+    from oracle.cases import VIT_CASES, make_vit_inputs, vit_cfg
+    from oracle.vit import random_state_dict as vit_sd
+    ref_loader.load()
+    ref_loader._pkg("contrastors.models.vit", os.path.join(ref_loader.REF_ROOT, "models", "vit"))
+    clip = importlib.import_module("contrastors.models.vit.clip")
+    for name, case in VIT_CASES.items():
+        cfg = vit_cfg(case)
+        sd = vit_sd(cfg, seed=case["wseed"])
+        hf_cfg = CLIPVisionConfig(hidden_size=cfg.n_embd, intermediate_size=cfg.n_inner, num_hidden_layers=cfg.n_layer,
+                                  num_attention_heads=cfg.n_head, image_size=cfg.img_size, patch_size=cfg.patch_size,
+                                  hidden_act=cfg.activation_function, layer_norm_eps=cfg.layer_norm_epsilon)
+        hf = CLIPVisionModel(hf_cfg)
+        d = cfg.n_embd
+        m = {"vision_model.embeddings.class_embedding": sd["embeddings.cls_token"].reshape(d),
+             "vision_model.embeddings.patch_embedding.weight": sd["embeddings.proj.weight"].reshape(d, 3, cfg.patch_size, cfg.patch_size),
+             "vision_model.embeddings.position_embedding.weight": sd["embeddings.pos_embed"][0],
+             "vision_model.pre_layrnorm.weight": sd["prepre_layernom.weight"], "vision_model.pre_layrnorm.bias": sd["prepre_layernom.bias"],
+             "vision_model.post_layernorm.weight": sd["ln_f.weight"], "vision_model.post_layernorm.bias": sd["ln_f.bias"]}
+        for i in range(cfg.n_layer):
+            a, b = f"vision_model.encoder.layers.{i}.", f"layers.{i}."
+            wq, wk, wv = sd[b + "attn.Wqkv.weight"].chunk(3, 0)
+            bq, bk, bv = sd[b + "attn.Wqkv.bias"].chunk(3, 0)
+            m.update({a + "self_attn.q_proj.weight": wq, a + "self_attn.k_proj.weight": wk, a + "self_attn.v_proj.weight": wv,
+                      a + "self_attn.q_proj.bias": bq, a + "self_attn.k_proj.bias": bk, a + "self_attn.v_proj.bias": bv,
+                      a + "self_attn.out_proj.weight": sd[b + "attn.out_proj.weight"], a + "self_attn.out_proj.bias": sd[b + "attn.out_proj.bias"],
+                      a + "layer_norm1.weight": sd[b + "norm1.weight"], a + "layer_norm1.bias": sd[b + "norm1.bias"],
+                      a + "layer_norm2.weight": sd[b + "norm2.weight"], a + "layer_norm2.bias": sd[b + "norm2.bias"],
+                      a + "mlp.fc1.weight": sd[b + "mlp.fc1.weight"], a + "mlp.fc1.bias": sd[b + "mlp.fc1.bias"],
+                      a + "mlp.fc2.weight": sd[b + "mlp.fc2.weight"], a + "mlp.fc2.bias": sd[b + "mlp.fc2.bias"]})
+        missing, unexpected = hf.load_state_dict(m, strict=False)
+        assert not unexpected and all("position_ids" in k for k in missing), (missing, unexpected)
+        # the reference's own remap must take the HF weights back to our reference-named dict
+        vit_config = types.SimpleNamespace(activation_function=cfg.activation_function, n_layer=cfg.n_layer)
+        back = clip.remap_state_dict_hf_clip({k: v.clone() for k, v in hf.state_dict().items()}, vit_config)
+        for k, v in sd.items():
+            assert torch.equal(back[k].reshape(v.shape), v), k
+        px, g = make_vit_inputs(case)
+        hf.train()
+        out = hf(pixel_values=torch.tensor(px)).pooler_output
+        (out * torch.tensor(g)).sum().backward()
+        grads = {k: p.grad for k, p in hf.named_parameters()}
+        res = dict(cls=out.detach().numpy(),
+                   g_fc2_last=grads[f"vision_model.encoder.layers.{cfg.n_layer - 1}.mlp.fc2.weight"].numpy(),
+                   g_fc1_bias0=grads["vision_model.encoder.layers.0.mlp.fc1.bias"].numpy(),
+                   g_out_proj0=grads["vision_model.encoder.layers.0.self_attn.out_proj.weight"].numpy(),
+                   g_qbias0=grads["vision_model.encoder.layers.0.self_attn.q_proj.bias"].numpy(),
+                   g_pos=grads["vision_model.embeddings.position_embedding.weight"].numpy(),
+                   g_cls=grads["vision_model.embeddings.class_embedding"].numpy(),
+                   g_patch_proj=(grads["vision_model.embeddings.patch_embedding.weight"].reshape(d, -1)
+                                 @ torch.linspace(-1.0, 1.0, 3 * cfg.patch_size ** 2)).numpy(),
+                   g_prepre_w=grads["vision_model.pre_layrnorm.weight"].numpy(), g_lnf_b=grads["vision_model.post_layernorm.bias"].numpy())
+        np.savez_compressed(os.path.join(GOLDEN, f"vit_{name}.npz"), **res)
+        print("vit", name, out[0, :4].tolist())
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("needs /root/reference (build container only)")
@@ -256,6 +316,7 @@ def main():
         np.savez_compressed(os.path.join(GOLDEN, f"gradcache_ws{ws}.npz"), **out)
         print("gradcache", ws, {k: v.item() for k, v in out.items() if "loss" in k})
     gen_encoder()
+    gen_vit()
 
 
 if __name__ == "__main__":

@@ -2,5 +2,4 @@
 set -x
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-timeout 1200 python bench.py 2>&1 | tail -2 | tee gpurun_out/bench_default.log
-timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1 | tee gpurun_out/bench_reference.log
+timeout 900 python -m pytest tests/test_gpu_vit.py -x -q -m gpu 2>&1 | tail -30 | tee gpurun_out/tests_vit.log

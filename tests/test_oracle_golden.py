@@ -131,3 +131,29 @@ def test_bf16_round():
     x = np.array([1.0, 1.00390625, 1.005859375, -3.14159, 1e-30, 65504.0], dtype=np.float32)
     want = torch.tensor(x).to(torch.bfloat16).float().numpy()
     assert np.array_equal(O.bf16_round(x), want)
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_gelu"])
+def test_vit_oracle_vs_hf_clip_golden(name):
+    """oracle/vit.py against transformers.CLIPVisionModel outputs/gradients (generated through the reference's remap)."""
+    from oracle.cases import VIT_CASES, make_vit_inputs, vit_cfg
+    from oracle.vit import random_state_dict as vit_sd, vit_forward
+    case = VIT_CASES[name]
+    cfg = vit_cfg(case)
+    z = golden(f"vit_{name}.npz")
+    sd = {k: v.clone().requires_grad_() for k, v in vit_sd(cfg, seed=case["wseed"]).items()}
+    px, g = make_vit_inputs(case)
+    out = vit_forward(sd, cfg, torch.tensor(px))
+    close(out.detach().numpy(), z["cls"], rtol=1e-4, atol=1e-5)
+    (out * torch.tensor(g)).sum().backward()
+    L = cfg.n_layer - 1
+    close(sd[f"layers.{L}.mlp.fc2.weight"].grad.numpy(), z["g_fc2_last"], rtol=2e-3, atol=1e-7)
+    close(sd["layers.0.mlp.fc1.bias"].grad.numpy(), z["g_fc1_bias0"], rtol=2e-3, atol=1e-7)
+    close(sd["layers.0.attn.out_proj.weight"].grad.numpy(), z["g_out_proj0"], rtol=2e-3, atol=1e-7)
+    close(sd["layers.0.attn.Wqkv.bias"].grad.numpy()[:cfg.n_embd], z["g_qbias0"], rtol=2e-3, atol=1e-7)
+    close(sd["embeddings.pos_embed"].grad.numpy()[0], z["g_pos"], rtol=2e-3, atol=1e-7)
+    close(sd["embeddings.cls_token"].grad.numpy().reshape(-1), z["g_cls"], rtol=2e-3, atol=1e-7)
+    K = 3 * cfg.patch_size ** 2
+    close(sd["embeddings.proj.weight"].grad.numpy() @ np.linspace(-1.0, 1.0, K, dtype=np.float32), z["g_patch_proj"], rtol=2e-3, atol=1e-6)
+    close(sd["prepre_layernom.weight"].grad.numpy(), z["g_prepre_w"], rtol=2e-3, atol=1e-7)
+    close(sd["ln_f.bias"].grad.numpy(), z["g_lnf_b"], rtol=2e-3, atol=1e-7)
