@@ -200,3 +200,22 @@ def test_full_size_properties():
     b = (dd.double() * db.double()).sum().item()
     assert abs(a - b) <= 2e-3 * abs(a) + 1e-4
     assert abs(st[2].item() - a) <= 3e-3 * abs(a) + 1e-4
+
+
+def test_grad_cache_driver_vs_reference_golden():
+    """grad_cache_loss with a generic torch tower (the reference's driver contract, loss.py:135-213) against the loss and
+    parameter gradients the reference's own grad_cache_loss produced (tests/golden/gradcache_ws1.npz, fp32 CPU run).
+    The tower runs under bf16 autocast here exactly as the reference does on a GPU, hence the 3e-2 tolerance."""
+    from contrastors_b200 import LogitScale, grad_cache_loss
+    from oracle.cases import GRADCACHE_CASE, TinyTower, make_gradcache_inputs
+    case = dict(GRADCACHE_CASE, ws=1)
+    z = golden("gradcache_ws1.npz")
+    tower = TinyTower(case).cuda()
+    xq, xd = make_gradcache_inputs(case, 0)
+    ls = LogitScale(logit_scale=case["scale"]).cuda()
+    loss = grad_cache_loss(tower, {"input_ids": torch.tensor(xq).cuda()}, tower, {"input_ids": torch.tensor(xd).cuda()},
+                           case["chunk"], ls)
+    assert abs(loss.item() - float(z["r0_loss"])) <= 5e-2 * max(float(z["r0_loss"]), 1e-2) + 2e-3
+    for k, p in tower.named_parameters():
+        ref = z["r0_gc_" + k]
+        assert np.abs(p.grad.cpu().numpy() - ref).max() <= 5e-2 * np.abs(ref).max() + 1e-5, k
