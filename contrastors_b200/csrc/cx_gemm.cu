@@ -1,6 +1,8 @@
 // Host launcher + C entry point for the tcgen05 GEMM (see cx_gemm.cuh for the kernel).
 #include "cx_gemm.cuh"
 
+#include <stdlib.h>
+
 namespace cx {
 
 int gemm_block_n(int N) { return (N % 256 == 0) ? 256 : 128; }
@@ -9,12 +11,52 @@ int gemm_grid(int M, int N, int splits, int tile_n) {
   const int bn = tile_n > 0 ? tile_n : gemm_block_n(N);
   const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + bn - 1) / bn) * splits;
   const int sms = sm_count();
-  return tiles < sms ? tiles : sms;
+  return tiles < sms ? tiles : sms;  // an upper bound on the CTA count in every launch mode (single or paired)
+}
+
+// CTA-pair (tcgen05 cta_group::2, 256 x 256 tiles) launch mode.  Numerically verified on B200 (the whole GEMM / InfoNCE
+// test-suite passes with it), but in its first form it runs at ~0.55x the single-CTA kernel (707 vs 1300 TFLOP/s at
+// 8192^3), so it is opt-in (CX_PAIR=1) until the operand-sharing path is tuned.
+bool gemm_use_pair(const GemmArgs& g) {
+  static const bool enabled = getenv("CX_PAIR") != nullptr;
+  return enabled && g.M >= 256 && ((g.mode == EPI_SWIGLU) || g.N % 256 == 0);
+}
+
+template <int MODE, bool OUT_F32, bool ACCUM, bool A_MN, bool B_MN>
+static int launch_pair(const GemmArgs& g, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                       const CUtensorMap& tmD) {
+  auto kern = gemm_kernel<256, A_MN, B_MN, MODE, OUT_F32, ACCUM, true>;
+  constexpr int smem = GemmSmem<256, true>::kTotal;
+  static bool configured = false;
+  if (!configured) {
+    CX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int tile_n = (MODE == EPI_SWIGLU) ? 128 : 256;
+  const int tiles = ((g.M + 255) / 256) * ((g.N + tile_n - 1) / tile_n) * g.splits;
+  int clusters = sm_count() / 2;
+  if (tiles < clusters) clusters = tiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = g.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CX_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmD, g.M, g.N, g.K, g.splits, g.ep));
+  CX_LAUNCH_CHECK();
+  return 0;
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int MODE, bool OUT_F32, bool ACCUM>
 static int launch_one(const GemmArgs& g, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                       const CUtensorMap& tmD) {
+  if (BLOCK_N == 256 && gemm_use_pair(g)) return launch_pair<MODE, OUT_F32, ACCUM, A_MN, B_MN>(g, tmA, tmB, tmC, tmD);
   auto kern = gemm_kernel<BLOCK_N, A_MN, B_MN, MODE, OUT_F32, ACCUM>;
   constexpr int smem = GemmSmem<BLOCK_N>::kTotal;
   static bool configured = false;  // per instantiation
@@ -93,8 +135,9 @@ int launch_gemm(const GemmArgs& g_in) {
   if (!g.a_mn) rc = make_tmap_2d(&tmA, BF, 2, g.A, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)g.lda * 2, kBlockK, kBlockM, SW);
   else rc = make_tmap_2d(&tmA, BF, 2, g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda * 2, 64, kBlockK, SW);
   if (rc) return rc;
+  const bool pair = (bn == 256) && gemm_use_pair(g);
   if (g.mode == EPI_SWIGLU) rc = make_tmap_2d(&tmB, BF, 2, g.B, (uint64_t)g.K, (uint64_t)2 * g.N, (uint64_t)g.ldb * 2, kBlockK, 128, SW);
-  else if (!g.b_mn) rc = make_tmap_2d(&tmB, BF, 2, g.B, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb * 2, kBlockK, (uint32_t)bn, SW);
+  else if (!g.b_mn) rc = make_tmap_2d(&tmB, BF, 2, g.B, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb * 2, kBlockK, pair ? 128u : (uint32_t)bn, SW);
   else rc = make_tmap_2d(&tmB, BF, 2, g.B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb * 2, 64, kBlockK, SW);
   if (rc) return rc;
   CUtensorMap tmD;

@@ -68,23 +68,31 @@ constexpr int kUmmaK = 16;
 constexpr int kGemmThreads = 384;  // 4 control warps + 8 epilogue warps (2 per SMSP: TLP hides TMEM-load latency)
 constexpr int kStageCBytes = 16384;  // 128 rows x 128 B
 
-template <int BLOCK_N>
+// PAIR: two CTAs of a cluster cooperate on one 256 x 256 tile (tcgen05 cta_group::2): each CTA stages its own 128 rows of
+// A and 128 of the 256 B rows (so the B operand is read from shared memory once per SM pair), the leader CTA issues the
+// MMAs for both, each CTA drains the 128 x 256 half of the accumulator that lives in its own TMEM.
+template <int BLOCK_N, bool PAIR = false>
 struct GemmSmem {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
-  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kBBytes = (PAIR ? BLOCK_N / 2 : BLOCK_N) * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kStages = PAIR ? 6 : ((BLOCK_N == 256) ? 4 : 6);
   static constexpr int kBarrierBytes = 256;
   static constexpr int kTotal = 1024 + kStages * kStageBytes + 2 * kStageCBytes + kBarrierBytes;
 };
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int MODE, bool OUT_F32, bool ACCUM>
+template <int BLOCK_N, bool A_MN, bool B_MN, int MODE, bool OUT_F32, bool ACCUM, bool PAIR = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD, int M, int N, int K,
             int splits, EpiParams ep) {
-  using S = GemmSmem<BLOCK_N>;
+  using S = GemmSmem<BLOCK_N, PAIR>;
+  static_assert(!PAIR || BLOCK_N == 256, "CTA pairs use 256-column tiles");
   constexpr int kStages = S::kStages;
+  constexpr int TILE_M = PAIR ? 2 * kBlockM : kBlockM;  // rows per work item
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const int tile_start = PAIR ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int tile_step = PAIR ? (int)num_clusters_x() : (int)gridDim.x;
   constexpr uint32_t kTmemCols = 2 * BLOCK_N;
   static_assert(kTmemCols <= 512, "TMEM budget");
 
@@ -100,7 +108,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_tiles = (M + kBlockM - 1) / kBlockM;
+  const int m_tiles = (M + TILE_M - 1) / TILE_M;
   constexpr int TILE_N = (MODE == EPI_SWIGLU) ? BLOCK_N / 2 : BLOCK_N;  // output columns per tile
   const int n_tiles = (N + TILE_N - 1) / TILE_N;
   const int num_tiles = m_tiles * n_tiles * splits;  // split-K slices are separate work items (reduce-add epilogue)
@@ -114,18 +122,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(&full_bar[i], 1);
+      mbar_init(&full_bar[i], PAIR ? 2 : 1);   // pair: leader's expect_tx arrive + the peer producer's remote arrive
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 256);
+      mbar_init(&tempty_bar[i], PAIR ? 512 : 256);  // pair: both CTAs' epilogue threads arrive on the leader's barrier
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr);
+  if (warp == 2) {
+    if (PAIR) tmem_alloc_2cta<kTmemCols>(tmem_ptr);
+    else tmem_alloc<kTmemCols>(tmem_ptr);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -134,15 +146,40 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile_start; tile < num_tiles; tile += tile_step) {
         const int mn = tile / splits, ks = tile % splits;
-        const int m0 = (mn / n_tiles) * kBlockM;
+        const int m0 = (mn / n_tiles) * TILE_M + (int)cta_rank * kBlockM;
         const int n0 = (mn % n_tiles) * TILE_N;
         const int kb0 = (int)((long long)ks * num_kb / splits), kb1 = (int)((long long)(ks + 1) * num_kb / splits);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * S::kStageBytes;
           uint8_t* sB = sA + S::kABytes;
+          if (PAIR) {
+            // both CTAs' TMA bytes are credited to the LEADER's full barrier
+            const uint32_t lead_bar = smem_u32(&full_bar[stage]) & 0xFEFFFFFFu;
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
+            else mbar_arrive_cluster(mapa_u32(smem_u32(&full_bar[stage]), 0));
+            if (!A_MN) {
+              tma_load_2d_2sm(sA, &tmA, lead_bar, kb * kBlockK, m0);
+            } else {
+#pragma unroll
+              for (int i = 0; i < kBlockM / 64; ++i) tma_load_2d_2sm(sA + i * 8192, &tmA, lead_bar, m0 + i * 64, kb * kBlockK);
+            }
+            // this CTA's half of the B rows: pair rank r stages rows [n0 + 128 r, +128) (SwiGLU: r = 0 -> fc11, r = 1 -> fc12)
+            const int nb = (MODE == EPI_SWIGLU) ? n0 + (int)cta_rank * N : n0 + (int)cta_rank * (BLOCK_N / 2);
+            if (!B_MN) {
+              tma_load_2d_2sm(sB, &tmB, lead_bar, kb * kBlockK, nb);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BLOCK_N / 128; ++i) tma_load_2d_2sm(sB + i * 8192, &tmB, lead_bar, nb + i * 64, kb * kBlockK);
+            }
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
           if (!A_MN) {
             tma_load_2d(sA, &tmA, &full_bar[stage], kb * kBlockK, m0);
@@ -168,13 +205,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
+    if (lane == 0 && cta_rank == 0) {  // pair: only the leader CTA issues (for both)
       // a_format [7,10) / b_format [10,13): 1 = bf16, 0 = f16
-      const uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, A_MN ? 1u : 0u, B_MN ? 1u : 0u) & ~(ep.ab_f16 ? ((1u << 7) | (1u << 10)) : 0u);
+      const uint32_t idesc = make_idesc_bf16(TILE_M, BLOCK_N, A_MN ? 1u : 0u, B_MN ? 1u : 0u) & ~(ep.ab_f16 ? ((1u << 7) | (1u << 10)) : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile_start; tile < num_tiles; tile += tile_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -193,10 +230,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                         : make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
             const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024)
                                         : make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
-            umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (PAIR) umma_f16_ss_2cta(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
-          if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
+          if (PAIR) {
+            umma_commit_2cta(&empty_bar[stage]);
+            if (kb == kb1 - 1) umma_commit_2cta(&tfull_bar[acc]);
+          } else {
+            umma_commit(&empty_bar[stage]);
+            if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
+          }
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -219,12 +262,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const float ep_scale = ep.scale * (ep.scale_dev != nullptr ? *ep.scale_dev : 1.f);
     const float ep_coef = ep.coef * (ep.coef_dev != nullptr ? *ep.coef_dev : 1.f);
     const float ep_alpha = ep.alpha * (ep.alpha_dev != nullptr ? *ep.alpha_dev : 1.f) * (ep.alpha_dev2 != nullptr ? *ep.alpha_dev2 : 1.f);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile_start; tile < num_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int mn = tile / splits;
       const int mt = mn / n_tiles, nt = mn % n_tiles;
-      const int m0 = mt * kBlockM, n0 = (MODE == EPI_SWIGLU) ? nt * TILE_N + hf * (TILE_N / 2) : nt * BLOCK_N + hf * HALF_N;
+      const int m0 = mt * TILE_M + (int)cta_rank * kBlockM, n0 = (MODE == EPI_SWIGLU) ? nt * TILE_N + hf * (TILE_N / 2) : nt * BLOCK_N + hf * HALF_N;
       const int row = m0 + row_in_tile;
       const bool row_ok = row < M;
       // fast path: no column masks and no per-column scale anywhere in this tile
@@ -512,9 +555,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       }
-      // accumulator drained -> hand the TMEM buffer back to the MMA warp
+      // accumulator drained -> hand the TMEM buffer back to the MMA warp (pair: the leader CTA's barrier)
       tc_fence_before();
-      mbar_arrive(&tempty_bar[acc]);
+      if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+      else mbar_arrive(&tempty_bar[acc]);
 
       if (MODE == EPI_NCE_STATS && row_ok) {  // partials stay in the log2 domain; the combine kernel converts
         const size_t o = static_cast<size_t>(nt * 2 + hf) * M + row;
@@ -537,10 +581,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // neither CTA may free TMEM / exit while its peer can still touch it
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_base);
+    if (PAIR) tmem_dealloc_2cta<kTmemCols>(tmem_base);
+    else tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 

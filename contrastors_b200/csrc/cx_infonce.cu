@@ -287,11 +287,12 @@ extern "C" int cx_infonce_bwd(const void* q, int64_t ldq, const void* d, int64_t
   g.ep.ds_f16 = f16 ? 1 : 0;
   g.ep.dlogit_part = w.dlogit_part;
   g.stream = stream;
-  const int grid1 = gemm_grid(n, m, 1);
-  CX_REQUIRE(grid1 <= kMaxGrid, "cx_infonce_bwd: grid too large");
+  // every CTA of the stage-1 launch writes one partial; the array is zeroed first so the (launch-mode dependent) CTA
+  // count never matters
+  CX_CUDA_CHECK(cudaMemsetAsync(w.dlogit_part, 0, (size_t)kMaxGrid * sizeof(float), stream));
   int rc = launch_gemm(g);
   if (rc) return rc;
-  nce_dlogit_kernel<<<1, 32, 0, stream>>>(w.dlogit_part, grid1, stats);
+  nce_dlogit_kernel<<<1, 32, 0, stream>>>(w.dlogit_part, kMaxGrid, stats);
   CX_LAUNCH_CHECK();
   const void* qB = q;
   const void* dB = d;
