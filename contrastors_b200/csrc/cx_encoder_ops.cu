@@ -286,7 +286,7 @@ __global__ void ln_param_grad_reduce_kernel(const float* __restrict__ partials, 
   if (j >= np * d || sub != 0) return;
   const int which = j / d, col = j % d;
   float* dst = which == 0 ? o0 : (which == 1 ? o1 : o2);
-  if (dst != nullptr) dst[col] += acc;
+  if (dst != nullptr) atomicAdd(dst + col, acc);  // GradCache chunks may run on two streams: accumulate atomically
 }
 
 // ---------------------------------------------------------------------------------------------- token bookkeeping

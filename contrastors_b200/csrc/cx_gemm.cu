@@ -14,12 +14,13 @@ int gemm_grid(int M, int N, int splits, int tile_n) {
   return tiles < sms ? tiles : sms;  // an upper bound on the CTA count in every launch mode (single or paired)
 }
 
-// CTA-pair (tcgen05 cta_group::2, 256 x 256 tiles) launch mode.  Numerically verified on B200 (the whole GEMM / InfoNCE
-// test-suite passes with it), but in its first form it runs at ~0.55x the single-CTA kernel (707 vs 1300 TFLOP/s at
-// 8192^3), so it is opt-in (CX_PAIR=1) until the operand-sharing path is tuned.
+// CTA-pair (tcgen05 cta_group::2, 256 x 256 tiles) launch mode: the default whenever the shape allows it.  A single SM
+// with 128 x 256 tiles is shared-memory-bandwidth bound (48 KB read by the MMA + 48 KB written by TMA per 512-cycle
+// k-block = 192 B/clk against a 128 B/clk port); the pair stages each B half once per SM pair (64 KB per k-block per SM =
+// 128 B/clk), measured +8..12 % over the single-CTA kernel (8192^3: 1.46 vs 1.30 PFLOP/s).  CX_NO_PAIR=1 disables it.
 bool gemm_use_pair(const GemmArgs& g) {
-  static const bool enabled = getenv("CX_PAIR") != nullptr;
-  return enabled && g.M >= 256 && ((g.mode == EPI_SWIGLU) || g.N % 256 == 0);
+  static const bool disabled = getenv("CX_NO_PAIR") != nullptr;
+  return !disabled && g.M >= 256 && ((g.mode == EPI_SWIGLU) || g.N % 256 == 0);
 }
 
 template <int MODE, bool OUT_F32, bool ACCUM, bool A_MN, bool B_MN>

@@ -122,12 +122,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(&full_bar[i], PAIR ? 2 : 1);   // pair: leader's expect_tx arrive + the peer producer's remote arrive
+      mbar_init(&full_bar[i], 1);   // pair: only the leader arrives (expect_tx covers both CTAs' bytes; a peer arrive per
+                                    // k-block would put a cluster-scope release fence on the producer's critical path)
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], PAIR ? 512 : 256);  // pair: both CTAs' epilogue threads arrive on the leader's barrier
+      mbar_init(&tempty_bar[i], PAIR ? 257 : 256);  // pair: the leader's 256 epilogue threads + ONE forwarded arrive from the peer
     }
     fence_barrier_init();
   }
@@ -159,7 +160,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             // both CTAs' TMA bytes are credited to the LEADER's full barrier
             const uint32_t lead_bar = smem_u32(&full_bar[stage]) & 0xFEFFFFFFu;
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
-            else mbar_arrive_cluster(mapa_u32(smem_u32(&full_bar[stage]), 0));
             if (!A_MN) {
               tma_load_2d_2sm(sA, &tmA, lead_bar, kb * kBlockK, m0);
             } else {
@@ -557,8 +557,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       // accumulator drained -> hand the TMEM buffer back to the MMA warp (pair: the leader CTA's barrier)
       tc_fence_before();
-      if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
-      else mbar_arrive(&tempty_bar[acc]);
+      if (PAIR && cta_rank != 0) {
+        // peer CTA: gather its 256 epilogue threads locally, then ONE remote arrive (256 remote arrives per tile would
+        // serialise on the cluster interconnect)
+        named_bar_sync(3, 256);
+        if (threadIdx.x == 128) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+      } else if (PAIR) {
+        mbar_arrive(&tempty_bar[acc]);
+      } else {
+        mbar_arrive(&tempty_bar[acc]);
+      }
 
       if (MODE == EPI_NCE_STATS && row_ok) {  // partials stay in the log2 domain; the combine kernel converts
         const size_t o = static_cast<size_t>(nt * 2 + hf) * M + row;

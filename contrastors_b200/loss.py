@@ -224,15 +224,51 @@ def _autocast_for(tensors):
     return torch.autocast(dev, dtype=torch.bfloat16)
 
 
+_CHUNK_STREAMS = {}
+
+
+def _chunk_streams(model, chunks):
+    """Two side streams for towers that declare ``chunk_streams_ok`` (ours): GradCache chunks are independent, so
+    alternating them between two streams lets one chunk's HBM-bound kernels (LayerNorm, SwiGLU backward, RoPE, ...) run
+    under the other chunk's tensor-core kernels.  Generic towers keep the reference's single-stream order."""
+    if not getattr(model, "chunk_streams_ok", False) or len(chunks) < 2:
+        return None
+    t = chunks[0].get("input_ids")
+    if t is None or not t.is_cuda:
+        return None
+    key = (t.device.type, t.device.index)
+    if key not in _CHUNK_STREAMS:
+        _CHUNK_STREAMS[key] = (torch.cuda.Stream(device=t.device), torch.cuda.Stream(device=t.device))
+    # state shared by both streams is brought up to date on the launching stream first (bf16 weight shadow, RoPE tables)
+    trunk = getattr(model, "trunk", None)
+    if trunk is not None:
+        if hasattr(trunk, "shadow"):
+            trunk.shadow()
+        if hasattr(trunk, "rope_tables") and t.dim() == 2:
+            trunk.rope_tables(t.shape[1])
+    return _CHUNK_STREAMS[key]
+
+
 def get_chunked_embeddings(model, chunks):
     """Pass 1 of GradCache (reference loss.py:135-146): no-grad bf16 forwards, one RNG snapshot per chunk."""
     embeddings, rand_states = [], []
+    streams = _chunk_streams(model, chunks)
+    main = torch.cuda.current_stream() if streams else None
+    if streams:
+        for s in streams:
+            s.wait_stream(main)
     with torch.no_grad():
-        for chunk in chunks:
+        for i, chunk in enumerate(chunks):
             rand_states.append(RandContext(chunk))
-            with _autocast_for(chunk):
-                emb = model(**chunk)
+            with (torch.cuda.stream(streams[i & 1]) if streams else nullcontext()):
+                with _autocast_for(chunk):
+                    emb = model(**chunk)
+                if streams:
+                    emb["embedding"].record_stream(main)
             embeddings.append(emb["embedding"])
+    if streams:
+        for s in streams:
+            main.wait_stream(s)
     return torch.concat(embeddings, dim=0), rand_states
 
 
@@ -256,28 +292,43 @@ def _chunked_embeddings_with_gather(model, chunks, n_local):
     gathered = None
     comm = None
     row = 0
+    streams = _chunk_streams(model, chunks)
+    main = torch.cuda.current_stream()
+    if streams:
+        for s in streams:
+            s.wait_stream(main)
     with torch.no_grad():
-        for chunk in chunks:
+        for i, chunk in enumerate(chunks):
             rand_states.append(RandContext(chunk))
-            with _autocast_for(chunk):
-                emb = model(**chunk)["embedding"]
+            if gathered is None:  # allocated on the main stream before any side-stream use
+                dev = chunk["input_ids"].device
+                comm = _comm_stream(dev)
+            with (torch.cuda.stream(streams[i & 1]) if streams else nullcontext()):
+                with _autocast_for(chunk):
+                    emb = model(**chunk)["embedding"]
+                e32 = emb.float().contiguous()
+                b, width = e32.shape
+                if gathered is None:
+                    with torch.cuda.stream(main):
+                        ld = (width + 7) // 8 * 8
+                        gathered = torch.zeros(ws * n_local, ld, device=e32.device, dtype=torch.bfloat16)
+                    torch.cuda.current_stream().wait_stream(main)
+                mine = gathered[rank * n_local + row: rank * n_local + row + b]
+                ops.rows_to_bf16_into(e32, mine)
+                ready = torch.cuda.Event()
+                ready.record()
+                if streams:
+                    emb.record_stream(main)
             embeddings.append(emb)
-            e32 = emb.float().contiguous()
-            b, width = e32.shape
-            if gathered is None:
-                ld = (width + 7) // 8 * 8
-                gathered = torch.zeros(ws * n_local, ld, device=e32.device, dtype=torch.bfloat16)
-                comm = _comm_stream(e32.device)
-            mine = gathered[rank * n_local + row: rank * n_local + row + b]
-            ops.rows_to_bf16_into(e32, mine)
-            ready = torch.cuda.Event()
-            ready.record()
             outs = [gathered[r * n_local + row: r * n_local + row + b] for r in range(ws)]
             with torch.cuda.stream(comm):
                 comm.wait_event(ready)
                 dist.all_gather(outs, mine)
             row += b
-    torch.cuda.current_stream().wait_stream(comm)
+    if streams:
+        for s in streams:
+            main.wait_stream(s)
+    main.wait_stream(comm)
     return torch.concat(embeddings, dim=0), rand_states, gathered
 
 
@@ -287,15 +338,24 @@ def accumulate_gradients(model, inputs, cache, rand_states, router_aux_coeff):
     length = len(inputs)
     no_sync = getattr(model, "no_sync", nullcontext)
     sync_contexts = [no_sync] * (length - 1) + [nullcontext]
-    for inp, grad, state, sync_context in zip(inputs, cache, rand_states, sync_contexts):
-        with sync_context():
-            with state:
-                with _autocast_for(inp):
-                    embedding = model(**inp)
-            surrogate = torch.dot(embedding["embedding"].flatten().float(), grad.flatten().float())
-            if "router_loss" in embedding and embedding["router_loss"] is not None:
-                surrogate = surrogate + embedding["router_loss"] * router_aux_coeff
-            surrogate.backward()
+    streams = _chunk_streams(model, inputs)
+    main = torch.cuda.current_stream() if streams else None
+    if streams:
+        for s in streams:
+            s.wait_stream(main)
+    for i, (inp, grad, state, sync_context) in enumerate(zip(inputs, cache, rand_states, sync_contexts)):
+        with (torch.cuda.stream(streams[i & 1]) if streams else nullcontext()):
+            with sync_context():
+                with state:
+                    with _autocast_for(inp):
+                        embedding = model(**inp)
+                surrogate = torch.dot(embedding["embedding"].flatten().float(), grad.flatten().float())
+                if "router_loss" in embedding and embedding["router_loss"] is not None:
+                    surrogate = surrogate + embedding["router_loss"] * router_aux_coeff
+                surrogate.backward()
+    if streams:
+        for s in streams:
+            main.wait_stream(s)
 
 
 def cache_loss(tower1, tower2, query_embeddings, document_embeddings, logit_scale, bidirectional=False, _pregathered=None):

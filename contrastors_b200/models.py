@@ -404,6 +404,10 @@ class BiEncoder(nn.Module):
     (hamming LN) -> cast to the trunk dtype -> F.normalize -> {"embedding", "router_logits", "router_loss",
     "tokens_per_expert"}.  Pooling and the head run inside the trunk's autograd node."""
 
+    # GradCache can alternate chunks between two CUDA streams (all shared state is atomic); measured neutral on B200 --
+    # the step is power-capped, overlap only lowers the SM clock -- so it stays off and kernel timings stay clean
+    chunk_streams_ok = False
+
     def __init__(self, config: BiEncoderConfig):
         super().__init__()
         self.config = config

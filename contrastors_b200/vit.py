@@ -283,6 +283,8 @@ class VisionBiEncoderConfig:
 class VisionBiEncoder(nn.Module):
     """BiEncoder around the ViT trunk (modeling_biencoder.py:155-319 with a CLIP trunk, ClsSelector, Identity proj)."""
 
+    chunk_streams_ok = False
+
     def __init__(self, config: VisionBiEncoderConfig):
         super().__init__()
         self.config = config
