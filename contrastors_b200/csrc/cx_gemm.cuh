@@ -76,9 +76,12 @@ struct GemmSmem {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = (PAIR ? BLOCK_N / 2 : BLOCK_N) * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = PAIR ? 6 : ((BLOCK_N == 256) ? 4 : 6);
+  // pair mode trades one pipeline stage (32 KB) for ping-pong epilogue staging (2 buffers per column half), so a TMA
+  // store never has to drain before the next 64 columns are packed
+  static constexpr int kCBufs = PAIR ? 4 : 2;
+  static constexpr int kStages = PAIR ? 5 : ((BLOCK_N == 256) ? 4 : 6);
   static constexpr int kBarrierBytes = 256;
-  static constexpr int kTotal = 1024 + kStages * kStageBytes + 2 * kStageCBytes + kBarrierBytes;
+  static constexpr int kTotal = 1024 + kStages * kStageBytes + kCBufs * kStageCBytes + kBarrierBytes;
 };
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int MODE, bool OUT_F32, bool ACCUM, bool PAIR = false>
@@ -99,7 +102,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_c = smem + kStages * S::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + 2 * kStageCBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + S::kCBufs * kStageCBytes);
   uint64_t* full_bar = bars;                   // [kStages]
   uint64_t* empty_bar = bars + kStages;        // [kStages]
   uint64_t* tfull_bar = bars + 2 * kStages;    // [2]
@@ -256,7 +259,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int hf = (warp - 4) >> 2;     // column half handled by this warp group
     const int row_in_tile = ew * 32 + lane;
     const int etid = (threadIdx.x - 128) & 127;  // thread index within the half's group
-    uint8_t* const stage_c = smem_c + hf * kStageCBytes;  // one staging buffer per half
+    // staging: one buffer per column half (single-CTA mode) or two that ping-pong (pair mode)
+    constexpr int kPing = S::kCBufs / 2;
+    uint8_t* const stage_base = smem_c + hf * kPing * kStageCBytes;
+    int cb = 0;
+#define CX_STAGE_ACQUIRE()                                         \
+  uint8_t* stage_c = stage_base + cb * kStageCBytes;               \
+  if (etid == 0) {                                                 \
+    if (kPing == 2) tma_store_wait_read<1>();                      \
+    else tma_store_wait_read<0>();                                 \
+  }                                                                \
+  cb = (kPing == 2) ? (cb ^ 1) : 0;
     int it = 0;
     float dl0 = 0.f, dl1 = 0.f, dl2 = 0.f, dl3 = 0.f;  // sum p*t (log2 domain) for the logit-scale gradient
     const float ep_scale = ep.scale * (ep.scale_dev != nullptr ? *ep.scale_dev : 1.f);
@@ -300,7 +313,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int npass = (ep.yg_out != nullptr) ? 3 : 1;
 #pragma unroll 1
         for (int pass = 0; pass < npass; ++pass) {
-          if (etid == 0) tma_store_wait_read<0>();
+          CX_STAGE_ACQUIRE();
           named_bar_sync(1 + hf, 128);
           uint8_t* dst = stage_c + row_in_tile * 128;
 #pragma unroll 1
@@ -383,7 +396,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               pk2[j] = pack_bf16x2(__uint_as_float(v2[2 * j]) * ep_alpha, __uint_as_float(v2[2 * j + 1]) * ep_alpha);
             }
           }
-          if (etid == 0) tma_store_wait_read<0>();
+          CX_STAGE_ACQUIRE();
           named_bar_sync(1 + hf, 128);
           uint8_t* dst = stage_c + row_in_tile * 128;
 #pragma unroll
@@ -505,7 +518,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           // stage + TMA store.  fp32: one 32-col chunk = 128 B per row; 16-bit: two chunks = 128 B per row.
           if (OUT_F32) {
-            if (etid == 0) tma_store_wait_read<0>();
+            CX_STAGE_ACQUIRE();
             named_bar_sync(1 + hf, 128);
             uint8_t* dst = stage_c + row_in_tile * 128;
 #pragma unroll
@@ -523,9 +536,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           } else {
             const int half = c & 1;
             if (half == 0) {
-              if (etid == 0) tma_store_wait_read<0>();
+              cb = (kPing == 2) ? (cb ^ 1) : 0;
+              if (etid == 0) {
+                if (kPing == 2) tma_store_wait_read<1>();
+                else tma_store_wait_read<0>();
+              }
               named_bar_sync(1 + hf, 128);
             }
+            uint8_t* stage_c = stage_base + cb * kStageCBytes;
             uint8_t* dst = stage_c + row_in_tile * 128;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {

@@ -2,6 +2,6 @@
 set -x
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/ -x -q -m gpu 2>&1 | tail -5 | tee gpurun_out/tests_all_gpu.log
-timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2 | tee gpurun_out/smoke.log
-timeout 1200 python bench.py --steps 1 --warmup 1 2>&1 | tail -1 | tee gpurun_out/bench_pair.log
+timeout 600 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_infonce.py tests/test_gpu_encoder.py -x -q -m gpu 2>&1 | tail -3 | tee gpurun_out/tests.log
+timeout 300 python tools/bench_kernels.py 2>&1 | tail -3 | tee gpurun_out/bench_kernels.log
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_chunk.csv python tools/profile_chunk.py 2 > gpurun_out/prof_chunk.log 2>&1
