@@ -72,7 +72,7 @@ def test_clip_loss_two_ranks(name, tmp_path):
         assert abs(got["loss"] - o["loss"]) <= 1e-3 * max(abs(o["loss"]), 1e-2)
         assert np.abs(got["dq"] - o["dq"]).max() <= rel * np.abs(o["dq"]).max()
         assert np.abs(got["dd"] - o["dd_local"]).max() <= rel * np.abs(o["dd_local"]).max()
-        assert abs(got["dlogit"] - o["dlogit"]) <= 2e-3 * o["dlogit_abs"]
+        assert abs(got["dlogit"] - o["dlogit"]) <= 2 * rel * o["dlogit_abs"] + 1e-6
         if name != "unsat":
             z = golden(f"infonce_{name}.npz")
             assert abs(got["loss"] - float(z[f"r{r}_loss"])) <= 5e-2 * max(float(z[f"r{r}_loss"]), 0.05)
