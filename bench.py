@@ -201,13 +201,14 @@ def run_ours(args):
     resident = {k: v.to(dev) for k, v in host.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
 
+    from contrastors_b200.trainer import training_step
+
     def train_step(batch):
-        q = {"input_ids": batch["query_input_ids"], "attention_mask": ones, "seq_lens": seq_lens}
-        d = {"input_ids": batch["document_input_ids"], "attention_mask": ones, "seq_lens": seq_lens}
-        loss = cb.grad_cache_loss(model, q, model, d, CHUNK, logit_scale)
-        allreduce_gradients(model)
-        model.trunk.fused_adamw_step(LR, weight_decay=WD, max_grad_norm=CLIP)
-        return loss
+        # the reference's collate schema (text_text_loader.py tokenize_pairs) + CPU-side lengths a loader has for free
+        full = {"query_input_ids": batch["query_input_ids"], "query_attention_mask": ones, "query_seq_lens": seq_lens,
+                "document_input_ids": batch["document_input_ids"], "document_attention_mask": ones,
+                "document_seq_lens": seq_lens, "dataset_name": "synthetic"}
+        return training_step(model, full, logit_scale, lr=LR, chunk_size=CHUNK, weight_decay=WD, max_grad_norm=CLIP)
 
     def timed(fn, steps):
         torch.cuda.synchronize()

@@ -107,3 +107,43 @@ def test_fused_adamw_matches_torch_adamw_on_tower():
     # two runs differ in atomic / split-K summation order; Adam's g/sqrt(v) amplifies that on near-zero gradients
     assert (a - b).abs().max().item() <= 0.2 * 1e-3
     assert torch.count_nonzero(model.trunk.flat_grad()) == 0
+
+
+def test_trainer_steps_gradcache_equals_plain_and_matryoshka_runs():
+    """trainer.training_step: the GradCache step and the plain step move the weights the same way (the equivalence the
+    reference's test_grad_cache.py only prints), and the Matryoshka step runs through the fused prefix loss."""
+    import os
+    import torch.distributed as dist
+    from contrastors_b200 import LogitScale
+    from contrastors_b200.trainer import training_step
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29539")
+    created = False
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", rank=0, world_size=1)
+        created = True
+    try:
+        case = ENCODER_CASES["tiny"]
+        ids, mask, _ = make_encoder_inputs(case)
+        n = ids.shape[0]
+        g = torch.Generator().manual_seed(3)
+        batch = {"query_input_ids": torch.tensor(ids), "query_attention_mask": torch.tensor(mask),
+                 "document_input_ids": torch.randint(0, 256, ids.shape, generator=g), "document_attention_mask": torch.tensor(mask),
+                 "dataset_name": "x"}
+        ls = LogitScale(logit_scale=20.0).cuda()
+        results = []
+        for chunk in (2, None):
+            model, _, _ = _build(case)
+            loss = training_step(model, dict(batch), ls, lr=1e-3, chunk_size=chunk, max_grad_norm=1.0)
+            results.append((loss.item(), model.trunk._flat.clone()))
+        assert abs(results[0][0] - results[1][0]) <= 2e-3 * abs(results[1][0])
+        # Adam's first step moves every weight by ~lr; near-zero gradients may flip sign between the two paths
+        diff = (results[0][1] - results[1][1]).abs()
+        assert (diff > 0.5e-3).float().mean().item() < 0.02
+        model, _, _ = _build(case, hamming=True)
+        loss = training_step(model, dict(batch), ls, lr=1e-3, chunk_size=None, matryoshka_dims=[128, 64, 32],
+                             matryoshka_loss_weights=[1.0, 1.0, 0.5])
+        assert torch.isfinite(loss)
+    finally:
+        if created:
+            dist.destroy_process_group()
