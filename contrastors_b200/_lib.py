@@ -31,11 +31,11 @@ SIGNATURES = {
                             _i64, _i, _vp, _vp, _vp]),
     "cx_rows_to_bf16": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _i, _i, _vp]),
     "cx_l2norm_bwd": (_i, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
-    "cx_add_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp]),
+    "cx_add_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _f, C.c_uint64, _vp]),
     "cx_layernorm_bwd_workspace_bytes": (_sz, [_i]),
-    "cx_add_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
-    "cx_embed_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
-    "cx_embed_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _vp]),
+    "cx_add_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _f, C.c_uint64, _vp, _vp]),
+    "cx_embed_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, C.c_uint64, _vp]),
+    "cx_embed_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _f, C.c_uint64, _vp]),
     "cx_token_positions": (_i, [_vp, _i, _vp, _vp, _vp]),
     "cx_rope_inplace": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "cx_dq_finalize_rope": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

@@ -40,6 +40,31 @@ struct BF8 {  // 8 bf16 = 16 bytes
 
 constexpr int kLnMaxVec = 4;  // up to d = 32 lanes * 8 * 4 = 1024 columns per row
 
+// Counter-based dropout: the keep mask of 8 consecutive columns is a pure function of (seed, row, col / 8), so the
+// backward (and GradCache's second pass, which replays the CPU RNG that produced the seed) regenerates it for free.
+struct DropParams {
+  float p;       // drop probability (0 = off)
+  float scale;   // 1 / (1 - p)
+  unsigned long long seed;
+};
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+// multiplies f[0..8) by keep * scale
+__device__ __forceinline__ void apply_dropout8(float (&f)[8], const DropParams& dp, int64_t row, int col, int d) {
+  const unsigned long long idx = (unsigned long long)row * (unsigned long long)(d / 8) + (unsigned long long)(col / 8);
+  const unsigned long long x = dp.seed + idx * 0x9E3779B97F4A7C15ull;
+  const unsigned long long r0 = splitmix64(x), r1 = splitmix64(x ^ 0xD1B54A32D192ED03ull);
+  const unsigned int thr = (unsigned int)(dp.p * 65536.f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const unsigned int u = (unsigned int)(((i < 4 ? r0 : r1) >> (16 * (i & 3))) & 0xFFFFull);
+    f[i] = (u >= thr) ? f[i] * dp.scale : 0.f;
+  }
+}
+
 __device__ __forceinline__ void load8f(const float* __restrict__ p, float (&f)[8]) {
   const float4 a = *reinterpret_cast<const float4*>(p);
   const float4 b = *reinterpret_cast<const float4*>(p + 4);
@@ -56,7 +81,7 @@ add_layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat1
                          const int64_t* __restrict__ ids, const int64_t* __restrict__ type_ids,
                          const __nv_bfloat16* __restrict__ type_emb, const float* __restrict__ gamma,
                          const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ stats, int rows,
-                         int d, float eps, __nv_bfloat16* __restrict__ z_out) {
+                         int d, float eps, __nv_bfloat16* __restrict__ z_out, DropParams dp) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -78,6 +103,7 @@ add_layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat1
     const int col = (c * 32 + lane) * 8;
     if (col < d) {
       ra[c].unpack(z[c]);
+      if (!EMBED && dp.p > 0.f) apply_dropout8(z[c], dp, row, col, d);  // z = dropout(a) + b  (block.py:422-431)
       if (br != nullptr) {
         float t[8];
         rb[c].unpack(t);
@@ -126,6 +152,7 @@ add_layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat1
         if (gamma != nullptr) v = fmaf(v, gm[i], bt[i]);
         o[i] = v;
       }
+      if (EMBED && dp.p > 0.f) apply_dropout8(o, dp, row, col, d);  // emb_drop AFTER emb_ln (modeling_nomic_bert.py:531-535)
       BF8 vo;
       vo.pack(o);
       *reinterpret_cast<uint4*>(y + (size_t)row * d + col) = vo.raw;
@@ -145,7 +172,7 @@ add_layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat1
                          const __nv_bfloat16* __restrict__ g2, const float* __restrict__ gamma,
                          const float* __restrict__ stats, __nv_bfloat16* __restrict__ dz, float* __restrict__ dword,
                          float* __restrict__ dtype_emb, float* __restrict__ partials, int rows, int d, int64_t padding_idx,
-                         const __nv_bfloat16* __restrict__ gres) {
+                         const __nv_bfloat16* __restrict__ gres, DropParams dp, __nv_bfloat16* __restrict__ da_out) {
   extern __shared__ float sh[];  // [warps][NP][d]
   constexpr int NP = EMBED ? 3 : 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -190,6 +217,7 @@ add_layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat1
       if (col < d) {
         float z[8], t[8], g[8];
         ra[c].unpack(z);
+        if (!EMBED && dp.p > 0.f) apply_dropout8(z, dp, row, col, d);  // re-create z = dropout(a) + b
         if (br != nullptr) {
           rb[c].unpack(t);
 #pragma unroll
@@ -201,6 +229,7 @@ add_layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat1
 #pragma unroll
           for (int i = 0; i < 8; ++i) g[i] += t[i];
         }
+        if (EMBED && dp.p > 0.f) apply_dropout8(g, dp, row, col, d);   // y = dropout(LN(z)): mask the upstream gradient
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float x = (z[i] - mean) * rstd;
@@ -244,6 +273,11 @@ add_layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat1
           BF8 vo;
           vo.pack(o);
           *reinterpret_cast<uint4*>(dz + (size_t)row * d + col) = vo.raw;
+          if (da_out != nullptr) {  // gradient of the dropped branch a: dz * keep / (1 - p)
+            if (dp.p > 0.f) apply_dropout8(o, dp, row, col, d);
+            vo.pack(o);
+            *reinterpret_cast<uint4*>(da_out + (size_t)row * d + col) = vo.raw;
+          }
         }
       }
     }
@@ -739,15 +773,25 @@ using namespace cx;
 
 static int ln_rows_grid(int rows, int warps) { return (rows + warps - 1) / warps; }
 
+static DropParams make_drop(float p, unsigned long long seed) {
+  DropParams dp;
+  dp.p = (p > 0.f && p < 1.f) ? p : 0.f;
+  dp.scale = dp.p > 0.f ? 1.f / (1.f - dp.p) : 1.f;
+  dp.seed = seed;
+  return dp;
+}
+
 extern "C" int cx_add_layernorm_fwd(const void* a, const void* b, const float* gamma, const float* beta, void* y, float* stats,
-                                    int rows, int d, float eps, void* z_out, cx_stream_t stream) {
+                                    int rows, int d, float eps, void* z_out, float p_drop, unsigned long long seed,
+                                    cx_stream_t stream) {
+  const DropParams dp = make_drop(p_drop, seed);
   CX_REQUIRE(a && y, "cx_add_layernorm_fwd: null pointer");
   CX_REQUIRE(d % 8 == 0 && d <= 256 * kLnMaxVec, "cx_add_layernorm_fwd: d must be a multiple of 8 and <= 1024");
   if (rows <= 0) return 0;
 #define CX_LN_FWD(NV_)                                                                                              \
   add_layernorm_fwd_kernel<false, NV_><<<ln_rows_grid(rows, 8), 256, 0, STREAM>>>(                                  \
       (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, nullptr, nullptr, nullptr, gamma, beta, (__nv_bfloat16*)y, stats, rows, d, eps, \
-      (__nv_bfloat16*)z_out)
+      (__nv_bfloat16*)z_out, dp)
   switch ((d + 255) / 256) {
     case 1: CX_LN_FWD(1); break;
     case 2: CX_LN_FWD(2); break;
@@ -761,14 +805,15 @@ extern "C" int cx_add_layernorm_fwd(const void* a, const void* b, const float* g
 
 extern "C" int cx_embed_layernorm_fwd(const int64_t* ids, const int64_t* type_ids, const void* word_emb, const void* type_emb,
                                       const float* gamma, const float* beta, void* y, float* stats, int rows, int d, float eps,
-                                      cx_stream_t stream) {
+                                      float p_drop, unsigned long long seed, cx_stream_t stream) {
+  const DropParams dp = make_drop(p_drop, seed);
   CX_REQUIRE(ids && word_emb && type_emb && y, "cx_embed_layernorm_fwd: null pointer");
   CX_REQUIRE(d % 8 == 0 && d <= 256 * kLnMaxVec, "cx_embed_layernorm_fwd: d must be a multiple of 8 and <= 1024");
   if (rows <= 0) return 0;
 #define CX_LN_FWD(NV_)                                                                                              \
   add_layernorm_fwd_kernel<true, NV_><<<ln_rows_grid(rows, 8), 256, 0, STREAM>>>(                                   \
       (const __nv_bfloat16*)word_emb, nullptr, ids, type_ids, (const __nv_bfloat16*)type_emb, gamma, beta, (__nv_bfloat16*)y, \
-      stats, rows, d, eps, nullptr)
+      stats, rows, d, eps, nullptr, dp)
   switch ((d + 255) / 256) {
     case 1: CX_LN_FWD(1); break;
     case 2: CX_LN_FWD(2); break;
@@ -792,14 +837,14 @@ template <bool EMBED, int NV>
 static int ln_bwd_launch(int grid, size_t smem, cudaStream_t st, const __nv_bfloat16* a, const __nv_bfloat16* b, const int64_t* ids,
                          const int64_t* type_ids, const __nv_bfloat16* type_emb, const __nv_bfloat16* g1, const __nv_bfloat16* g2,
                          const float* gamma, const float* stats, __nv_bfloat16* dz, float* dword, float* dtype_emb, float* partials,
-                         int rows, int d, int64_t padding_idx, const __nv_bfloat16* gres) {
+                         int rows, int d, int64_t padding_idx, const __nv_bfloat16* gres, DropParams dp, __nv_bfloat16* da_out) {
   static bool configured = false;
   if (!configured) {
     CX_CUDA_CHECK(cudaFuncSetAttribute(add_layernorm_bwd_kernel<EMBED, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4));
     configured = true;
   }
   add_layernorm_bwd_kernel<EMBED, NV><<<grid, 256, smem, st>>>(a, b, ids, type_ids, type_emb, g1, g2, gamma, stats, dz, dword, dtype_emb,
-                                                               partials, rows, d, padding_idx, gres);
+                                                               partials, rows, d, padding_idx, gres, dp, da_out);
   CX_LAUNCH_CHECK();
   return 0;
 }
@@ -815,7 +860,8 @@ static int ln_bwd_dispatch(int d, Args... args) {
 
 extern "C" int cx_add_layernorm_bwd(const void* a, const void* b, const void* g1, const void* g2, const float* gamma,
                                     const float* stats, void* dz, float* dgamma, float* dbeta, void* workspace, int rows, int d,
-                                    const void* gres, cx_stream_t stream) {
+                                    const void* gres, float p_drop, unsigned long long seed, void* da_out, cx_stream_t stream) {
+  const DropParams dp = make_drop(p_drop, seed);
   CX_REQUIRE(a && g1 && stats && dz, "cx_add_layernorm_bwd: null pointer");
   CX_REQUIRE(d % 8 == 0 && d <= 256 * kLnMaxVec, "cx_add_layernorm_bwd: d must be a multiple of 8 and <= 1024");
   CX_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "cx_add_layernorm_bwd: dgamma/dbeta go together");
@@ -826,7 +872,8 @@ extern "C" int cx_add_layernorm_bwd(const void* a, const void* b, const void* g1
   int rc = ln_bwd_dispatch<false>(d, grid, smem, STREAM, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (const int64_t*)nullptr,
                                   (const int64_t*)nullptr, (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)g1,
                                   (const __nv_bfloat16*)g2, gamma, stats, (__nv_bfloat16*)dz, (float*)nullptr, (float*)nullptr,
-                                  dgamma ? (float*)workspace : (float*)nullptr, rows, d, (int64_t)-1, (const __nv_bfloat16*)gres);
+                                  dgamma ? (float*)workspace : (float*)nullptr, rows, d, (int64_t)-1, (const __nv_bfloat16*)gres, dp,
+                                  (__nv_bfloat16*)da_out);
   if (rc) return rc;
   if (dgamma) {
     ln_param_grad_reduce_kernel<<<(2 * d * 8 + 255) / 256, 256, 0, STREAM>>>((const float*)workspace, grid, d, 2, dgamma, dbeta, nullptr);
@@ -838,7 +885,8 @@ extern "C" int cx_add_layernorm_bwd(const void* a, const void* b, const void* g1
 extern "C" int cx_embed_layernorm_bwd(const int64_t* ids, const int64_t* type_ids, const void* word_emb, const void* type_emb,
                                       const void* g1, const void* g2, const float* gamma, const float* stats, float* dword,
                                       float* dtype_emb, float* dgamma, float* dbeta, void* workspace, int rows, int d,
-                                      int64_t padding_idx, cx_stream_t stream) {
+                                      int64_t padding_idx, float p_drop, unsigned long long seed, cx_stream_t stream) {
+  const DropParams dp = make_drop(p_drop, seed);
   CX_REQUIRE(ids && word_emb && type_emb && g1 && stats && dword && dtype_emb && dgamma && dbeta && workspace,
              "cx_embed_layernorm_bwd: null pointer");
   CX_REQUIRE(d % 8 == 0 && d <= 256 * kLnMaxVec, "cx_embed_layernorm_bwd: d must be a multiple of 8 and <= 1024");
@@ -848,7 +896,7 @@ extern "C" int cx_embed_layernorm_bwd(const int64_t* ids, const int64_t* type_id
   int rc = ln_bwd_dispatch<true>(d, grid, smem, STREAM, (const __nv_bfloat16*)word_emb, (const __nv_bfloat16*)nullptr, ids, type_ids,
                                  (const __nv_bfloat16*)type_emb, (const __nv_bfloat16*)g1, (const __nv_bfloat16*)g2, gamma, stats,
                                  (__nv_bfloat16*)nullptr, dword, dtype_emb, (float*)workspace, rows, d, padding_idx,
-                                 (const __nv_bfloat16*)nullptr);
+                                 (const __nv_bfloat16*)nullptr, dp, (__nv_bfloat16*)nullptr);
   if (rc) return rc;
   // type_ids == NULL: every token is type 0, its embedding-row gradient is the third column-sum partial
   ln_param_grad_reduce_kernel<<<(3 * d * 8 + 255) / 256, 256, 0, STREAM>>>((const float*)workspace, grid, d, 3, dgamma, dbeta,

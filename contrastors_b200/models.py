@@ -59,6 +59,8 @@ class NomicBertConfig:
     initializer_range: float = 0.02
     pad_token_id: Optional[int] = None
     max_position: int = 8192
+    resid_pdrop: float = 0.0   # dropout of the fused dropout-add-LayerNorm sites and emb_drop (0.0 in nomic-bert-2048;
+                               # 0.1 when a config is derived from BERT, models/encoder/bert.py:20-21)
 
     @property
     def head_dim(self):
@@ -298,9 +300,15 @@ class _TrunkFn(torch.autograd.Function):
         scale = 1.0 / math.sqrt(Dh)
         cos_t, sin_t = model.rope_tables(packed.max_seqlen)
         eps = cfg.layer_norm_epsilon
+        # dropout: one 64-bit seed per tower call drawn from torch's CPU generator -- RandContext replays that generator
+        # for GradCache's second pass, so the re-forward regenerates exactly the same keep masks (rand_state.py)
+        pdrop = float(cfg.resid_pdrop) if model.training else 0.0
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if pdrop > 0 else 0
+        site = lambda k: (seed + k * 0x632BE59BD9B4E019) & 0xFFFFFFFFFFFFFFFF
+        ctx.drop = (pdrop, seed)
         h, st0 = ops.embed_layernorm_fwd(packed.ids, None, v(W, "embeddings.word_embeddings.weight"),
                                          v(W, "embeddings.token_type_embeddings.weight"), v(P, "emb_ln.weight"),
-                                         v(P, "emb_ln.bias"), eps)
+                                         v(P, "emb_ln.bias"), eps, p_drop=pdrop, seed=site(0))
         saved = []
         for i in range(cfg.n_layer):
             p = f"encoder.layers.{i}."
@@ -310,7 +318,8 @@ class _TrunkFn(torch.autograd.Function):
             ops.rope_inplace(qkv, packed.pos, cos_t, sin_t, H, Dh)
             attn, lse = ops.attn_fwd(qkv, packed.cu, packed.max_seqlen, H, Dh, scale)
             o = ops.gemm(attn, v(W, p + "attn.out_proj.weight"))
-            h1, st1 = ops.add_layernorm_fwd(o, h, v(P, p + "norm1.weight"), v(P, p + "norm1.bias"), eps)
+            h1, st1 = ops.add_layernorm_fwd(o, h, v(P, p + "norm1.weight"), v(P, p + "norm1.bias"), eps, p_drop=pdrop,
+                                            seed=site(1 + 2 * i))
             w1 = _w1(model, W, i)
             if cfg.n_inner % 128 == 0:
                 a, yg = ops.gemm_swiglu(h1, w1, keep_preact=need_grad)  # SwiGLU fused into the GEMM epilogue
@@ -318,7 +327,8 @@ class _TrunkFn(torch.autograd.Function):
                 yg = ops.gemm(h1, w1)
                 a = ops.swiglu_fwd(yg)
             m = ops.gemm(a, v(W, p + "mlp.fc2.weight"))
-            h2, st2 = ops.add_layernorm_fwd(m, h1, v(P, p + "norm2.weight"), v(P, p + "norm2.bias"), eps)
+            h2, st2 = ops.add_layernorm_fwd(m, h1, v(P, p + "norm2.weight"), v(P, p + "norm2.bias"), eps, p_drop=pdrop,
+                                            seed=site(2 + 2 * i))
             if need_grad:
                 saved.append((h, qkv, attn, lse, o, st1, h1, yg, a, m, st2))
             h = h2
@@ -347,23 +357,27 @@ class _TrunkFn(torch.autograd.Function):
         else:
             g_a = g_out.contiguous().to(torch.bfloat16)
         g_b = None
-        f32 = torch.float32
+        pdrop, seed = ctx.drop
+        site = lambda k: (seed + k * 0x632BE59BD9B4E019) & 0xFFFFFFFFFFFFFFFF
         for i in reversed(range(cfg.n_layer)):
             p = f"encoder.layers.{i}."
             h, qkv, attn, lse, o, st1, h1, yg, a, m, st2 = ctx.saved[i]
             ctx.saved[i] = None
-            dz2 = ops.add_layernorm_bwd(m, h1, g_a, g_b, v(P, p + "norm2.weight"), st2, v(G, p + "norm2.weight"),
-                                        v(G, p + "norm2.bias"))
-            da = ops.gemm(dz2, v(W, p + "mlp.fc2.weight"), b_major=MAJOR_MN)
-            ops.gemm(dz2, a, a_major=MAJOR_MN, b_major=MAJOR_MN, out=v(G, p + "mlp.fc2.weight"), accumulate=True)
+            # dz2: gradient of the residual input h1; dm: gradient of the (dropped) MLP output m -- the same tensor at p = 0
+            r = ops.add_layernorm_bwd(m, h1, g_a, g_b, v(P, p + "norm2.weight"), st2, v(G, p + "norm2.weight"),
+                                      v(G, p + "norm2.bias"), p_drop=pdrop, seed=site(2 + 2 * i))
+            dz2, dm = r if pdrop > 0 else (r, r)
+            da = ops.gemm(dm, v(W, p + "mlp.fc2.weight"), b_major=MAJOR_MN)
+            ops.gemm(dm, a, a_major=MAJOR_MN, b_major=MAJOR_MN, out=v(G, p + "mlp.fc2.weight"), accumulate=True)
             dyg = ops.swiglu_bwd(da, yg)
             w1 = _w1(model, W, i)
             dh1 = ops.gemm(dyg, w1, b_major=MAJOR_MN)
             ops.gemm(dyg, h1, a_major=MAJOR_MN, b_major=MAJOR_MN, out=_w1(model, G, i), accumulate=True)
-            dz1 = ops.add_layernorm_bwd(o, h, dz2, dh1, v(P, p + "norm1.weight"), st1, v(G, p + "norm1.weight"),
-                                        v(G, p + "norm1.bias"))
-            dattn = ops.gemm(dz1, v(W, p + "attn.out_proj.weight"), b_major=MAJOR_MN)
-            ops.gemm(dz1, attn, a_major=MAJOR_MN, b_major=MAJOR_MN, out=v(G, p + "attn.out_proj.weight"), accumulate=True)
+            r = ops.add_layernorm_bwd(o, h, dz2, dh1, v(P, p + "norm1.weight"), st1, v(G, p + "norm1.weight"),
+                                      v(G, p + "norm1.bias"), p_drop=pdrop, seed=site(1 + 2 * i))
+            dz1, do = r if pdrop > 0 else (r, r)
+            dattn = ops.gemm(do, v(W, p + "attn.out_proj.weight"), b_major=MAJOR_MN)
+            ops.gemm(do, attn, a_major=MAJOR_MN, b_major=MAJOR_MN, out=v(G, p + "attn.out_proj.weight"), accumulate=True)
             dqkv = ops.attn_bwd(qkv, attn, dattn, lse, packed.cu, packed.max_seqlen, H, Dh, scale, packed.pos, cos_t, sin_t)
             dh = ops.gemm(dqkv, v(W, p + "attn.Wqkv.weight"), b_major=MAJOR_MN)
             ops.gemm(dqkv, h, a_major=MAJOR_MN, b_major=MAJOR_MN, out=v(G, p + "attn.Wqkv.weight"), accumulate=True)
@@ -372,7 +386,7 @@ class _TrunkFn(torch.autograd.Function):
                                 v(W, "embeddings.token_type_embeddings.weight"), g_a, g_b, v(P, "emb_ln.weight"), ctx.st0,
                                 v(G, "embeddings.word_embeddings.weight"), v(G, "embeddings.token_type_embeddings.weight"),
                                 v(G, "emb_ln.weight"), v(G, "emb_ln.bias"),
-                                padding_idx=-1 if cfg.pad_token_id is None else cfg.pad_token_id)
+                                padding_idx=-1 if cfg.pad_token_id is None else cfg.pad_token_id, p_drop=pdrop, seed=site(0))
         ctx.saved = None
         return None, None, None, None
 

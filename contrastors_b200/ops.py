@@ -215,8 +215,8 @@ def _ws_bytes(nbytes, device):
     return torch.empty(max(int(nbytes), 16), device=device, dtype=torch.uint8)
 
 
-def add_layernorm_fwd(a, b, gamma, beta, eps, want_z=False):
-    """y = LN(a + b) (b may be None); returns (y bf16 [rows,d], stats fp32 [rows,2]) (+ z = a + b when want_z)."""
+def add_layernorm_fwd(a, b, gamma, beta, eps, want_z=False, p_drop=0.0, seed=0):
+    """y = LN(dropout(a) + b) (b may be None); returns (y bf16 [rows,d], stats fp32 [rows,2]) (+ z when want_z)."""
     _require_cuda(a, b)
     rows, d = a.shape
     y = torch.empty_like(a)
@@ -224,23 +224,26 @@ def add_layernorm_fwd(a, b, gamma, beta, eps, want_z=False):
     stats = torch.empty(rows, 2, device=a.device, dtype=torch.float32)
     lib = _lib.load()
     _lib.check(lib.cx_add_layernorm_fwd(a.data_ptr(), _ptr(b), _ptr(gamma), _ptr(beta), y.data_ptr(), stats.data_ptr(),
-                                        rows, d, float(eps), _ptr(z), _stream()), "cx_add_layernorm_fwd")
+                                        rows, d, float(eps), _ptr(z), float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, _stream()),
+               "cx_add_layernorm_fwd")
     return (y, stats, z) if want_z else (y, stats)
 
 
-def add_layernorm_bwd(a, b, g1, g2, gamma, stats, dgamma, dbeta, gres=None):
-    """dz (bf16) for z = a + b given upstream g1 (+ g2) (+ gres on the residual stream); ADDS into dgamma/dbeta."""
+def add_layernorm_bwd(a, b, g1, g2, gamma, stats, dgamma, dbeta, gres=None, p_drop=0.0, seed=0):
+    """dz (bf16) for z = dropout(a) + b given upstream g1 (+ g2) (+ gres on the residual stream); ADDS into dgamma/dbeta.
+    With dropout returns (dz, da): dz is the gradient of b / the residual, da that of the dropped branch a."""
     rows, d = a.shape
     dz = torch.empty_like(a)
+    da = torch.empty_like(a) if p_drop > 0 else None
     lib = _lib.load()
     ws = _ws_bytes(lib.cx_layernorm_bwd_workspace_bytes(d), a.device) if dgamma is not None else None
     _lib.check(lib.cx_add_layernorm_bwd(a.data_ptr(), _ptr(b), g1.data_ptr(), _ptr(g2), _ptr(gamma), stats.data_ptr(),
-                                        dz.data_ptr(), _ptr(dgamma), _ptr(dbeta), _ptr(ws), rows, d, _ptr(gres), _stream()),
-               "cx_add_layernorm_bwd")
-    return dz
+                                        dz.data_ptr(), _ptr(dgamma), _ptr(dbeta), _ptr(ws), rows, d, _ptr(gres), float(p_drop),
+                                        int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(da), _stream()), "cx_add_layernorm_bwd")
+    return (dz, da) if p_drop > 0 else dz
 
 
-def embed_layernorm_fwd(ids, type_ids, word_emb, type_emb, gamma, beta, eps):
+def embed_layernorm_fwd(ids, type_ids, word_emb, type_emb, gamma, beta, eps, p_drop=0.0, seed=0):
     _require_cuda(ids, word_emb)
     rows = ids.numel()
     d = word_emb.shape[1]
@@ -249,12 +252,13 @@ def embed_layernorm_fwd(ids, type_ids, word_emb, type_emb, gamma, beta, eps):
     lib = _lib.load()
     _lib.check(lib.cx_embed_layernorm_fwd(ids.data_ptr(), _ptr(type_ids), word_emb.data_ptr(), type_emb.data_ptr(),
                                           gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), stats.data_ptr(), rows, d,
-                                          float(eps), _stream()), "cx_embed_layernorm_fwd")
+                                          float(eps), float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, _stream()),
+               "cx_embed_layernorm_fwd")
     return y, stats
 
 
 def embed_layernorm_bwd(ids, type_ids, word_emb, type_emb, g1, g2, gamma, stats, dword, dtype_emb, dgamma, dbeta,
-                        padding_idx=-1):
+                        padding_idx=-1, p_drop=0.0, seed=0):
     rows = ids.numel()
     d = word_emb.shape[1]
     lib = _lib.load()
@@ -262,7 +266,8 @@ def embed_layernorm_bwd(ids, type_ids, word_emb, type_emb, g1, g2, gamma, stats,
     _lib.check(lib.cx_embed_layernorm_bwd(ids.data_ptr(), _ptr(type_ids), word_emb.data_ptr(), type_emb.data_ptr(),
                                           g1.data_ptr(), _ptr(g2), gamma.data_ptr(), stats.data_ptr(), dword.data_ptr(),
                                           dtype_emb.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), rows, d,
-                                          int(padding_idx), _stream()), "cx_embed_layernorm_bwd")
+                                          int(padding_idx), float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF, _stream()),
+               "cx_embed_layernorm_bwd")
 
 
 def token_positions(cu_seqlens, total_tokens):

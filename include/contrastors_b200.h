@@ -100,26 +100,28 @@ CX_API int cx_l2norm_bwd(const float* x, int64_t ldx, const float* g, int64_t ld
 /* ---- fused (dropout-)add-LayerNorm (replaces flash-attn dropout_add_layer_norm: layers/block.py:422-431,453-462,
  *      models/encoder/modeling_nomic_bert.py:531-535).  y = LN(a + b) * gamma + beta; b may be NULL;
  *      stats[rows][2] = (mean, rstd) for the backward; z_out (bf16, may be NULL) receives z = a + b, the residual
- *      stream of the pre-norm blocks (layers/block.py:293-388, ViT). */
+ *      stream of the pre-norm blocks (layers/block.py:293-388, ViT).  p_drop > 0: z = dropout(a)/(1-p) + b with a
+ *      counter-based keep mask that is a pure function of (seed, row, column) -- the backward regenerates it. */
 CX_API int cx_add_layernorm_fwd(const void* a, const void* b, const float* gamma, const float* beta, void* y, float* stats,
-                         int rows, int d, float eps, void* z_out, cx_stream_t stream);
+                         int rows, int d, float eps, void* z_out, float p_drop, unsigned long long seed, cx_stream_t stream);
 /* backward: z = a + b is recomputed, upstream gradient g = g1 + g2 (g2 may be NULL); writes dz (bf16, the gradient of
  * both a and b) and ADDS the parameter gradients into dgamma/dbeta (pass both NULL to skip them).
  * workspace: cx_layernorm_bwd_workspace_bytes(d).  gres (bf16, may be NULL): gradient arriving on the residual stream
- * z itself (pre-norm blocks), added to dz. */
+ * z itself (pre-norm blocks), added to dz.  With dropout (same p_drop / seed as the forward) dz is the gradient of b and of
+ * the residual stream, da_out (bf16, may be NULL) receives the gradient of the dropped branch a = dz * keep / (1 - p). */
 CX_API size_t cx_layernorm_bwd_workspace_bytes(int d);
 CX_API int cx_add_layernorm_bwd(const void* a, const void* b, const void* g1, const void* g2, const float* gamma,
                          const float* stats, void* dz, float* dgamma, float* dbeta, void* workspace, int rows, int d,
-                         const void* gres, cx_stream_t stream);
+                         const void* gres, float p_drop, unsigned long long seed, void* da_out, cx_stream_t stream);
 /* ---- embeddings + emb_ln (layers/embedding.py:594-615 + modeling_nomic_bert.py:531-534): y = LN(word[ids] + type[type_ids]).
- *      type_ids may be NULL (all zeros).  Backward scatters into the fp32 table gradients (atomic adds), ADDS dgamma/dbeta. */
+ *      type_ids may be NULL (all zeros); p_drop > 0 applies emb_drop AFTER the LayerNorm (:535).  Backward scatters into the fp32 table gradients (atomic adds), ADDS dgamma/dbeta. */
 CX_API int cx_embed_layernorm_fwd(const int64_t* ids, const int64_t* type_ids, const void* word_emb, const void* type_emb,
                            const float* gamma, const float* beta, void* y, float* stats, int rows, int d, float eps,
-                           cx_stream_t stream);
+                           float p_drop, unsigned long long seed, cx_stream_t stream);
 CX_API int cx_embed_layernorm_bwd(const int64_t* ids, const int64_t* type_ids, const void* word_emb, const void* type_emb,
                            const void* g1, const void* g2, const float* gamma, const float* stats, float* dword,
                            float* dtype_emb, float* dgamma, float* dbeta, void* workspace, int rows, int d,
-                           int64_t padding_idx, cx_stream_t stream);
+                           int64_t padding_idx, float p_drop, unsigned long long seed, cx_stream_t stream);
 /* ---- unpadded-token bookkeeping (flash-attn bert_padding: modeling_nomic_bert.py:333): pos[t] = t - cu_seqlens[seq(t)] */
 CX_API int cx_token_positions(const int32_t* cu_seqlens, int nseq, int32_t* pos, int32_t* seq_id, cx_stream_t stream);
 /* ---- rotary embedding, NeoX halves, in place on q and k of qkv [T,3,H,Dh] (layers/embedding.py:653-745);

@@ -210,3 +210,64 @@ def test_adamw_and_clip_match_torch():
         assert torch.count_nonzero(gg) == 0
     assert torch.allclose(p, ref_p.detach(), rtol=1e-5, atol=1e-7)
     assert torch.equal(shadow, p.to(torch.bfloat16))
+
+
+def test_fused_dropout_add_layernorm():
+    """dropout_add_layer_norm semantics (layers/block.py:422-431): z = dropout(a)/(1-p) + b, counter-based mask that is a
+    pure function of (seed, row, col): same seed -> same mask, backward re-creates it, statistics match p."""
+    from contrastors_b200 import ops
+    torch.manual_seed(7)
+    rows, d, p = 4096, 768, 0.1
+    a = bf(torch.randn(rows, d, device="cuda"))
+    b = bf(torch.randn(rows, d, device="cuda"))
+    gamma = 1 + 0.1 * torch.randn(d, device="cuda")
+    beta = 0.1 * torch.randn(d, device="cuda")
+    y1, st1, z1 = ops.add_layernorm_fwd(a, b, gamma, beta, 1e-12, want_z=True, p_drop=p, seed=1234)
+    y2, st2, z2 = ops.add_layernorm_fwd(a, b, gamma, beta, 1e-12, want_z=True, p_drop=p, seed=1234)
+    y3, _, z3 = ops.add_layernorm_fwd(a, b, gamma, beta, 1e-12, want_z=True, p_drop=p, seed=99)
+    assert torch.equal(y1, y2) and torch.equal(z1, z2) and not torch.equal(z1, z3)
+    # recover the keep mask: z - b is either 0 or a / (1 - p)
+    contrib = z1.float() - b.float()
+    keep = contrib.abs() > 0.5 * a.float().abs().clamp_min(1e-3) * 0 + 1e-2 * (a.float().abs() > 0.05)
+    sel = a.float().abs() > 0.05
+    frac = 1.0 - keep[sel].float().mean().item()
+    assert abs(frac - p) < 0.01, frac
+    # kept entries are scaled by 1/(1-p); dropped ones contribute nothing
+    ref_z = torch.where(keep, a.float() / (1 - p), torch.zeros_like(contrib)) + b.float()
+    assert (z1.float()[sel] - ref_z[sel]).abs().max().item() <= 0.05
+    ref_y = torch.nn.functional.layer_norm(z1.float(), (d,), gamma, beta, 1e-12)
+    close(y1, ref_y, 2 ** -6, "y with dropout")
+    # backward: dz (for b) is the plain LN backward; da = dz * keep / (1 - p)
+    g = bf(torch.randn(rows, d, device="cuda"))
+    dz, da = ops.add_layernorm_bwd(a, b, g, None, gamma, st1, None, None, p_drop=p, seed=1234)
+    zz = z1.float().requires_grad_()
+    torch.nn.functional.layer_norm(zz, (d,), gamma, beta, 1e-12).backward(g.float())
+    close(dz, zz.grad, 2 ** -6, "dz")
+    want_da = torch.where(keep, dz.float() / (1 - p), torch.zeros_like(dz.float()))
+    assert (da.float()[sel] - want_da[sel]).abs().max().item() <= 2 ** -6 * want_da.abs().max().item() + 1e-3
+
+
+def test_tower_dropout_replays_under_randcontext():
+    """GradCache contract (rand_state.py): re-running the tower inside the chunk's RandContext reproduces the embedding
+    bit for bit even with dropout on, and without the context the masks differ."""
+    import contrastors_b200 as cb
+    cfg = cb.NomicBertConfig(vocab_size=256, n_embd=128, n_head=2, n_inner=256, n_layer=2, resid_pdrop=0.1)
+    model = cb.BiEncoder(cb.BiEncoderConfig(encoder=cfg)).cuda()
+    model.trunk.reset_parameters(seed=1)
+    model.train()
+    ids = torch.randint(0, 256, (4, 64), device="cuda")
+    chunk = {"input_ids": ids}
+    torch.manual_seed(5)
+    state = cb.RandContext(chunk)
+    with torch.no_grad():
+        e1 = model(**chunk)["embedding"]
+        e_other = model(**chunk)["embedding"]
+    assert not torch.equal(e1, e_other)
+    with state:
+        e2 = model(**chunk)["embedding"]
+    assert torch.equal(e1, e2.detach())
+    e2.sum().backward()
+    assert torch.isfinite(model.trunk.flat_grad()).all() and torch.count_nonzero(model.trunk.flat_grad()) > 0
+    model.eval()
+    with torch.no_grad():
+        assert torch.equal(model(**chunk)["embedding"], model(**chunk)["embedding"])  # no dropout in eval mode
