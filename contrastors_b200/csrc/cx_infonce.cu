@@ -264,7 +264,6 @@ extern "C" int cx_infonce_bwd(const void* q, int64_t ldq, const void* d, int64_t
                               float scale, const float* scale_dev, const float* rq, const float* rd, int label_offset, int label_stride,
                               const float* lse, float coef, const float* coef_dev, float* dq, int64_t lddq, float* dd, int64_t lddd,
                               int accumulate_dd, float* stats, void* workspace, cx_stream_t stream_) {
-  const int ws_has_f16 = 0;
   CX_REQUIRE(q && d && lse && dq && dd && stats && workspace, "cx_infonce_bwd: null pointer");
   CX_REQUIRE(n > 0 && m > 0 && k_dim > 0, "cx_infonce_bwd: empty problem");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -297,7 +296,7 @@ extern "C" int cx_infonce_bwd(const void* q, int64_t ldq, const void* d, int64_t
   const void* qB = q;
   const void* dB = d;
   int64_t ldqB = ldq, lddB = ldd;
-  if (f16 && ws_has_f16 == 0) {
+  if (f16) {
     const int threads = 256;
     const int64_t per_row = (k_dim + 7) / 8;
     const int vq = (ldq % 8 == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0) ? 1 : 0;
