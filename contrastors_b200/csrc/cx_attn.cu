@@ -268,20 +268,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __restrict
 }
 
 // ============================================================================================== backward
-// delta[h, t] = sum_d dO[t,h,d] * O[t,h,d]
+// delta[h, t] = sum_d dO[t,h,d] * O[t,h,d]; 8 threads per (t, h) row of 64, 16-byte loads
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
                                   float* __restrict__ delta, int T, int H) {
-  // one warp per (t, h): 64 elements = 2 per lane
-  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (w >= (int64_t)T * H) return;
-  const int t = (int)(w / H), h = (int)(w % H);
-  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(o + ((size_t)t * H + h) * kDh + lane * 2);
-  const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(dout + ((size_t)t * H + h) * kDh + lane * 2);
-  float s = __low2float(a) * __low2float(b) + __high2float(a) * __high2float(b);
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = gid >> 3;  // (t, h) flattened: element offset row * 64
+  const int sub = (int)(gid & 7);
+  float s = 0.f;
+  if (row < (int64_t)T * H) {
+    const uint4 a = *reinterpret_cast<const uint4*>(o + row * kDh + sub * 8);
+    const uint4 b = *reinterpret_cast<const uint4*>(dout + row * kDh + sub * 8);
+    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
 #pragma unroll
-  for (int o_ = 16; o_ > 0; o_ >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o_);
-  if (lane == 0) delta[(size_t)h * T + t] = s;
+    for (int i = 0; i < 4; ++i) s += __low2float(pa[i]) * __low2float(pb[i]) + __high2float(pa[i]) * __high2float(pb[i]);
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  if (sub == 0 && row < (int64_t)T * H) {
+    const int t = (int)(row / H), h = (int)(row % H);
+    delta[(size_t)h * T + t] = s;
+  }
 }
 
 constexpr int kBwdThreads = 384;  // 4 control warps + 2 x 4 worker warps (each group owns 64 of the 128 key columns)
@@ -430,7 +438,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       const int q_row = i * 128 + r;
       const bool row_ok = q_row < len;
       const float lse2 = row_ok ? lse[(size_t)head * T + seq_begin + q_row] * kLog2e : INFINITY;  // +inf => P = 0
-      const float dl = row_ok ? delta[(size_t)head * T + seq_begin + q_row] : 0.f;
+      const float dl = row_ok ? delta[(size_t)head * T + seq_begin + q_row] * softmax_scale : 0.f;  // pre-scaled
       mbar_wait(sdp_full, i & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -452,7 +460,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
             p[t] = fast_exp2(fmaf(__uint_as_float(vs[8 * q + t]), scale2, -lse2));
-            ds[t] = p[t] * (__uint_as_float(vd[8 * q + t]) - dl) * softmax_scale;
+            ds[t] = p[t] * fmaf(__uint_as_float(vd[8 * q + t]), softmax_scale, -dl);
           }
           uint4 w, x;
           w.x = pack_bf16x2(p[0], p[1]);
@@ -582,8 +590,8 @@ extern "C" int cx_attn_bwd(const void* qkv, const void* out, const void* dout, c
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int T = total_tokens;
   {
-    const int64_t warps = (int64_t)T * H;
-    attn_delta_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta, T, H);
+    const int64_t threads = (int64_t)T * H * 8;
+    attn_delta_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta, T, H);
     CX_LAUNCH_CHECK();
   }
   CUtensorMap tmQKV, tmDO, tmDQ;

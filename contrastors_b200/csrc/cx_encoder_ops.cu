@@ -827,11 +827,11 @@ extern "C" int cx_embed_layernorm_fwd(const int64_t* ids, const int64_t* type_id
 
 static int ln_bwd_grid(int rows) {
   int g = (rows + 7) / 8;
-  const int cap = 2 * sm_count();
+  const int cap = 2 * sm_count();  // 4x measured slower (72 vs 63 us at T = 32768)
   return g < cap ? (g < 1 ? 1 : g) : cap;
 }
 
-extern "C" size_t cx_layernorm_bwd_workspace_bytes(int d) { return (size_t)2 * sm_count() * 3 * d * sizeof(float); }
+extern "C" size_t cx_layernorm_bwd_workspace_bytes(int d) { return (size_t)4 * sm_count() * 3 * d * sizeof(float); }
 
 template <bool EMBED, int NV>
 static int ln_bwd_launch(int grid, size_t smem, cudaStream_t st, const __nv_bfloat16* a, const __nv_bfloat16* b, const int64_t* ids,
