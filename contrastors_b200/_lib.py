@@ -61,6 +61,7 @@ SIGNATURES = {
     "cx_cls_select_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "cx_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "cx_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
+    "cx_debug_attn_trace": (_i, [_vp]),
 }
 
 

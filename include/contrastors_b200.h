@@ -180,6 +180,10 @@ CX_API int cx_attn_bwd(const void* qkv, const void* out, const void* dout, const
                 void* dqkv, float* dq_acc, float* delta, int total_tokens, int nseq, int max_seqlen, int H, int Dh,
                 float softmax_scale, cx_stream_t stream);
 
+/* Profiling hook: buf = device int64 [n_ctas, 64] (or NULL to switch off).  While set, the pipelined attention kernels
+ * record clock64() stamps of their pipeline events per CTA (tools/trace_attn.py decodes them).  Never set in production. */
+CX_API int cx_debug_attn_trace(void* buf);
+
 #ifdef __cplusplus
 }
 #endif

@@ -161,9 +161,14 @@ def _attn_ref(qkv, lens, H, Dh, scale):
     return torch.cat(outs, 0)
 
 
-@pytest.mark.parametrize("lens,H", [([128], 1), ([512, 512], 2), ([300, 17, 512, 129, 1], 3), ([197] * 4, 12), ([640, 1000], 2)])
-def test_attention_fwd_bwd(lens, H):
+@pytest.mark.parametrize("modes", [(6, 2), (7, 2), (3, 2), (2, 2), (1, 1)],
+                         ids=["wideS", "wideS-poly", "pipelined-tmemP", "pipelined-smemP", "serial"])
+@pytest.mark.parametrize("lens,H", [([128], 1), ([512, 512], 2), ([300, 17, 512, 129, 1], 3), ([197] * 4, 12), ([640, 1000], 2),
+                                    ([64], 1), ([65, 191, 192, 193], 2)])
+def test_attention_fwd_bwd(lens, H, modes, monkeypatch):
     from contrastors_b200 import ops
+    monkeypatch.setenv("CX_ATTN_FWD", str(modes[0]))  # kernel generation, read by the library at every call
+    monkeypatch.setenv("CX_ATTN_BWD", str(modes[1]))
     torch.manual_seed(5)
     Dh = 64
     scale = 1.0 / math.sqrt(Dh)
