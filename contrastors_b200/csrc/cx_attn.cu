@@ -32,23 +32,6 @@ constexpr int kDh = 64;
 // 64 slots per CTA, so a session can see where a CTA's lifetime goes.  Null in production (one predictable branch).
 __device__ long long* g_attn_trace = nullptr;
 
-// Arrival bookkeeping per SM: (launch epoch << 8) | CTAs of that launch that have started on the SM so far.  The forward
-// kernel runs two CTAs per SM that would otherwise start, load and drain in lockstep (same work per CTA), so their TMA
-// prologues and epilogues coincide and nothing overlaps them; the second CTA to arrive on an SM is held back by about half
-// a CTA lifetime once, and every later CTA in that slot inherits the offset.
-__device__ unsigned int g_sm_arrivals[1024];
-__device__ __forceinline__ unsigned int sm_arrival_slot(unsigned int epoch) {
-  unsigned int smid;
-  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-  unsigned int* w = &g_sm_arrivals[smid & 1023];
-  unsigned int old = *reinterpret_cast<volatile unsigned int*>(w);
-  while (true) {
-    const unsigned int want = ((old >> 8) == epoch) ? old + 1 : ((epoch << 8) | 1u);
-    const unsigned int seen = atomicCAS(w, old, want);
-    if (seen == old) return ((old >> 8) == epoch) ? (old & 0xffu) : 0u;
-    old = seen;
-  }
-}
 __device__ __forceinline__ void trace_put(long long* tr, int slot) {
   if (tr != nullptr) tr[slot] = clock64();
 }
@@ -323,8 +306,7 @@ struct Fwd2Smem {
 template <bool kPTmem, uint32_t kPolyMask>
 __global__ void __launch_bounds__(kFwd2Threads, 2)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __restrict__ cu_seqlens,
-                 __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int T, int H, float scale2, int ablate,
-                 unsigned int epoch, int dephase_clks) {
+                 __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int T, int H, float scale2, int ablate) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Fwd2Smem::kBars);
   uint64_t* q_full = bars;          // [1]
@@ -347,10 +329,6 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __restric
   const int nk = (len + 127) / 128;  // 128-key TMA tiles
   const int nu = (len + 63) / 64;    // 64-key sub-tiles
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  if (threadIdx.x == 0 && dephase_clks > 0 && sm_arrival_slot(epoch) == 1u) {
-    const long long t0 = clock64();
-    while (clock64() - t0 < dephase_clks) __nanosleep(200);
-  }
   long long* tr = g_attn_trace;
   if (tr != nullptr) {
     tr += ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 64;
@@ -1628,19 +1606,20 @@ __global__ void dq_finalize_kernel(const float* __restrict__ dq_acc, __nv_bfloat
 
 using namespace cx;
 
-// Kernel generation selectable at run time for A/B timing (CX_ATTN_FWD = 1: serial 128-key tiles, 2: pipelined 64-key
-// sub-tiles with P in shared memory, 3: same with P in tensor memory, 4 / 5: as 3 with 3/8 / 4/8 of the exponentials on
-// the FMA pipe, 6: wide-S (one N = 128 score chain per key tile, P in its own TMEM columns) = default, 7: 6 + 3/8
-// polynomial; CX_ATTN_BWD = 1: serial, 2: pipelined = default).  Measured on B200, 64 x 512 tokens x 12 heads:
-// forward 138 / 131 / 127 / 145 / 150 / 113.5 / 113.6 us, backward (incl. delta, zero fill, finalize) 415 / 386 us.
+// Kernel generation selectable at run time for A/B timing and profiling sessions.  CX_ATTN_FWD = 1: serial 128-key tiles,
+// 3: pipelined 64-key sub-tiles (P in tensor memory; carries the trace / ablation hooks), 6: wide-S = default, 7: wide-S
+// with 3/8 of the exponentials on the FMA pipe; CX_ATTN_BWD = 1: serial, 2: pipelined = default.  Measured on B200,
+// 64 x 512 tokens x 12 heads, L2 flushed: forward 138 / 127 / 110.6 / 113.6 us; backward (incl. delta, zero fill, dQ
+// finalize) 415 / 376 us.  (Also tried and dropped: P through shared memory in the sub-tile kernel 131 us; 3/8 and 4/8
+// polynomial exponentials there 145 / 150 us; holding back the second CTA of each SM to de-phase the pair: no gain.)
 constexpr int kFwdDefaultMode = 6;
 constexpr int kBwdDefaultMode = 2;
-constexpr uint32_t kPoly38 = 0x52, kPoly48 = 0xAA;  // column-pair pattern (period 8) routed to the polynomial
+constexpr uint32_t kPoly38 = 0x52;  // column-pair pattern (period 8) routed to the polynomial
 static int attn_mode(const char* name, int dflt) {
   const char* e = getenv(name);
   if (!e || !*e) return dflt;
   const int v = atoi(e);
-  return v >= 1 && v <= 7 ? v : dflt;
+  return (v == 1 || v == 2 || v == 3 || v == 6 || v == 7) ? v : dflt;
 }
 
 extern "C" int cx_debug_attn_trace(void* buf) {
@@ -1667,10 +1646,7 @@ extern "C" int cx_attn_fwd(const void* qkv, const int32_t* cu_seqlens, void* out
   static bool configured = false;
   if (!configured) {
     CX_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::kTotal));
-    CX_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd2_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2Smem::kTotal));
     CX_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd2_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2Smem::kTotal));
-    CX_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd2_kernel<true, kPoly38>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2Smem::kTotal));
-    CX_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd2_kernel<true, kPoly48>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2Smem::kTotal));
     CX_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2Smem::kTotal));
     CX_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd3_kernel<kPoly38>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2Smem::kTotal));
     configured = true;
@@ -1678,32 +1654,18 @@ extern "C" int cx_attn_fwd(const void* qkv, const int32_t* cu_seqlens, void* out
   dim3 grid((max_seqlen + 127) / 128, H, nseq);
   const int mode = attn_mode("CX_ATTN_FWD", kFwdDefaultMode);
   const int ablate = attn_ablate();
-  static std::atomic<unsigned int> launch_epoch{1};
-  const unsigned int epoch = launch_epoch.fetch_add(1, std::memory_order_relaxed) & 0xffffffu;
-  // CX_ATTN_DEPHASE = clocks to hold the second CTA of each SM back once (see g_sm_arrivals)
-  const char* de = getenv("CX_ATTN_DEPHASE");
-  const int dephase = (de && *de) ? atoi(de) : 0;  // opt-in: measured no gain (the tensor pipe's per-instruction cost binds)
   if (mode == 1)
     attn_fwd_kernel<<<grid, kFwdThreads, FwdSmem::kTotal, stream>>>(tm, cu_seqlens, (__nv_bfloat16*)out, lse, total_tokens, H,
                                                                    softmax_scale * kLog2e);
-  else if (mode == 2)
-    attn_fwd2_kernel<false, 0><<<grid, kFwd2Threads, Fwd2Smem::kTotal, stream>>>(tm, cu_seqlens, (__nv_bfloat16*)out, lse,
-                                                                                total_tokens, H, softmax_scale * kLog2e, ablate, epoch, dephase);
   else if (mode == 3)
     attn_fwd2_kernel<true, 0><<<grid, kFwd2Threads, Fwd2Smem::kTotal, stream>>>(tm, cu_seqlens, (__nv_bfloat16*)out, lse,
-                                                                               total_tokens, H, softmax_scale * kLog2e, ablate, epoch, dephase);
-  else if (mode == 6)
-    attn_fwd3_kernel<0><<<grid, kFwd2Threads, Fwd2Smem::kTotal, stream>>>(tm, cu_seqlens, (__nv_bfloat16*)out, lse, total_tokens, H,
-                                                                         softmax_scale * kLog2e);
+                                                                               total_tokens, H, softmax_scale * kLog2e, ablate);
   else if (mode == 7)
     attn_fwd3_kernel<kPoly38><<<grid, kFwd2Threads, Fwd2Smem::kTotal, stream>>>(tm, cu_seqlens, (__nv_bfloat16*)out, lse, total_tokens,
                                                                                H, softmax_scale * kLog2e);
-  else if (mode == 4)
-    attn_fwd2_kernel<true, kPoly38><<<grid, kFwd2Threads, Fwd2Smem::kTotal, stream>>>(tm, cu_seqlens, (__nv_bfloat16*)out, lse,
-                                                                                     total_tokens, H, softmax_scale * kLog2e, ablate, epoch, dephase);
   else
-    attn_fwd2_kernel<true, kPoly48><<<grid, kFwd2Threads, Fwd2Smem::kTotal, stream>>>(tm, cu_seqlens, (__nv_bfloat16*)out, lse,
-                                                                                     total_tokens, H, softmax_scale * kLog2e, ablate, epoch, dephase);
+    attn_fwd3_kernel<0><<<grid, kFwd2Threads, Fwd2Smem::kTotal, stream>>>(tm, cu_seqlens, (__nv_bfloat16*)out, lse, total_tokens, H,
+                                                                         softmax_scale * kLog2e);
   CX_LAUNCH_CHECK();
   return 0;
 }

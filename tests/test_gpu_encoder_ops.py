@@ -161,8 +161,7 @@ def _attn_ref(qkv, lens, H, Dh, scale):
     return torch.cat(outs, 0)
 
 
-@pytest.mark.parametrize("modes", [(6, 2), (7, 2), (3, 2), (2, 2), (1, 1)],
-                         ids=["wideS", "wideS-poly", "pipelined-tmemP", "pipelined-smemP", "serial"])
+@pytest.mark.parametrize("modes", [(6, 2), (7, 2), (3, 2), (1, 1)], ids=["wideS", "wideS-poly", "subtile", "serial"])
 @pytest.mark.parametrize("lens,H", [([128], 1), ([512, 512], 2), ([300, 17, 512, 129, 1], 3), ([197] * 4, 12), ([640, 1000], 2),
                                     ([64], 1), ([65, 191, 192, 193], 2)])
 def test_attention_fwd_bwd(lens, H, modes, monkeypatch):

@@ -1,5 +1,7 @@
 """Timing ablations of the pipelined attention kernels (CX_ATTN_ABLATE bit mask; results are wrong by design):
-1 = no dQ TMA reduce-add, 2 = no exponentials, 4 = no P/dS stores, 8 = no TMEM score reads, 16 = 1/8 of the dV/dK/dQ MMAs."""
+1 = no dQ TMA reduce-add, 2 = no exponentials, 4 = no P/dS stores, 8 = no TMEM score reads (the filler uses I2F, i.e. the
+SFU: read that bit with care), 16 = 1/8 of the dV/dK/dQ MMAs, 32 = interleaved issue order of the independent MMA chains
+(results stay correct).  Forward ablations exist in the 64-key sub-tile kernel (CX_ATTN_FWD=3) only."""
 import json
 import math
 import os
@@ -40,7 +42,7 @@ res = {}
 # fixed overheads of the backward wrapper (delta + zero fill + finalize): time them via the pieces
 dq_acc = torch.zeros(T, H * Dh, device="cuda")
 res["zero_fill_ms"] = timeit(lambda: dq_acc.zero_())
-for fm in (3, 4, 5, 2):
+for fm in (3,):
     for ab in (0, 2, 4, 8, 2 | 4, 2 | 8, 2 | 4 | 8):
         os.environ["CX_ATTN_FWD"], os.environ["CX_ATTN_ABLATE"] = str(fm), str(ab)
         res[f"fwd{fm}_ablate{ab}_ms"] = timeit(lambda: ops.attn_fwd(qkv, cu, S, H, Dh, scale))

@@ -27,7 +27,7 @@ def timeit(fn, iters=8, warm=2):
 
 
 # usage: bench_attn.py [fwd_mode,bwd_mode ...]   (a trapped kernel poisons the context: one process per generation)
-MODES = [tuple(int(x) for x in a.split(",")) for a in sys.argv[1:]] or [(1, 1), (2, 2), (3, 2)]
+MODES = [tuple(int(x) for x in a.split(",")) for a in sys.argv[1:]] or [(1, 1), (3, 2), (6, 2)]
 TAG = "_".join(f"{a}{b}" for a, b in MODES)
 res = {}
 for name, nseq, S, H in [("bert_64x512", 64, 512, 12), ("vit_256x197", 256, 197, 12)]:

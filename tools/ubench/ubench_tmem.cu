@@ -81,7 +81,8 @@ __global__ void mufu_kernel(int iters, long long* out, float* sink) {
 // UTCHMMA issue->completion rate: warp 0 (converged, one elected lane) issues `n` back-to-back MMAs on garbage operands.
 // variant 0: SS N=128 (A,B K-major)  1: SS N=64 (A K-major, B MN-major)  2: TS N=64 (A from TMEM, B MN-major)
 //         3: SS N=64 (A,B MN-major)  4: SS N=256 (A,B K-major)          5: SS N=64 (A,B K-major)
-__global__ void mma_kernel(int variant, int n, int nacc, long long* out) {
+template <int variant, int nacc>
+__global__ void mma_kernel(int n, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t tptr;
   __shared__ uint64_t bar;
@@ -159,22 +160,17 @@ int main() {
     cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
     printf("MUFU.EX2 (+FADD), %2d warps/SM: %.2f ex2/clk/SM\n", threads / 32, (double)iters * 16 * threads / med(h, nb));
   }
-  cudaFuncSetAttribute(mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
   const char* names[6] = {"SS M128 N128 K16 (A,B K-major)", "SS M128 N64 (A K-major, B MN-major)", "TS M128 N64 (A tmem, B MN-major)",
                           "SS M128 N64 (A,B MN-major)", "SS M128 N256 (A,B K-major)", "SS M128 N64 (A,B K-major)"};
-  for (int v = 0; v < 6; ++v) {
-    const int n = 4096;
-    double r[3];
-    int k = 0;
-    for (int nacc : {1, 2, 4}) {
-      if (v == 4 && nacc > 2) { r[k++] = 0; continue; }  // N=256: only two accumulators fit in the 256 columns used
-      mma_kernel<<<nb, 128, 98304>>>(v, n, nacc, d);
-      cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
-      r[k++] = med(h, nb) / n;
-    }
-    printf("UTCHMMA %-40s: %.1f / %.1f / %.1f clk per MMA with 1 / 2 / 4 independent accumulators (%s)\n", names[v], r[0], r[1], r[2],
-           cudaGetErrorString(cudaGetLastError()));
-  }
+  const int n = 4096;
+#define RUN_MMA(V, A)                                                                                   \
+  cudaFuncSetAttribute(mma_kernel<V, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);           \
+  mma_kernel<V, A><<<nb, 128, 98304>>>(n, d);                                                            \
+  cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);                                                   \
+  printf("UTCHMMA %-40s: %.1f clk per MMA with %d accumulator(s) (%s)\n", names[V], med(h, nb) / n, A, \
+         cudaGetErrorString(cudaGetLastError()));
+  RUN_MMA(0, 1) RUN_MMA(0, 2) RUN_MMA(1, 1) RUN_MMA(1, 2) RUN_MMA(1, 4) RUN_MMA(2, 1) RUN_MMA(2, 2) RUN_MMA(3, 1) RUN_MMA(3, 2)
+  RUN_MMA(3, 4) RUN_MMA(4, 1) RUN_MMA(5, 1) RUN_MMA(5, 2)
   cudaDeviceSynchronize();
   printf("done: %s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
