@@ -15,9 +15,13 @@
 //   dK/dV accumulate in TMEM, dQ partials leave through TMA reduce-add into an fp32 accumulator (own 4-warp group);
 //   S(i+1) / dP(i+1) are issued as soon as P(i) / dS(i) have left the registers.
 // Older generations (attn_fwd_kernel, attn_fwd2_kernel, attn_bwd_kernel) stay selectable for A/B timing (see below).
-// What binds (tools/ubench, tools/trace_attn.py): a tcgen05.mma with N <= 128 costs ~82-150 clk of tensor-pipe time
-// whatever its size (operand fetch from smem / TMEM), so both passes are bound by the NUMBER of MMA instructions per tile,
-// not by the exponentials (MUFU 16 / clk / SM) or by TMEM reads (> 800 B / clk / SM).
+// What binds (tools/ubench, tools/trace_attn.py, profiles/r01_ubench_tmem_mma.txt): forward, the SFU: 16384 exponentials
+// per 128 x 128 tile at 16 / clk / SM = 1024 clk against 512 clk of tensor time (S as N = 128: 64 clk per MMA; PV from TMEM:
+// 32 clk per MMA) -- plus ~30 % of each CTA's lifetime in prologue (TMA round trip) and epilogue.  Backward, the shared-
+// memory port: 240 KB of MMA operands + 128 KB of P / dS / dQ-staging traffic per tile at 128 B/clk = 2900 clk against
+// 1664 clk of tensor time (an SS MMA with N = 64 takes 48 clk, not 32: its 6 KB of operands come through that port).
+// The thread that ISSUES the MMAs must stay tight: the TMA / MMA warps run converged with elect.sync around the
+// asynchronous instructions only (under `if (lane == 0)` every UTCHMMA sits in an elect-and-branch loop, ~80 clk each).
 #include <math.h>
 #include <stdlib.h>
 
@@ -645,9 +649,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __restric
 }
 
 // ---------------------------------------------------------------------------------------------- forward, wide-S variant
-// As attn_fwd2_kernel, but the scores of a whole 128-key tile come from ONE chain of four N = 128 MMAs (a tcgen05.mma
-// with N = 64 costs as much issue/operand-fetch time as one with N = 128: measured ~126 vs ~82 clk, tools/ubench), while
-// the softmax still works in 64-column halves with one thread per row.  P (bf16) gets its own 2 x 32 TMEM columns, so
+// As attn_fwd2_kernel, but the scores of a whole 128-key tile come from ONE chain of four N = 128 MMAs (half the
+// instructions to issue, and Q is read from shared memory once per key tile instead of twice), while the softmax still
+// works in 64-column halves with one thread per row.  P (bf16) gets its own 2 x 32 TMEM columns, so
 // the score columns are free as soon as every thread has LOADED the second half into registers (s_free): S(j+1) then
 // runs under the exponentials of the second half of tile j.  TMEM: S [0,128)  O [128,192)  P0 [192,224)  P1 [224,256).
 template <uint32_t kPolyMask>
