@@ -11,7 +11,7 @@ from .loss import (accumulate_gradients, cache_loss, clip_loss, get_chunked_embe
                    matryoshka_clip_loss, symmetric_clip_loss)
 from .models import BiEncoder, BiEncoderConfig, NomicBertConfig, NomicBertModel, nomic_bert_base  # noqa: F401
 from .rand_state import RandContext  # noqa: F401
-from . import trainer  # noqa: F401
+from . import checkpoint, trainer  # noqa: F401
 from .vit import DualEncoder, ViTConfig, ViTModel, VisionBiEncoder, VisionBiEncoderConfig, vit_b16, vit_l14  # noqa: F401
 
 __version__ = "0.1.0"

@@ -231,6 +231,30 @@ class NomicBertModel(nn.Module):
     def flat_grad(self):
         return self._flat_grad
 
+    def optimizer_state_dict(self):
+        """State of the fused AdamW in torch.optim.AdamW's terms (``step``, ``exp_avg``, ``exp_avg_sq`` per parameter), keyed by
+        the reference's parameter names so it does not depend on the flat layout (``optimizer.pt``, trainers/base.py:323-324)."""
+        if self._opt_state is None:
+            return {"state": {}, "step": 0}
+        st = self._opt_state
+        state = {name: {"step": st["step"], "exp_avg": self.view(st["m"], name).detach().cpu().clone(),
+                        "exp_avg_sq": self.view(st["v"], name).detach().cpu().clone()} for name in self._offsets}
+        return {"state": state, "step": st["step"]}
+
+    def load_optimizer_state_dict(self, sd):
+        if not sd.get("state"):
+            self._opt_state = None
+            return
+        missing = [k for k in self._offsets if k not in sd["state"]]
+        if missing:
+            raise KeyError(f"optimizer state misses {missing}")
+        m, v = torch.zeros_like(self._flat), torch.zeros_like(self._flat)
+        with torch.no_grad():
+            for name in self._offsets:
+                self.view(m, name).copy_(sd["state"][name]["exp_avg"].to(m.device))
+                self.view(v, name).copy_(sd["state"][name]["exp_avg_sq"].to(v.device))
+        self._opt_state = dict(step=int(sd["step"]), m=m, v=v)
+
     # ---------------------------------------------------------------- forward
     def forward(self, input_ids, attention_mask=None, position_ids=None, token_type_ids=None, seq_lens=None, **kwargs):
         """Returns the last hidden state re-padded to [B, S, d] (zeros at pad positions, modeling_nomic_bert.py:392-393)."""
