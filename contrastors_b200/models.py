@@ -337,7 +337,8 @@ class _TrunkFn(torch.autograd.Function):
         for i in range(cfg.n_layer):
             p = f"encoder.layers.{i}."
             # (cx_gemm_qkv_rope fuses the rotation into the epilogue but its per-row cos/sin gather costs more than this
-            #  standalone 7 TB/s pass: measured 213 us vs 98 + 28 us at T = 32768, so the two-kernel form stays)
+            #  standalone 7 TB/s pass: measured 219 us vs 89 + 35 us at T = 32768 (tools/bench_qkv_rope.py), so the
+            #  two-kernel form stays)
             qkv = ops.gemm(h, v(W, p + "attn.Wqkv.weight"))
             ops.rope_inplace(qkv, packed.pos, cos_t, sin_t, H, Dh)
             attn, lse = ops.attn_fwd(qkv, packed.cu, packed.max_seqlen, H, Dh, scale)

@@ -1,3 +1,5 @@
+#!/bin/bash
+# quick confirmation of HEAD on a B200: full GPU parity suite + the driver's smoke entry
 cd "${GRAFT_REPO_ROOT:-/root/repo}"; mkdir -p gpurun_out
-timeout 200 python -m pytest tests/test_gpu_encoder_ops.py tests/test_gpu_encoder.py -q -m gpu 2>&1 | tail -3
-timeout 60 ./tools/ubench/ubench_tmem 2>&1 | tee gpurun_out/ubench4.log | grep UTCHMMA
+timeout 600 python -m pytest tests -q -m gpu 2>&1 | tail -4 | tee gpurun_out/tests.log
+timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
