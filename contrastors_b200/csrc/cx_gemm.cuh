@@ -147,7 +147,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (converged warp; one elected lane issues:
-    // code under `lane == 0` makes ptxas wrap every TMA / MMA / commit in an elect-and-branch loop, see cx_attn.cu)
+    // code under `lane == 0` makes ptxas wrap every TMA / MMA / commit in an elect-and-branch loop, see cx_attn_fwd.cuh)
     {
       int stage = 0;
       uint32_t phase = 0;
