@@ -26,3 +26,14 @@ def test_default_arm_needs_a_gpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True,
                          text=True, timeout=300, cwd=ROOT)
     assert out.returncode != 0 and "no CPU fallback" in (out.stdout + out.stderr)
+
+
+def test_tool_scripts_compile():
+    """tools/*.py are GPU session scripts: at least keep them syntactically valid on the CPU box."""
+    import glob
+    import py_compile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    scripts = sorted(glob.glob(os.path.join(root, "tools", "*.py")))
+    assert scripts
+    for path in scripts:
+        py_compile.compile(path, doraise=True)
