@@ -15,9 +15,10 @@
 //   dK/dV accumulate in TMEM, dQ partials leave through TMA reduce-add into an fp32 accumulator (own 4-warp group);
 //   S(i+1) / dP(i+1) are issued as soon as P(i) / dS(i) have left the registers.
 // Older generations (attn_fwd_kernel, attn_fwd2_kernel, attn_bwd_kernel) stay selectable for A/B timing (see below).
-// What binds (tools/ubench, tools/trace_attn.py, profiles/r01_ubench_tmem_mma.txt): forward, the SFU: 16384 exponentials
-// per 128 x 128 tile at 16 / clk / SM = 1024 clk against 512 clk of tensor time (S as N = 128: 64 clk per MMA; PV from TMEM:
-// 32 clk per MMA) -- plus ~30 % of each CTA's lifetime in prologue (TMA round trip) and epilogue.  Backward, the shared-
+// What binds (tools/ubench, tools/trace_attn.py, profiles/r01_ubench_tmem_mma.txt): forward, nearest hard bound the SFU
+// (16384 exponentials per 128 x 128 tile at 16 / clk / SM = 1024 clk against 512 clk of tensor time: S as N = 128 is 64 clk
+// per MMA, PV from TMEM 32 clk), in practice the latency chain of the one softmax warp per SM sub-partition per CTA (the
+// loop runs at 1200-1450 clk per tile) -- plus ~30 % of each CTA's lifetime in prologue (TMA round trip) and epilogue.  Backward, the shared-
 // memory port: 240 KB of MMA operands + 128 KB of P / dS / dQ-staging traffic per tile at 128 B/clk = 2900 clk against
 // 1664 clk of tensor time (an SS MMA with N = 64 takes 48 clk, not 32: its 6 KB of operands come through that port).
 // The thread that ISSUES the MMAs must stay tight: the TMA / MMA warps run converged with elect.sync around the
