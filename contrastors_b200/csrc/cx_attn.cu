@@ -52,7 +52,7 @@ using namespace cx;
 
 // Kernel generation selectable at run time for A/B timing and profiling sessions.  CX_ATTN_FWD = 1: serial 128-key tiles,
 // 3: pipelined 64-key sub-tiles (P in tensor memory; carries the trace / ablation hooks), 6: wide-S = default, 7: wide-S
-// with 3/8 of the exponentials on the FMA pipe, 8: EXPERIMENTAL two-threads-per-row wide-S kernel (not yet run on hardware);
+// with 3/8 of the exponentials on the FMA pipe, 8 / 9: EXPERIMENTAL two-threads-per-row wide-S kernel, non-persistent / persistent (not yet run on hardware);
 // CX_ATTN_BWD = 1: serial, 2: pipelined = default, 3: EXPERIMENTAL transposed-score kernel (dV / dK fed from TMEM; not yet run
 // on hardware).  Measured on B200,
 // 64 x 512 tokens x 12 heads, L2 flushed: forward 138 / 127 / 110.6 / 113.6 us; backward (incl. delta, zero fill, dQ
@@ -65,7 +65,7 @@ static int attn_mode(const char* name, int dflt) {
   const char* e = getenv(name);
   if (!e || !*e) return dflt;
   const int v = atoi(e);
-  return (v == 1 || v == 2 || v == 3 || v == 6 || v == 7 || v == 8) ? v : dflt;
+  return (v == 1 || v == 2 || v == 3 || (v >= 6 && v <= 9)) ? v : dflt;
 }
 
 extern "C" int cx_debug_attn_trace(void* buf) {
@@ -95,6 +95,7 @@ extern "C" int cx_attn_fwd(const void* qkv, const int32_t* cu_seqlens, void* out
     CX_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd2_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2Smem::kTotal));
     CX_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2Smem::kTotal));
     CX_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd4Smem::kTotal));
+    CX_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd5Smem::kTotal));
     CX_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd3_kernel<kPoly38>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2Smem::kTotal));
     configured = true;
   }
@@ -107,7 +108,13 @@ extern "C" int cx_attn_fwd(const void* qkv, const int32_t* cu_seqlens, void* out
   else if (mode == 3)
     attn_fwd2_kernel<true, 0><<<grid, kFwd2Threads, Fwd2Smem::kTotal, stream>>>(tm, cu_seqlens, (__nv_bfloat16*)out, lse,
                                                                                total_tokens, H, softmax_scale * kLog2e, ablate);
-  else if (mode == 8)
+  else if (mode == 9) {
+    const int nqt = (max_seqlen + 127) / 128, n_items = nqt * H * nseq;
+    int ctas = 2 * sm_count();
+    if (ctas > n_items) ctas = n_items;
+    attn_fwd5_kernel<<<ctas, kFwd4Threads, Fwd5Smem::kTotal, stream>>>(tm, cu_seqlens, (__nv_bfloat16*)out, lse, total_tokens, H,
+                                                                      softmax_scale * kLog2e, nqt, n_items);
+  } else if (mode == 8)
     attn_fwd4_kernel<<<grid, kFwd4Threads, Fwd4Smem::kTotal, stream>>>(tm, cu_seqlens, (__nv_bfloat16*)out, lse, total_tokens, H,
                                                                       softmax_scale * kLog2e);
   else if (mode == 7)

@@ -1159,3 +1159,337 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __restric
   }
 }
 
+// ---------------------------------------------------------------------------------------------- forward, persistent
+// EXPERIMENTAL (CX_ATTN_FWD=9; written after the last GPU minute of round 1: it compiles and its mbarrier protocol runs
+// clean on tools/sim_attn_protocol.py, it has NOT run on hardware yet).  attn_fwd4_kernel made persistent: 2 CTAs per SM
+// loop over the work items (sequence, head, 128 query rows), so the next item's Q / K / V loads and its first score tile
+// run under the current item's loop and epilogue (tools/trace_attn.py: ~30 % of a non-persistent CTA's lifetime is the TMA
+// round trip of its first loads plus its epilogue).  All pipeline barriers run on counters that continue across items; Q is
+// double-buffered and the finished item's Q buffer doubles as the staging tile of its epilogue (q_empty = the MMA commit +
+// 256 softmax arrivals after the copy-out); the single O accumulator is handed back through o_free before the next item's
+// first PV overwrites it.  TMEM as attn_fwd4_kernel: S [0,128)  O [128,192)  P [192,256).
+struct Fwd5Smem {
+  static constexpr int kTile = 128 * kDh * 2;      // 16 KB: 128 rows x 128 B
+  static constexpr int kQ = 0;                     // 2 buffers (item parity)
+  static constexpr int kK = kQ + 2 * kTile;        // 2 stages of 128 keys
+  static constexpr int kV = kK + 2 * kTile;        // 2 stages
+  static constexpr int kX = kV + 2 * kTile;        // exchange: 2 x [2 groups][128 rows] bf16 maxima, then [2][128] fp32 row sums
+  static constexpr int kBars = kX + 1024;
+  static constexpr int kTotal = kBars + 256;       // 99,584 B: two CTAs per SM
+};
+
+struct Fwd5Item {
+  int seq_begin, len, q0, nk, head;
+};
+// work item w -> (sequence, head, query tile); false if the tile lies past the end of its sequence
+__device__ __forceinline__ bool fwd5_item(int w, int nqt, int H, const int* __restrict__ cu_seqlens, Fwd5Item& it) {
+  const int qt = w % nqt, rest = w / nqt;
+  it.head = rest % H;
+  const int seq = rest / H;
+  it.seq_begin = cu_seqlens[seq];
+  it.len = cu_seqlens[seq + 1] - it.seq_begin;
+  it.q0 = qt * 128;
+  it.nk = (it.len + 127) / 128;
+  return it.q0 < it.len;
+}
+
+__global__ void __launch_bounds__(kFwd4Threads, 2)
+attn_fwd5_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __restrict__ cu_seqlens,
+                 __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int T, int H, float scale2, int nqt, int n_items) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Fwd5Smem::kBars);
+  uint64_t* q_full = bars;          // [2]
+  uint64_t* q_empty = bars + 2;     // [2]  257 arrivals: the MMA commit behind the item's last S + the 256 epilogue threads
+  uint64_t* k_full = bars + 4;      // [2]
+  uint64_t* k_empty = bars + 6;     // [2]
+  uint64_t* v_full = bars + 8;      // [2]
+  uint64_t* v_empty = bars + 10;    // [2]
+  uint64_t* s_full = bars + 12;     // S(g) in TMEM
+  uint64_t* s_free = bars + 13;     // every softmax thread holds its 64 scores of S(g) in registers (256 arrivals)
+  uint64_t* p_ready = bars + 14;    // P(g) written (256 arrivals)
+  uint64_t* pv_done = bars + 15;    // PV(g) complete
+  uint64_t* o_full = bars + 16;     // item n: O complete
+  uint64_t* o_free = bars + 17;     // item n: O read out by the epilogue (256 arrivals)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 257);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 256);
+    mbar_init(p_ready, 256);
+    mbar_init(pv_done, 1);
+    mbar_init(o_full, 1);
+    mbar_init(o_free, 256);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmQKV);
+  }
+  if (warp == 2) tmem_alloc<256>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer: runs ahead across items
+    int g = 0, n = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      Fwd5Item it;
+      if (!fwd5_item(w, nqt, H, cu_seqlens, it)) continue;
+      const int col_q = (0 * H + it.head) * kDh, col_k = (1 * H + it.head) * kDh, col_v = (2 * H + it.head) * kDh;
+      const int qb = n & 1;
+      mbar_wait(&q_empty[qb], ((n >> 1) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&q_full[qb], Fwd5Smem::kTile);
+        tma_load_2d(smem + Fwd5Smem::kQ + qb * Fwd5Smem::kTile, &tmQKV, &q_full[qb], col_q, it.seq_begin + it.q0);
+      }
+      __syncwarp();
+      for (int j = 0; j < it.nk; ++j, ++g) {
+        const int st = g & 1;
+        const uint32_t ph = (g >> 1) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&k_full[st], Fwd5Smem::kTile);
+          tma_load_2d(smem + Fwd5Smem::kK + st * Fwd5Smem::kTile, &tmQKV, &k_full[st], col_k, it.seq_begin + j * 128);
+        }
+        __syncwarp();
+        mbar_wait(&v_empty[st], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&v_full[st], Fwd5Smem::kTile);
+          tma_load_2d(smem + Fwd5Smem::kV + st * Fwd5Smem::kTile, &tmQKV, &v_full[st], col_v, it.seq_begin + j * 128);
+        }
+        __syncwarp();
+      }
+      ++n;
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer: one flat sequence of key tiles
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);  // S = Q K^T (128 keys): both K-major
+    constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);   // O += P V: A (P) from TMEM, B (V) MN-major
+    const uint64_t qd = make_smem_desc_sw128(smem_u32(smem + Fwd5Smem::kQ), 0, 1024);
+    const uint64_t kd = make_smem_desc_sw128(smem_u32(smem + Fwd5Smem::kK), 0, 1024);
+    const uint64_t vd = make_smem_desc_sw128(smem_u32(smem + Fwd5Smem::kV), 8192, 1024);
+    auto issue_s = [&](const int qb, const int st) {  // S(next tile) from Q buffer qb and key stage st
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_f16_ss(tmem_base, qd + (uint64_t)((qb * Fwd5Smem::kTile + kk * 32) >> 4),
+                      kd + (uint64_t)((st * Fwd5Smem::kTile + kk * 32) >> 4), idesc_s, kk > 0 ? 1u : 0u);
+        umma_commit(s_full);
+        umma_commit(&k_empty[st]);
+      }
+      __syncwarp();
+    };
+    // cursor over the valid items of this CTA: (w, nk) of the current item and of the next one
+    int w_cur = blockIdx.x, nk_cur = 0;
+    {
+      Fwd5Item it;
+      while (w_cur < n_items && !fwd5_item(w_cur, nqt, H, cu_seqlens, it)) w_cur += gridDim.x;
+      nk_cur = it.nk;
+    }
+    if (w_cur < n_items) {
+      int g = 0, n = 0;
+      mbar_wait(&q_full[0], 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      while (w_cur < n_items) {
+        int w_nxt = w_cur + gridDim.x, nk_nxt = 0;
+        {
+          Fwd5Item it;
+          while (w_nxt < n_items && !fwd5_item(w_nxt, nqt, H, cu_seqlens, it)) w_nxt += gridDim.x;
+          nk_nxt = it.nk;
+        }
+        for (int j = 0; j < nk_cur; ++j, ++g) {
+          const bool last = j == nk_cur - 1;
+          const bool has_next = !last || w_nxt < n_items;
+          if (has_next) {  // S(g+1) as soon as the score columns have been read out: it runs under softmax(g)
+            const int qb = last ? ((n + 1) & 1) : (n & 1);
+            mbar_wait(s_free, g & 1);
+            if (last) mbar_wait(&q_full[qb], ((n + 1) >> 1) & 1);
+            mbar_wait(&k_full[(g + 1) & 1], ((g + 1) >> 1) & 1);
+            tc_fence_after();
+            issue_s(qb, (g + 1) & 1);
+          }
+          if (last) {  // every S of item n has been issued: its Q buffer is free once they complete (+ the epilogue's copy-out)
+            if (elect_one()) umma_commit(&q_empty[n & 1]);
+            __syncwarp();
+          }
+          mbar_wait(&v_full[g & 1], (g >> 1) & 1);
+          mbar_wait(p_ready, g & 1);
+          if (j == 0 && n > 0) mbar_wait(o_free, (n - 1) & 1);  // the previous item's O has been read out
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              umma_f16_ts(tmem_base + 128, tmem_base + 192 + kk * 8,
+                          vd + (uint64_t)(((g & 1) * Fwd5Smem::kTile + kk * 2048) >> 4), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+            umma_commit(&v_empty[g & 1]);
+            umma_commit(pv_done);
+            if (last) umma_commit(o_full);
+          }
+          __syncwarp();
+        }
+        ++n;
+        w_cur = w_nxt;
+        nk_cur = nk_nxt;
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- softmax + epilogue: two threads per query row
+    const int ew = warp & 3;
+    const int grp = (warp - 4) >> 2;             // key columns [grp*64, +64) of each tile; O columns [grp*32, +32)
+    const int r = ew * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(ew * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_base + grp * 64;
+    const uint32_t t_o = tmem_base + lane_base + 128 + grp * 32;
+    const uint32_t t_p = tmem_base + lane_base + 192 + grp * 32;
+    __nv_bfloat16* smax = reinterpret_cast<__nv_bfloat16*>(smem + Fwd5Smem::kX);  // [2 parities][2 groups][128 rows]
+    float* lsum = reinterpret_cast<float*>(smem + Fwd5Smem::kX);
+    const float2 sc2 = make_float2(scale2, scale2);
+    int g = 0, n = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      Fwd5Item it;
+      if (!fwd5_item(w, nqt, H, cu_seqlens, it)) continue;
+      const int len = it.len, q0 = it.q0, head = it.head, seq_begin = it.seq_begin;
+      const int q_row = q0 + r;
+      float m_run = -INFINITY, l_run = 0.f;        // l_run: this thread's 64-column share of the row sum
+      for (int j = 0; j < it.nk; ++j, ++g) {
+        mbar_wait(s_full, g & 1);
+        tc_fence_after();
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32(t_s, va);
+        tmem_ld_32x32(t_s + 32, vb);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(s_free);                       // this thread's scores are in registers
+        const int kv_valid = min(128, len - j * 128) - grp * 64;
+        if (kv_valid < 64) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (i >= kv_valid) va[i] = 0xff800000u;       // -inf: never the maximum, exp2 -> 0
+            if (32 + i >= kv_valid) vb[i] = 0xff800000u;
+          }
+        }
+        float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          a0 = fmax3(a0, __uint_as_float(va[i]), __uint_as_float(va[i + 1]));
+          a1 = fmax3(a1, __uint_as_float(va[i + 2]), __uint_as_float(va[i + 3]));
+          a2 = fmax3(a2, __uint_as_float(va[i + 4]), __uint_as_float(va[i + 5]));
+          a3 = fmax3(a3, __uint_as_float(va[i + 6]), __uint_as_float(va[i + 7]));
+          a0 = fmax3(a0, __uint_as_float(vb[i]), __uint_as_float(vb[i + 1]));
+          a1 = fmax3(a1, __uint_as_float(vb[i + 2]), __uint_as_float(vb[i + 3]));
+          a2 = fmax3(a2, __uint_as_float(vb[i + 4]), __uint_as_float(vb[i + 5]));
+          a3 = fmax3(a3, __uint_as_float(vb[i + 6]), __uint_as_float(vb[i + 7]));
+        }
+        const float mx = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+        const __nv_bfloat16 mine = __float2bfloat16_ru(mx * scale2);
+        __nv_bfloat16* xm = smax + (g & 1) * 256;
+        xm[grp * 128 + r] = mine;
+        named_bar_sync(2, 256);
+        const float m_c = fmaxf(__bfloat162float(mine), __bfloat162float(xm[(grp ^ 1) * 128 + r]));
+        const bool raise = m_c > m_run + 8.f;      // always true on an item's first tile (m_run = -inf); same in both threads
+        float alpha = 1.f;
+        if (raise) {
+          alpha = fast_exp2(m_run - m_c);          // 0 on the first tile
+          m_run = m_c;
+        }
+        const float2 nm2 = make_float2(-m_run, -m_run);
+        float2 rs0 = make_float2(0.f, 0.f), rs1 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          uint32_t pp[16];
+#pragma unroll
+          for (int t = 0; t < 16; t += 2) {
+            const uint32_t* v0 = (b == 0) ? &va[2 * t] : &vb[2 * t];
+            float2 x0 = ffma2(make_float2(__uint_as_float(v0[0]), __uint_as_float(v0[1])), sc2, nm2);
+            float2 x1 = ffma2(make_float2(__uint_as_float(v0[2]), __uint_as_float(v0[3])), sc2, nm2);
+            x0 = make_float2(fast_exp2(x0.x), fast_exp2(x0.y));
+            x1 = make_float2(fast_exp2(x1.x), fast_exp2(x1.y));
+            rs0 = fadd2(rs0, x0);
+            rs1 = fadd2(rs1, x1);
+            pp[t] = pack_bf16x2(x0.x, x0.y);
+            pp[t + 1] = pack_bf16x2(x1.x, x1.y);
+          }
+          if (b == 0 && g > 0) {  // PV(g-1) (possibly the previous item's last) has finished reading the P columns
+            mbar_wait_quiet(pv_done, (g - 1) & 1);
+            tc_fence_after();
+          }
+          tmem_st_32x16(t_p + b * 16, pp);
+        }
+        l_run = l_run * alpha + ((rs0.x + rs0.y) + (rs1.x + rs1.y));
+        // rescale this thread's 32 output columns only if some row of the warp raised its maximum (never on the first tile:
+        // its PV starts a fresh accumulator)
+        if (j > 0 && __any_sync(0xffffffffu, raise)) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_o, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          tmem_st_32x32(t_o, v);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(p_ready);
+      }
+      // ---- epilogue of item n: read O out (frees the accumulator), O / l -> bf16 -> the item's own (dead) Q buffer -> global
+      mbar_wait(o_full, n & 1);
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld_32x32(t_o, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(o_free);
+      named_bar_sync(2, 256);                      // every thread is past its last exchange read of this item
+      lsum[grp * 128 + r] = l_run;
+      named_bar_sync(2, 256);
+      const float l_tot = l_run + lsum[(grp ^ 1) * 128 + r];
+      const float inv_l = 1.f / l_tot;
+      const bool row_ok = q_row < len;
+      uint8_t* stg = smem + Fwd5Smem::kQ + (n & 1) * Fwd5Smem::kTile;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 wv;
+        wv.x = pack_bf16x2(__uint_as_float(v[8 * q + 0]) * inv_l, __uint_as_float(v[8 * q + 1]) * inv_l);
+        wv.y = pack_bf16x2(__uint_as_float(v[8 * q + 2]) * inv_l, __uint_as_float(v[8 * q + 3]) * inv_l);
+        wv.z = pack_bf16x2(__uint_as_float(v[8 * q + 4]) * inv_l, __uint_as_float(v[8 * q + 5]) * inv_l);
+        wv.w = pack_bf16x2(__uint_as_float(v[8 * q + 6]) * inv_l, __uint_as_float(v[8 * q + 7]) * inv_l);
+        *reinterpret_cast<uint4*>(stg + r * 128 + (((grp * 4 + q) ^ (r & 7)) << 4)) = wv;
+      }
+      named_bar_sync(2, 256);                      // (also orders the next item's first exchange write behind the lsum reads)
+      {
+        const int tid = threadIdx.x - 128;
+        const int rows_ok = min(128, len - q0);
+        uint8_t* obase = reinterpret_cast<uint8_t*>(out + ((size_t)(seq_begin + q0) * H + head) * kDh);
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const int idx = i4 * 256 + tid, row = idx >> 3, ch = idx & 7;
+          if (row < rows_ok)
+            *reinterpret_cast<uint4*>(obase + (size_t)row * H * kDh * 2 + ch * 16) =
+                *reinterpret_cast<const uint4*>(stg + row * 128 + ((ch ^ (row & 7)) << 4));
+        }
+      }
+      fence_proxy_async_smem();                    // the staging reads precede the TMA write that refills this Q buffer
+      mbar_arrive(&q_empty[n & 1]);
+      if (row_ok && grp == 0) lse[(size_t)head * T + seq_begin + q_row] = (m_run + log2f(l_tot)) * kLn2;
+      ++n;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+

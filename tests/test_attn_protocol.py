@@ -17,7 +17,7 @@ def test_protocol_terminates_without_hazards(name):
 
 
 @pytest.mark.parametrize("name,bug", [("attn_fwd3_kernel", "no_s_free"), ("attn_fwd4_kernel", "no_s_free"),
-                                      ("attn_fwd4_kernel", "no_pv_done"), ("attn_bwd2_kernel", "no_dq_full_wait"),
+                                      ("attn_fwd4_kernel", "no_pv_done"), ("attn_fwd5_kernel", "no_q_full"), ("attn_bwd2_kernel", "no_dq_full_wait"),
                                       ("attn_bwd3_kernel", "no_dq_full_wait")])
 def test_model_catches_a_removed_wait(name, bug):
     caught = 0
