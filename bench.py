@@ -10,10 +10,13 @@ documents, the fused InfoNCE loss + its embedding gradients (bf16 all-gather / r
 re-forward + backward of both towers (shared weights), gradient all-reduce, global-norm clip + AdamW.  The global batch
 is fixed, so N GPUs each take 16384/N pairs ("scaling": "strong").  Synthetic token ids, random-init weights.
 
-Printed JSON (rank 0): value = whole-job pairs/s with inputs resident in HBM; e2e = the same step through the public
+Printed JSON (rank 0): value = whole-job pairs/s with inputs resident in HBM; e2e = the same K steps through the public
 API from pinned HOST buffers (H2D copies + a D2H read of the loss inside the timed region); roofline = the dominant
-kernel (tcgen05 GEMM) timed live with CUDA events on the launching stream, against MEASURED_PEAKS.json;
-cpu_baseline = the oracle port of the reference step on this box's host cores over a bounded sample.
+kernel (tcgen05 GEMM) timed live with CUDA events on the launching stream (1 launch in 17: coprime with the 16 GEMMs of
+a layer), against MEASURED_PEAKS.json; comm_ms = device time of every collective of a step; selfcheck = the loss of the
+first 64 pairs at step 0 against the CPU oracle; gpu_baseline = the UNMODIFIED reference (its pure-PyTorch NomicBertModel
++ its grad_cache_loss, from baseline/_ref) on the same B200 under bf16 autocast over a bounded sample; cpu_baseline = the
+same reference code on this box's host cores (median of 3 after a warm-up).
 """
 from __future__ import annotations
 
@@ -24,7 +27,9 @@ import subprocess
 import sys
 import threading
 import time
+import warnings
 
+warnings.filterwarnings("ignore", message=".*Disabling autocast.*")  # the reference's hard-coded cuda autocast on the CPU arm
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -32,6 +37,7 @@ GLOBAL_BATCH = 16384
 SEQ_LEN = 512
 CHUNK = 64
 LOGIT_SCALE = 50.0
+SELFCHECK_PAIRS = 64
 LR, WD, CLIP = 2.0e-4, 0.01, 1.0
 METRIC = "pairs/sec at global_bs=16384 (nomic-bert-base text-text InfoNCE, bf16, seq=512, GradCache)"
 WORKLOAD = "configs[1]: nomic-bert-base text-text InfoNCE bf16 seq=512 global_bs=16384 GradCache chunk=64"
@@ -108,31 +114,10 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------------- reference arm (CPU)
-def cpu_step_sample(n_pairs, seq, threads):
-    """The oracle port of one reference training step on a bounded sample (``n_pairs`` pairs x ``seq`` tokens): both tower
-    passes of nomic-bert-base, mean pool, normalize, clip_loss forward + backward (fp32, torch CPU kernels)."""
-    import numpy as np
-    import torch
-    from oracle import infonce as O
-    from oracle.encoder import EncoderConfig, biencoder_forward, random_state_dict
-    torch.set_num_threads(threads)
-    cfg = EncoderConfig()
-    sd = {k: v.requires_grad_() for k, v in random_state_dict(cfg, seed=0, ln_jitter=0.0).items()}
-    g = torch.Generator().manual_seed(42)
-    q_ids = torch.randint(0, 30000, (n_pairs, seq), generator=g)
-    d_ids = torch.randint(0, 30000, (n_pairs, seq), generator=g)
-    mask = torch.ones(n_pairs, seq, dtype=torch.long)
-    t0 = time.perf_counter()
-    q = biencoder_forward(sd, cfg, q_ids, mask)
-    d = biencoder_forward(sd, cfg, d_ids, mask)
-    o = O.clip_loss_fwd_bwd(q.detach().numpy(), d.detach().numpy(), LOGIT_SCALE)
-    torch.autograd.backward([q, d], [torch.from_numpy(o["dq"]).float(), torch.from_numpy(o["dd"]).float()])
-    dt = time.perf_counter() - t0
-    return dt, float(o["loss"])
-
-
-CPU_SAMPLE_PAIRS = 2
+# ------------------------------------------------------------------------------------------------- reference arms
+CPU_SAMPLE_PAIRS = 4   # per CPU step: 4 pairs x 512 tokens through the full GradCache step (chunk 2)
+CPU_CHUNK = 2
+GPU_BASE_CHUNKS = 8    # gpu_baseline: 8 chunks x 64 pairs x 512 tokens per tower per step
 
 
 def cpu_threads():
@@ -141,29 +126,180 @@ def cpu_threads():
     return min(os.cpu_count() or 1, 32)
 
 
+def _ensure_group(backend):
+    import torch.distributed as dist
+    if dist.is_initialized():
+        return False
+    import socket
+    with socket.socket() as sk:  # a private 1-rank group on a free port (never the torchrun rendezvous store)
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    dist.init_process_group(backend, init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    return True
+
+
+class ReferenceStep:
+    """One training step of the reference's own code on ``device``: its pure-PyTorch NomicBertModel (modeling_hf_nomic_bert.py:
+    1650) in a mean-pool + normalize tower, its ``grad_cache_loss`` (loss.py:187-213; bf16 autocast on CUDA, fp32 on the
+    host), ``clip_grad_norm_`` + ``torch.optim.AdamW`` + ``zero_grad(set_to_none=True)`` as trainers/base.py:366-393.  Falls back
+    to the oracle port of the same step when neither /root/reference nor baseline/_ref is present (``kind`` says which)."""
+
+    def __init__(self, device, n_pairs, chunk):
+        import torch
+        from oracle import ref_loader
+        self.torch, self.device, self.n_pairs, self.chunk = torch, device, n_pairs, chunk
+        g = torch.Generator().manual_seed(42)
+        self.q = torch.randint(0, 30000, (n_pairs, SEQ_LEN), generator=g).to(device)
+        self.d = torch.randint(0, 30000, (n_pairs, SEQ_LEN), generator=g).to(device)
+        self.mask = torch.ones(n_pairs, SEQ_LEN, dtype=torch.long, device=device)
+        if ref_loader.available():
+            from oracle import ref_tower
+            self.kind = "reference"
+            torch.manual_seed(0)
+            self.ref, self.model = ref_tower.build(device)
+            self.model.train()
+            self.scale = ref_tower.LogitScale(LOGIT_SCALE).to(device)
+            self.opt = torch.optim.AdamW(self.model.parameters(), lr=LR, weight_decay=WD)
+            self.source = ref_loader.source()
+        else:
+            from oracle.encoder import EncoderConfig, random_state_dict
+            self.kind = "port"
+            self.cfg = EncoderConfig()
+            self.sd = {k: v.to(device).requires_grad_() for k, v in random_state_dict(self.cfg, seed=0, ln_jitter=0.0).items()}
+            self.opt = torch.optim.AdamW(list(self.sd.values()), lr=LR, weight_decay=WD)
+            self.source = "oracle port"
+
+    def step(self):
+        torch = self.torch
+        if self.kind == "reference":
+            loss = self.ref.loss.grad_cache_loss(self.model, {"input_ids": self.q, "attention_mask": self.mask}, self.model,
+                                                 {"input_ids": self.d, "attention_mask": self.mask}, self.chunk, self.scale)
+            torch.nn.utils.clip_grad_norm_(self.model.parameters(), CLIP)
+        else:
+            from oracle import infonce as O
+            from oracle.encoder import biencoder_forward
+            q = biencoder_forward(self.sd, self.cfg, self.q, self.mask)
+            d = biencoder_forward(self.sd, self.cfg, self.d, self.mask)
+            o = O.clip_loss_fwd_bwd(q.detach().cpu().numpy(), d.detach().cpu().numpy(), LOGIT_SCALE)
+            torch.autograd.backward([q, d], [torch.from_numpy(o["dq"]).float().to(q.device), torch.from_numpy(o["dd"]).float().to(d.device)])
+            torch.nn.utils.clip_grad_norm_(list(self.sd.values()), CLIP)
+            loss = torch.tensor(o["loss"])
+        self.opt.step()
+        self.opt.zero_grad(set_to_none=True)
+        return float(loss)
+
+    def describe(self, where):
+        what = ("the reference's HF NomicBertModel + grad_cache_loss + AdamW (" + self.source + ")") if self.kind == "reference" \
+            else "oracle port of the step (reference package not present)"
+        return f"{self.n_pairs} pairs x seq {SEQ_LEN} per step, GradCache chunk {self.chunk}, {where}: {what}"
+
+
+def cpu_baseline(threads, steps=3, warmup=1):
+    """(pairs/s median over ``steps`` after ``warmup``, per-step seconds, kind, sample description, last loss)."""
+    import torch
+    torch.set_num_threads(threads)
+    created = _ensure_group("gloo")
+    try:
+        ref = ReferenceStep(torch.device("cpu"), CPU_SAMPLE_PAIRS, CPU_CHUNK)
+        for _ in range(warmup):
+            ref.step()
+        times, loss = [], None
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            loss = ref.step()
+            times.append(time.perf_counter() - t0)
+    finally:
+        if created:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+    med = sorted(times)[len(times) // 2]
+    return CPU_SAMPLE_PAIRS / med, times, ref.kind, ref.describe(f"fp32 on {threads} host threads"), loss
+
+
+def gpu_baseline(dev, steps=3, warmup=1):
+    """The reference code on the same B200: bf16 autocast (loss.py:139,156,175), its own kernels (torch SDPA / cuBLAS / ATen).
+    Needs an initialised process group (clip_loss calls dist.get_world_size()); the caller's NCCL group is used."""
+    import torch
+    n_pairs = GPU_BASE_CHUNKS * CHUNK
+    ref = ReferenceStep(dev, n_pairs, CHUNK)
+    for _ in range(warmup):
+        ref.step()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    loss = None
+    for _ in range(steps):
+        loss = ref.step()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / steps
+    out = {"value": n_pairs / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "steps": steps, "warmup": warmup, "kind": ref.kind,
+           "dtype": "bf16 autocast, fp32 master weights", "loss": loss,
+           "sample": ref.describe("on cuda:%d (1 GPU; data-parallel replicas scale it by N)" % dev.index)}
+    del ref
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = cpu_threads()
-    n_pairs = CPU_SAMPLE_PAIRS
-    for _ in range(min(args.warmup, 1)):  # CPU warm-up: one bounded sample is plenty
-        cpu_step_sample(1, SEQ_LEN, threads)
+    import torch
+    torch.set_num_threads(threads)
+    created = _ensure_group("gloo")
+    ref = ReferenceStep(torch.device("cpu"), CPU_SAMPLE_PAIRS, CPU_CHUNK)
+    for _ in range(max(1, min(args.warmup, 2))):  # CPU warm-up: thread pool + allocator; two bounded samples are plenty
+        ref.step()
     times = []
     for _ in range(args.steps):
-        dt, _ = cpu_step_sample(n_pairs, SEQ_LEN, threads)
-        times.append(dt)
+        t0 = time.perf_counter()
+        ref.step()
+        times.append(time.perf_counter() - t0)
+    if created:
+        import torch.distributed as dist
+        dist.destroy_process_group()
     total = sum(times)
-    value = n_pairs * len(times) / total
-    sample = f"{n_pairs} pairs x seq {SEQ_LEN} per step (fwd+bwd of both towers + InfoNCE), oracle port, fp32 torch CPU kernels"
+    value = CPU_SAMPLE_PAIRS * len(times) / total
+    sample = ref.describe(f"fp32 on {threads} host threads")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": GLOBAL_BATCH, "seq_len": SEQ_LEN, "parallelism": "cpu"},
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": ref.kind, "sample": sample,
+                         "median_pairs_per_s": CPU_SAMPLE_PAIRS / sorted(times)[len(times) // 2]},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def oracle_selfcheck(model, logit_scale, q_ids, d_ids):
+    """Loss of the first ``n`` pairs through the product path (GradCache forward only: no-grad chunked embeddings + fused
+    InfoNCE) against the CPU oracle on the same weights: the bench checks its own arithmetic before it times anything."""
+    import torch
+    import contrastors_b200 as cb
+    from oracle import infonce as O
+    from oracle.encoder import EncoderConfig, biencoder_forward
+    n = q_ids.shape[0]
+    with torch.no_grad():
+        eq = model(q_ids, seq_lens=torch.full((n,), SEQ_LEN))["embedding"]
+        ed = model(d_ids, seq_lens=torch.full((n,), SEQ_LEN))["embedding"]
+        got = float(cb.clip_loss(eq, ed, logit_scale).item())
+        sd = {k[len("trunk."):]: v.detach().float().cpu() for k, v in model.state_dict().items()}
+        cfg = EncoderConfig()
+        t0 = time.perf_counter()
+        oq = biencoder_forward(sd, cfg, q_ids.cpu(), None).numpy()
+        od = biencoder_forward(sd, cfg, d_ids.cpu(), None).numpy()
+        want = float(O.clip_loss_fwd_bwd(oq, od, LOGIT_SCALE)["loss"])
+        emb_err = float(max(abs(eq.cpu().numpy() - oq).max(), abs(ed.cpu().numpy() - od).max()))
+    rel = abs(got - want) / max(abs(want), 1e-6)
+    out = {"pairs": n, "loss": got, "oracle_loss": want, "rel_err": rel, "max_abs_embedding_err": emb_err, "tolerance": 2e-2,
+           "ok": bool(rel <= 2e-2), "oracle_seconds": time.perf_counter() - t0,
+           "note": "fp32 CPU oracle vs bf16 tower at random init (logits ~ scale * cos ~ 50 * O(1)): bf16-level agreement"}
+    if not out["ok"]:
+        raise SystemExit(f"bench self-check FAILED: loss {got} vs oracle {want} on the first {n} pairs")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------- our arm (GPU)
@@ -225,6 +361,10 @@ def run_ours(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
+    selfcheck = None
+    if rank == 0 and not args.no_selfcheck:
+        selfcheck = oracle_selfcheck(model, logit_scale, resident["query_input_ids"][:SELFCHECK_PAIRS],
+                                     resident["document_input_ids"][:SELFCHECK_PAIRS])
     for _ in range(args.warmup):
         train_step(resident)
     torch.cuda.synchronize()
@@ -235,9 +375,20 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     launches0 = _lib.launch_count()
-    ops.TIMER = ops.KernelTimer(sample_every=16)
-    ms_dev = timed(lambda: train_step(resident), args.steps)
+    from contrastors_b200 import distributed as cxd
+    ops.TIMER = ops.KernelTimer(sample_every=17)  # coprime with the 16 GEMMs of a layer: every GEMM shape gets sampled
+    cxd.COMM_EVENTS = []
+    host_t0 = time.perf_counter()
+    host_enqueue = [0.0]
+
+    def timed_step():
+        t0 = time.perf_counter()
+        train_step(resident)
+        host_enqueue[0] += time.perf_counter() - t0
+
+    ms_dev = timed(timed_step, args.steps)
     timer, ops.TIMER = ops.TIMER, None
+    comm_events, cxd.COMM_EVENTS = cxd.COMM_EVENTS, None
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
 
@@ -248,8 +399,13 @@ def run_ours(args):
         batch = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
         losses.append(train_step(batch).item())
 
-    e2e_steps = max(1, min(args.steps, 2))
+    e2e_steps = args.steps
     ms_e2e = timed(e2e_step, e2e_steps)
+    comm = {}
+    for kind, a, b in comm_events:
+        c = comm.setdefault(kind, [0, 0.0])
+        c[0] += 1
+        c[1] += a.elapsed_time(b)
 
     if rank != 0:
         dist.destroy_process_group()
@@ -279,10 +435,24 @@ def run_ours(args):
             extra["infonce"] = {"achieved_tflops": tf, "frac": tf / pk["tflops_burst"], "peak": pk["tflops_burst"],
                                 "note": "6*N*M*D algorithmic FLOPs / (fwd+bwd time); burst peak (kernel timed alone)"}
         roof["other_kernels"] = extra
-    # CPU baseline: bounded sample of the same step on the host cores (oracle port)
+    # the model, optimizer state and activations of our arm are no longer needed: free them before the baselines run
+    del model
+    torch.cuda.empty_cache()
+    dist.destroy_process_group()
+    gpu_base = None
+    if not args.no_gpu_baseline:
+        created = _ensure_group("gloo")  # the reference's clip_loss asks for a process group; 1 rank: its gather is the identity
+        try:
+            gpu_base = gpu_baseline(dev)
+        except Exception as ex:  # the baseline must never take the bench line down with it
+            gpu_base = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
+        if created:
+            dist.destroy_process_group()
+    # CPU baseline: the reference's own step on the host cores, bounded sample, median of 3 after a warm-up
     threads = cpu_threads()
-    cpu_pairs = CPU_SAMPLE_PAIRS
-    cpu_dt, _ = cpu_step_sample(cpu_pairs, SEQ_LEN, threads)
+    cpu_value, cpu_times, cpu_kind, cpu_sample, _ = cpu_baseline(threads)
+    comm_ms = {k: {"calls_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps} for k, v in comm.items()}
+    comm_total = sum(v["ms_per_step"] for v in comm_ms.values())
     out = {
         "metric": METRIC, "value": GLOBAL_BATCH * args.steps / (ms_dev * 1e-3), "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
@@ -294,12 +464,17 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
-        "cpu_baseline": {"value": cpu_pairs / cpu_dt, "unit": "pairs/s", "cores": threads, "kind": "port",
-                         "sample": f"{cpu_pairs} pairs x seq {SEQ_LEN}: fwd+bwd of both towers + InfoNCE, oracle port (fp32 torch CPU kernels)"},
+        "comm_ms": {"total_per_step": comm_total, "share_of_step": comm_total / (ms_dev / args.steps), "by_kind": comm_ms,
+                    "note": "device time of rank 0's collectives (CUDA events on the stream each is launched on; the chunk gathers and "
+                            "the gradient buckets run on side streams under compute, so this is occupancy, not exposed time)"},
+        "host_enqueue_ms_per_step": 1000.0 * host_enqueue[0] / args.steps,
+        "selfcheck": selfcheck,
+        "gpu_baseline": gpu_base,
+        "cpu_baseline": {"value": cpu_value, "unit": "pairs/s", "cores": threads, "kind": cpu_kind, "sample": cpu_sample,
+                         "step_seconds": cpu_times, "stat": "median of 3 after 1 warm-up"},
         "loss": losses[-1] if losses else None,
     }
     print(json.dumps(out))
-    dist.destroy_process_group()
 
 
 def main():
@@ -308,6 +483,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-selfcheck", action="store_true", help="skip the step-0 loss check against the CPU oracle")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference-on-the-same-GPU leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -160,14 +160,16 @@ def load_logit_scale(logit_scale: LogitScale, model_dir: str) -> bool:
 def save_state(output_dir: str, model: BiEncoder, logit_scale: Optional[LogitScale] = None, process_index: int = 0,
                scheduler_state: Optional[dict] = None) -> None:
     """``BaseTrainer.save_state`` (trainers/base.py:316-344): model/, optimizer.pt, scheduler.pt, random_states_{rank}.pt.
-    The optimizer here is the fused AdamW on the flat buffers (``NomicBertModel.fused_adamw_step``): optimizer.pt holds its
-    step count and both moment buffers."""
+    The optimizer here is the fused AdamW on the flat buffers (``FlatParamModule.fused_adamw_step``); optimizer.pt is written
+    as the ``torch.optim.AdamW.state_dict()`` of the optimizer the reference's ``configure_optimizer`` builds for the same
+    tower (integer ids, decay / no-decay ``param_groups``), so ``optimizer.load_state_dict`` (base.py:300-301) accepts it
+    and a file written by the reference trainer loads here."""
     os.makedirs(output_dir, exist_ok=True)
     if process_index == 0:
         save_pretrained(model, os.path.join(output_dir, "model"))
         if logit_scale is not None:
             save_logit_scale(logit_scale, os.path.join(output_dir, "model"))
-        torch.save(model.trunk.optimizer_state_dict(), os.path.join(output_dir, "optimizer.pt"))
+        torch.save(model.trunk.optimizer_state_dict(prefix="trunk."), os.path.join(output_dir, "optimizer.pt"))
         torch.save(scheduler_state or {}, os.path.join(output_dir, "scheduler.pt"))
     states = {"torch": torch.get_rng_state(), "numpy": np.random.get_state(), "random": random.getstate(),
               "cuda": torch.cuda.get_rng_state_all() if torch.cuda.is_available() else []}
@@ -179,7 +181,8 @@ def load_state(input_dir: str, model: BiEncoder, logit_scale: Optional[LogitScal
     load_weights(model, read_state_dict(os.path.join(input_dir, "model")))
     if logit_scale is not None:
         load_logit_scale(logit_scale, os.path.join(input_dir, "model"))
-    model.trunk.load_optimizer_state_dict(torch.load(os.path.join(input_dir, "optimizer.pt"), map_location="cpu", weights_only=True))
+    model.trunk.load_optimizer_state_dict(torch.load(os.path.join(input_dir, "optimizer.pt"), map_location="cpu", weights_only=True),
+                                          prefix="trunk.")
     sched = torch.load(os.path.join(input_dir, "scheduler.pt"), map_location="cpu", weights_only=True)
     states = torch.load(os.path.join(input_dir, f"random_states_{process_index}.pt"), map_location="cpu", weights_only=False)
     torch.set_rng_state(states["torch"])

@@ -12,6 +12,24 @@ import torch
 import torch.distributed as dist
 
 
+# bench.py sets this to a list to collect (kind, start_event, end_event) around every collective of the path, recorded on
+# the stream the collective is launched on (``comm_ms`` of the bench line); None = no events, no overhead
+COMM_EVENTS = None
+
+
+def _timed(kind, fn):
+    from . import distributed as _self  # the list is swapped at run time: always read the module attribute
+    ev = _self.COMM_EVENTS
+    if ev is None or not torch.cuda.is_available():
+        return fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    out = fn()
+    b.record()
+    ev.append((kind, a, b))
+    return out
+
+
 def _ws():
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
@@ -27,7 +45,7 @@ def all_gather_rows(t: torch.Tensor) -> torch.Tensor:
         return t
     t = t.contiguous()
     out = torch.empty((ws * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-    dist.all_gather_into_tensor(out, t)
+    _timed("allgather", lambda: dist.all_gather_into_tensor(out, t))
     return out
 
 
@@ -40,7 +58,7 @@ def reduce_scatter_rows(full: torch.Tensor) -> torch.Tensor:
     n = full.shape[0] // ws
     if dist.get_backend() == "nccl":
         out = torch.empty((n,) + tuple(full.shape[1:]), dtype=full.dtype, device=full.device)
-        dist.reduce_scatter_tensor(out, full, op=dist.ReduceOp.SUM)
+        _timed("reduce_scatter", lambda: dist.reduce_scatter_tensor(out, full, op=dist.ReduceOp.SUM))
         return out
     full = full.clone()
     dist.all_reduce(full, op=dist.ReduceOp.SUM)

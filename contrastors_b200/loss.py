@@ -22,7 +22,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops
-from .distributed import _rank, all_gather_rows, gather_with_grad, reduce_scatter_rows  # noqa: F401
+from .distributed import _rank, _timed, all_gather_rows, gather_with_grad, reduce_scatter_rows  # noqa: F401
 from .rand_state import RandContext
 
 
@@ -323,7 +323,7 @@ def _chunked_embeddings_with_gather(model, chunks, n_local):
             outs = [gathered[r * n_local + row: r * n_local + row + b] for r in range(ws)]
             with torch.cuda.stream(comm):
                 comm.wait_event(ready)
-                dist.all_gather(outs, mine)
+                _timed("allgather_chunk", lambda: dist.all_gather(outs, mine))
             row += b
     if streams:
         for s in streams:
@@ -332,9 +332,10 @@ def _chunked_embeddings_with_gather(model, chunks, n_local):
     return torch.concat(embeddings, dim=0), rand_states, gathered
 
 
-def accumulate_gradients(model, inputs, cache, rand_states, router_aux_coeff):
+def accumulate_gradients(model, inputs, cache, rand_states, router_aux_coeff, _grad_reducer=None):
     """Pass 2 of GradCache (reference loss.py:149-161): re-forward each chunk with its RNG replayed and back-propagate
-    <embedding, cached gradient>; DDP gradient sync only on the last chunk."""
+    <embedding, cached gradient>; DDP gradient sync only on the last chunk (``_grad_reducer``: our explicit equivalent, armed
+    right before the last chunk's backward so the bucketed all-reduce runs under it)."""
     length = len(inputs)
     no_sync = getattr(model, "no_sync", nullcontext)
     sync_contexts = [no_sync] * (length - 1) + [nullcontext]
@@ -352,6 +353,8 @@ def accumulate_gradients(model, inputs, cache, rand_states, router_aux_coeff):
                 surrogate = torch.dot(embedding["embedding"].flatten().float(), grad.flatten().float())
                 if "router_loss" in embedding and embedding["router_loss"] is not None:
                     surrogate = surrogate + embedding["router_loss"] * router_aux_coeff
+                if _grad_reducer is not None and i == length - 1:
+                    _grad_reducer.arm()
                 surrogate.backward()
     if streams:
         for s in streams:
@@ -370,7 +373,7 @@ def cache_loss(tower1, tower2, query_embeddings, document_embeddings, logit_scal
 
 
 def grad_cache_loss(tower1, t1_inputs, tower2, t2_inputs, chunk_size, logit_scale, bidirectional=False,
-                    router_aux_coeff=False):
+                    router_aux_coeff=False, _grad_reducers=None):
     """GradCache step (reference loss.py:187-213): chunked no-grad embeddings for both towers, the loss and its
     embedding gradients, then chunked re-forward/backward per tower; leaves gradients in ``param.grad`` and returns
     the detached loss.  Tower 2 is skipped when it is not training (reference :210)."""
@@ -392,9 +395,16 @@ def grad_cache_loss(tower1, t1_inputs, tower2, t2_inputs, chunk_size, logit_scal
     query_cache, document_cache, loss = cache_loss(tower1, tower2, query_embs, document_embs, logit_scale,
                                                    bidirectional=bidirectional, _pregathered=pregathered)
 
+    # explicit gradient reduction (the reference's DDP hooks): a tower's reducer is armed before the step's LAST backward
+    # through that tower's weights -- tower 2's last chunk when both towers share the weights
+    trunk1, trunk2 = getattr(tower1, "trunk", tower1), getattr(tower2, "trunk", tower2)
+    red = _grad_reducers or {}
+    second_pass = bool(tower2.training)
+    r1 = red.get(id(trunk1)) if not (second_pass and trunk1 is trunk2) else None
+    r2 = red.get(id(trunk2)) if second_pass else None
     accumulate_gradients(tower1, chunked_queries, query_cache.split(chunk_size), query_rand_states,
-                         router_aux_coeff=router_aux_coeff)
-    if tower2.training:
+                         router_aux_coeff=router_aux_coeff, _grad_reducer=r1)
+    if second_pass:
         accumulate_gradients(tower2, chunked_documents, document_cache.split(chunk_size), doc_rand_states,
-                             router_aux_coeff=router_aux_coeff)
+                             router_aux_coeff=router_aux_coeff, _grad_reducer=r2)
     return loss

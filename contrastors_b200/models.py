@@ -28,20 +28,7 @@ import torch.nn as nn
 from . import ops
 from .ops import MAJOR_K, MAJOR_MN  # noqa: F401
 
-# Any torch optimizer step may have rewritten the fp32 master weights through the parameter views; a global post-step
-# hook bumps this counter so the bf16 shadow is re-cast before the next forward (our fused AdamW refreshes it itself).
-_OPT_STEPS = [0]
-
-
-def _on_any_optimizer_step(optimizer, args, kwargs):
-    _OPT_STEPS[0] += 1
-
-
-try:
-    from torch.optim.optimizer import register_optimizer_step_post_hook
-    register_optimizer_step_post_hook(_on_any_optimizer_step)
-except Exception:  # pragma: no cover - very old torch
-    pass
+from .flat_params import FlatParamModule, _OPT_STEPS, _attach  # noqa: F401  (re-exported for vit.py / older imports)
 
 
 @dataclass
@@ -90,18 +77,8 @@ def _param_specs(cfg: NomicBertConfig):
     return two_d, one_d
 
 
-def _attach(root: nn.Module, dotted: str, param: nn.Parameter):
-    parts = dotted.split(".")
-    mod = root
-    for name in parts[:-1]:
-        if name not in mod._modules:
-            mod.add_module(name, nn.Module())
-        mod = mod._modules[name]
-    mod.register_parameter(parts[-1], param)
-
-
-class NomicBertModel(nn.Module):
-    """Trunk: ids -> last hidden state over packed tokens.  See module docstring for the layout."""
+class NomicBertModel(FlatParamModule):
+    """Trunk: ids -> last hidden state over packed tokens.  Storage: see ``flat_params.FlatParamModule``."""
 
     def __init__(self, config: NomicBertConfig):
         super().__init__()
@@ -109,50 +86,12 @@ class NomicBertModel(nn.Module):
         assert config.head_dim == 64, "the sm_100a attention kernel is specialised for head_dim 64"
         assert config.n_embd % 64 == 0 and config.n_inner % 64 == 0
         two_d, one_d = _param_specs(config)
-        self._specs = two_d + one_d
-        self._offsets = {}
-        off = 0
-        for name, shape in self._specs:
-            n = math.prod(shape)
-            self._offsets[name] = (off, n, shape)
-            off += (n + 63) // 64 * 64  # keep every tensor 256-byte aligned (TMA bases)
-        self._n_decay = self._offsets[one_d[0][0]][0]
-        self._n_total = off
-        self._flat = torch.zeros(off, dtype=torch.float32)
-        self._flat_grad = torch.zeros(off, dtype=torch.float32)
-        self._shadow = None          # bf16 copy of _flat, refreshed lazily
-        self._shadow_version = None
-        self._master_version = 0     # bumped by everything in this class that rewrites the master weights
         self._rope = None
-        self._opt_state = None
-        for name, shape in self._specs:
-            _attach(self, name, nn.Parameter(torch.empty(0)))
-        self._rebind()
+        self._init_flat(two_d, one_d)
         self.reset_parameters()
 
-    # ---------------------------------------------------------------- flat storage plumbing
-    def _named_leaf(self, dotted):
-        mod = self
-        parts = dotted.split(".")
-        for name in parts[:-1]:
-            mod = mod._modules[name]
-        return mod, parts[-1]
-
-    def _rebind(self):
-        for name, (off, n, shape) in self._offsets.items():
-            mod, leaf = self._named_leaf(name)
-            p = mod._parameters[leaf]
-            p.data = self._flat[off:off + n].view(shape)
-            p.grad = self._flat_grad[off:off + n].view(shape)
-
-    def _apply(self, fn, recurse=True):
-        flat = fn(self._flat)
-        grad = fn(self._flat_grad)
-        self._flat = flat.float() if flat.dtype != torch.float32 else flat  # master weights stay fp32
-        self._flat_grad = grad.float() if grad.dtype != torch.float32 else grad
-        self._shadow, self._shadow_version, self._rope, self._opt_state = None, None, None, None
-        self._rebind()
-        return self
+    def _on_apply(self):
+        self._rope = None
 
     def reset_parameters(self, seed: Optional[int] = None):
         """N(0, initializer_range) for Linear/Embedding, (1, 0) for LayerNorm (modeling_nomic_bert.py:284-292)."""
@@ -168,36 +107,17 @@ class NomicBertModel(nn.Module):
                     v.zero_()
             if self.config.pad_token_id is not None:
                 self.view(self._flat, "embeddings.word_embeddings.weight")[self.config.pad_token_id].zero_()
-        self._master_version = getattr(self, "_master_version", 0) + 1
-
-    def load_reference_state_dict(self, sd, strict=True):
-        """Load a state dict with the reference's key names (NomicBertModel / HF copy)."""
-        missing = [k for k in self._offsets if k not in sd]
-        if strict and missing:
-            raise KeyError(f"missing keys: {missing}")
-        with torch.no_grad():
-            for name, (off, n, shape) in self._offsets.items():
-                if name in sd:
-                    self._flat[off:off + n].copy_(sd[name].reshape(-1).to(self._flat.device, torch.float32))
         self.mark_weights_updated()
 
-    def mark_weights_updated(self):
-        """Call after writing the fp32 master weights by any route other than a torch optimizer / fused_adamw_step."""
-        self._master_version += 1
-
-    def view(self, buf, name):
-        off, n, shape = self._offsets[name]
-        return buf[off:off + n].view(shape)
-
-    def shadow(self):
-        """bf16 weights for the GEMMs; re-cast only when the fp32 master may have changed."""
-        ver = (self._master_version, _OPT_STEPS[0])
-        if self._shadow is None or self._shadow_version != ver:
-            if self._shadow is None:
-                self._shadow = torch.empty(self._n_total, device=self._flat.device, dtype=torch.bfloat16)
-            ops.cast_f32_bf16(self._flat, self._shadow)
-            self._shadow_version = ver
-        return self._shadow
+    def layer_grad_slices(self):
+        """[lo, hi) of each transformer layer's 2-D weights in the flat buffers (contiguous per layer): the buckets of
+        ``parallel.GradientBucketReducer``."""
+        out = []
+        for i in range(self.config.n_layer):
+            lo = self._offsets[f"encoder.layers.{i}.attn.Wqkv.weight"][0]
+            off, n, _ = self._offsets[f"encoder.layers.{i}.mlp.fc2.weight"]
+            out.append((lo, off + (n + 63) // 64 * 64))
+        return out
 
     def rope_tables(self, seqlen):
         if self._rope is None or self._rope[0].shape[0] < seqlen or self._rope[0].device != self._flat.device:
@@ -207,53 +127,6 @@ class NomicBertModel(nn.Module):
             freqs = torch.outer(torch.arange(n, dtype=torch.float32), inv_freq)  # fp32, as embedding.py / HF :1148-1183
             self._rope = (torch.cos(freqs).to(self._flat.device), torch.sin(freqs).to(self._flat.device))
         return self._rope
-
-    # ---------------------------------------------------------------- optimizer tail on the flat buffers
-    def fused_adamw_step(self, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, max_grad_norm=None, grad_scale=1.0):
-        """clip_grad_norm_ + AdamW (decay on >=2-D weights only, optimizer.py:7-47) + zero_grad + bf16 refresh, fused:
-        two launches over the flat buffers, no host sync (the clip coefficient stays on the device)."""
-        if self._opt_state is None:
-            self._opt_state = dict(step=0, m=torch.zeros_like(self._flat), v=torch.zeros_like(self._flat))
-        st = self._opt_state
-        st["step"] += 1
-        coef = None
-        if max_grad_norm is not None and max_grad_norm > 0:
-            coef = ops.grad_clip_coef(self._flat_grad, max_grad_norm)[1:]
-        if self._shadow is None:
-            self._shadow = torch.empty(self._n_total, device=self._flat.device, dtype=torch.bfloat16)
-        nd = self._n_decay
-        for lo, hi, wd in ((0, nd, weight_decay), (nd, self._n_total, 0.0)):
-            ops.adamw_step(self._flat[lo:hi], self._flat_grad[lo:hi], st["m"][lo:hi], st["v"][lo:hi], self._shadow[lo:hi], lr,
-                           betas[0], betas[1], eps, wd, st["step"], grad_scale_dev=coef, grad_scale=grad_scale, zero_grad=True)
-        self._master_version += 1
-        self._shadow_version = (self._master_version, _OPT_STEPS[0])  # the kernel just refreshed the shadow
-
-    def flat_grad(self):
-        return self._flat_grad
-
-    def optimizer_state_dict(self):
-        """State of the fused AdamW in torch.optim.AdamW's terms (``step``, ``exp_avg``, ``exp_avg_sq`` per parameter), keyed by
-        the reference's parameter names so it does not depend on the flat layout (``optimizer.pt``, trainers/base.py:323-324)."""
-        if self._opt_state is None:
-            return {"state": {}, "step": 0}
-        st = self._opt_state
-        state = {name: {"step": st["step"], "exp_avg": self.view(st["m"], name).detach().cpu().clone(),
-                        "exp_avg_sq": self.view(st["v"], name).detach().cpu().clone()} for name in self._offsets}
-        return {"state": state, "step": st["step"]}
-
-    def load_optimizer_state_dict(self, sd):
-        if not sd.get("state"):
-            self._opt_state = None
-            return
-        missing = [k for k in self._offsets if k not in sd["state"]]
-        if missing:
-            raise KeyError(f"optimizer state misses {missing}")
-        m, v = torch.zeros_like(self._flat), torch.zeros_like(self._flat)
-        with torch.no_grad():
-            for name in self._offsets:
-                self.view(m, name).copy_(sd["state"][name]["exp_avg"].to(m.device))
-                self.view(v, name).copy_(sd["state"][name]["exp_avg_sq"].to(v.device))
-        self._opt_state = dict(step=int(sd["step"]), m=m, v=v)
 
     # ---------------------------------------------------------------- forward
     def forward(self, input_ids, attention_mask=None, position_ids=None, token_type_ids=None, seq_lens=None, **kwargs):
@@ -370,6 +243,8 @@ class _TrunkFn(torch.autograd.Function):
     def backward(ctx, g_out):
         model, packed, head = ctx.model, ctx.packed, ctx.head
         cfg = model.config
+        model._ensure_grad_views()
+        reducer = getattr(model, "_bucket_reducer", None)
         W, P, G = model.shadow(), model._flat, model._flat_grad
         v = model.view
         H, Dh = cfg.n_head, cfg.head_dim
@@ -406,12 +281,16 @@ class _TrunkFn(torch.autograd.Function):
             dqkv = ops.attn_bwd(qkv, attn, dattn, lse, packed.cu, packed.max_seqlen, H, Dh, scale, packed.pos, cos_t, sin_t)
             dh = ops.gemm(dqkv, v(W, p + "attn.Wqkv.weight"), b_major=MAJOR_MN)
             ops.gemm(dqkv, h, a_major=MAJOR_MN, b_major=MAJOR_MN, out=v(G, p + "attn.Wqkv.weight"), accumulate=True)
+            if reducer is not None:
+                reducer.layer_done(i)  # this layer's weight gradients are final: reduce them under the remaining layers
             g_a, g_b = dz1, dh
         ops.embed_layernorm_bwd(packed.ids, None, v(W, "embeddings.word_embeddings.weight"),
                                 v(W, "embeddings.token_type_embeddings.weight"), g_a, g_b, v(P, "emb_ln.weight"), ctx.st0,
                                 v(G, "embeddings.word_embeddings.weight"), v(G, "embeddings.token_type_embeddings.weight"),
                                 v(G, "emb_ln.weight"), v(G, "emb_ln.bias"),
                                 padding_idx=-1 if cfg.pad_token_id is None else cfg.pad_token_id, p_drop=pdrop, seed=site(0))
+        if reducer is not None:
+            reducer.finish()  # embeddings + every 1-D parameter (the LayerNorm gradients are reduced by a kernel per layer)
         ctx.saved = None
         return None, None, None, None
 

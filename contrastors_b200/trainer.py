@@ -14,7 +14,9 @@ from typing import Optional
 import torch
 
 from .loss import clip_loss, gather_with_grad, grad_cache_loss, matryoshka_clip_loss
-from .parallel import allreduce_gradients
+import torch.distributed as dist
+
+from .parallel import GradientBucketReducer, allreduce_gradients, allreduce_scalar_grads
 
 
 def _split_batch(batch, device):
@@ -50,17 +52,65 @@ def forward_step(model, batch, logit_scale, matryoshka_dims=None, matryoshka_los
     return {"loss": loss}
 
 
+class _ScalarAdamW:
+    """AdamW (weight_decay 0: ``logit_scale`` is in the reference's no-decay group, optimizer.py:22-23) for the 0-dim
+    logit-scale parameter, as a handful of 1-element device ops: no host sync, no torch optimizer object (whose global
+    post-step hook would force a re-cast of the towers' bf16 shadows)."""
+
+    def __init__(self, param):
+        self.p, self.step = param, 0
+        self.m, self.v = torch.zeros_like(param), torch.zeros_like(param)
+
+    @torch.no_grad()
+    def update(self, lr, betas=(0.9, 0.999), eps=1e-8):
+        g = self.p.grad
+        if g is None:
+            return
+        self.step += 1
+        b1, b2 = betas
+        self.m.mul_(b1).add_(g, alpha=1 - b1)
+        self.v.mul_(b2).addcmul_(g, g, value=1 - b2)
+        denom = (self.v / (1 - b2 ** self.step)).sqrt_().add_(eps)
+        self.p.addcdiv_(self.m, denom, value=-lr / (1 - b1 ** self.step))
+        g.zero_()
+
+
+def _step_logit_scale(logit_scale, lr, betas, eps):
+    """A trainable logit scale is a model of its own in the reference (DDP-wrapped, in the optimizer's no-decay group, not
+    part of ``clip_gradients``: trainers/text_text.py:172-182, base.py:361-362): average its gradient over ranks and step it."""
+    params = [p for p in getattr(logit_scale, "parameters", lambda: [])() if p.requires_grad]
+    if not params:
+        return
+    allreduce_scalar_grads(logit_scale)
+    opts = logit_scale.__dict__.setdefault("_cx_scalar_adamw", {})
+    for p in params:
+        opts.setdefault(id(p), _ScalarAdamW(p)).update(lr, betas, eps)
+
+
 def training_step(model, batch, logit_scale, *, lr: float, chunk_size: Optional[int] = 64, betas=(0.9, 0.999), eps=1e-8,
-                  weight_decay=0.01, max_grad_norm: Optional[float] = 1.0, matryoshka_dims=None, matryoshka_loss_weights=None):
+                  weight_decay=0.01, max_grad_norm: Optional[float] = 1.0, matryoshka_dims=None, matryoshka_loss_weights=None,
+                  overlap_grad_reduce: bool = True):
     """base.py:366-393 for a BiEncoder tower on the fused path: forward (+ backward), gradient all-reduce across ranks
-    (DDP's job in the reference), global-norm clip + AdamW + zero_grad in two launches.  ``chunk_size=None`` selects the
-    plain (non-GradCache) step."""
+    (DDP's job in the reference; in layer-ordered buckets under the last backward when ``overlap_grad_reduce``), global-norm
+    clip + AdamW + zero_grad in two launches with DDP's 1 / world_size folded into the step, and the trainable logit
+    scale's own all-reduce + AdamW.  ``chunk_size=None`` selects the plain (non-GradCache) step."""
     model.train()
+    reducer = None
+    if overlap_grad_reduce and dist.is_initialized() and dist.get_world_size() > 1 and hasattr(model.trunk, "layer_grad_slices"):
+        reducer = model.__dict__.get("_cx_reducer")
+        if reducer is None:
+            reducer = model.__dict__["_cx_reducer"] = GradientBucketReducer(model.trunk)
     if chunk_size:
-        out = grad_cache_forward_step(model, batch, logit_scale, chunk_size)
+        q, d = _split_batch(batch, model.device)
+        out = {"loss": grad_cache_loss(tower1=model, t1_inputs=q, tower2=model, t2_inputs=d, chunk_size=chunk_size,
+                                       logit_scale=logit_scale, _grad_reducers={id(model.trunk): reducer} if reducer else None)}
     else:
         out = forward_step(model, batch, logit_scale, matryoshka_dims, matryoshka_loss_weights)
+        if reducer is not None:
+            reducer.arm()
         out["loss"].backward()
-    allreduce_gradients(model)
-    model.trunk.fused_adamw_step(lr, betas=betas, eps=eps, weight_decay=weight_decay, max_grad_norm=max_grad_norm)
+    grad_scale = reducer.wait() if reducer is not None else allreduce_gradients(model, average=False)
+    model.trunk.fused_adamw_step(lr, betas=betas, eps=eps, weight_decay=weight_decay, max_grad_norm=max_grad_norm,
+                                 grad_scale=grad_scale)
+    _step_logit_scale(logit_scale, lr, betas, eps)
     return out["loss"].detach()

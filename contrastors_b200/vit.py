@@ -23,7 +23,7 @@ import torch.nn as nn
 from . import ops
 from .loss import symmetric_clip_loss
 from .logit_scale import LogitScale
-from .models import _OPT_STEPS, _attach
+from .flat_params import FlatParamModule
 from .ops import MAJOR_MN
 
 
@@ -72,49 +72,14 @@ def _vit_specs(cfg: ViTConfig):
     return two_d, one_d
 
 
-class ViTModel(nn.Module):
+class ViTModel(FlatParamModule):
     def __init__(self, config: ViTConfig):
         super().__init__()
         self.config = config
         assert config.n_embd // config.n_head == 64, "the sm_100a attention kernel is specialised for head_dim 64"
         two_d, one_d = _vit_specs(config)
-        self._specs = two_d + one_d
-        self._offsets, off = {}, 0
-        for name, shape in self._specs:
-            n = math.prod(shape)
-            self._offsets[name] = (off, n, shape)
-            off += (n + 63) // 64 * 64
-        self._n_decay = self._offsets[one_d[0][0]][0]
-        self._n_total = off
-        self._flat = torch.zeros(off, dtype=torch.float32)
-        self._flat_grad = torch.zeros(off, dtype=torch.float32)
-        self._shadow, self._shadow_version, self._master_version, self._opt_state = None, None, 0, None
-        for name, shape in self._specs:
-            _attach(self, name, nn.Parameter(torch.empty(0)))
-        self._rebind()
+        self._init_flat(two_d, one_d)
         self.reset_parameters()
-
-    # flat-buffer plumbing (same contract as NomicBertModel)
-    def _named_leaf(self, dotted):
-        mod, parts = self, dotted.split(".")
-        for name in parts[:-1]:
-            mod = mod._modules[name]
-        return mod, parts[-1]
-
-    def _rebind(self):
-        for name, (off, n, shape) in self._offsets.items():
-            mod, leaf = self._named_leaf(name)
-            p = mod._parameters[leaf]
-            p.data = self._flat[off:off + n].view(shape)
-            p.grad = self._flat_grad[off:off + n].view(shape)
-
-    def _apply(self, fn, recurse=True):
-        flat, grad = fn(self._flat), fn(self._flat_grad)
-        self._flat = flat.float() if flat.dtype != torch.float32 else flat
-        self._flat_grad = grad.float() if grad.dtype != torch.float32 else grad
-        self._shadow, self._shadow_version, self._opt_state = None, None, None
-        self._rebind()
-        return self
 
     def reset_parameters(self, seed: Optional[int] = None):
         g = torch.Generator().manual_seed(seed) if seed is not None else None
@@ -127,34 +92,7 @@ class ViTModel(nn.Module):
                     v.zero_()
                 else:
                     v.copy_((torch.randn(n, generator=g) * self.config.initializer_range).to(v.device))
-        self._master_version += 1
-
-    def load_reference_state_dict(self, sd):
-        with torch.no_grad():
-            for name, (off, n, shape) in self._offsets.items():
-                self._flat[off:off + n].copy_(sd[name].reshape(-1).to(self._flat.device, torch.float32))
-        self._master_version += 1
-
-    def view(self, buf, name):
-        off, n, shape = self._offsets[name]
-        return buf[off:off + n].view(shape)
-
-    def flat_grad(self):
-        return self._flat_grad
-
-    def mark_weights_updated(self):
-        self._master_version += 1
-
-    def shadow(self):
-        ver = (self._master_version, _OPT_STEPS[0])
-        if self._shadow is None or self._shadow_version != ver:
-            if self._shadow is None:
-                self._shadow = torch.empty(self._n_total, device=self._flat.device, dtype=torch.bfloat16)
-            ops.cast_f32_bf16(self._flat, self._shadow)
-            self._shadow_version = ver
-        return self._shadow
-
-    fused_adamw_step = None  # bound below (shares the text tower's implementation)
+        self.mark_weights_updated()
 
     def forward(self, input_ids, **kwargs):
         """``input_ids`` = pixel tensor [B, C, H, W] (the reference keys pixels as input_ids, image_text_loader.py:339).
@@ -162,14 +100,6 @@ class ViTModel(nn.Module):
         B = input_ids.shape[0]
         h = _ViTFn.apply(self._flat, self, input_ids, False)
         return (h.view(B, self.config.num_patches + 1, -1),)
-
-
-def _bind_adamw():
-    from .models import NomicBertModel
-    ViTModel.fused_adamw_step = NomicBertModel.fused_adamw_step
-
-
-_bind_adamw()
 
 
 class _ViTFn(torch.autograd.Function):
@@ -227,6 +157,7 @@ class _ViTFn(torch.autograd.Function):
     def backward(ctx, g_out):
         model = ctx.model
         cfg = model.config
+        model._ensure_grad_views()
         W, P, G, v = model.shadow(), model._flat, model._flat_grad, model.view
         patches, z0, st_pre, a_f, b_f, st_f, cu, B, S, act = ctx.misc
         d, H, Dh, nP = cfg.n_embd, cfg.n_head, 64, cfg.num_patches

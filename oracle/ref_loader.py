@@ -2,7 +2,9 @@
 
 TEST INFRASTRUCTURE ONLY.  Used by ``oracle/gen_golden.py`` (fixture generation) and by the
 ``ref``-marked tests that cross-check the oracle against the live reference when it is present.
-/root/reference does not exist on the GPU box; nothing on the gpu/bench path calls this.
+/root/reference does not exist on the GPU box; there the same modules come from ``baseline/_ref`` (the unmodified
+package installed by ``baseline/install_ref.sh``), used only by ``bench.py``'s baseline legs (``--impl reference``,
+``cpu_baseline``, ``gpu_baseline``): the reference is the thing TIMED there, never part of the product path.
 
 Bypass: ``src/contrastors/__init__.py:1`` star-imports flash-attn-only
 modules, so we register an empty ``contrastors`` package whose ``__path__`` points at the
@@ -16,11 +18,19 @@ import os
 import sys
 import types
 
-REF_ROOT = "/root/reference/src/contrastors"
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# the read-only tree in the build container, else the unmodified install that travels to the GPU box
+# (baseline/install_ref.sh -> baseline/_ref, git-ignored)
+_CANDIDATES = ["/root/reference/src/contrastors", os.path.join(os.path.dirname(_HERE), "baseline", "_ref", "contrastors")]
+REF_ROOT = next((p for p in _CANDIDATES if os.path.isdir(p)), _CANDIDATES[0])
 
 
 def available() -> bool:
     return os.path.isdir(REF_ROOT)
+
+
+def source() -> str:
+    return "tree" if REF_ROOT == _CANDIDATES[0] else "baseline/_ref"
 
 
 def _pkg(name: str, path: str):

@@ -105,9 +105,12 @@ def test_save_state_load_state_round_trip(tmp_path):
     assert sorted(os.listdir(os.path.join(out, "model"))) == ["config.json", "logit_scale.pt", "model.safetensors"]
     want_torch, want_np = torch.rand(4), np.random.rand(4)  # what the RNG streams produce right after the save point
     opt = torch.load(os.path.join(out, "optimizer.pt"), weights_only=True)
-    assert opt["step"] == 7 and set(opt["state"]) == set(trunk._offsets)
+    # torch.optim.AdamW layout: integer ids in param_groups order (decay names sorted, then no-decay names sorted)
+    decay, no_decay = trunk._optimizer_param_order("trunk.")
+    assert [g["params"] for g in opt["param_groups"]] == [list(range(len(decay))), list(range(len(decay), len(decay) + len(no_decay)))]
+    assert set(opt["state"]) == set(range(len(trunk._offsets))) and float(opt["state"][0]["step"]) == 7.0
     name = "encoder.layers.1.mlp.fc2.weight"
-    assert torch.equal(opt["state"][name]["exp_avg"], trunk.view(trunk._opt_state["m"], name))
+    assert torch.equal(opt["state"][decay.index("trunk." + name)]["exp_avg"], trunk.view(trunk._opt_state["m"], name))
 
     fresh, _, _ = _tiny()
     fresh.trunk._flat.zero_()
@@ -123,6 +126,71 @@ def test_save_state_load_state_round_trip(tmp_path):
         assert torch.equal(fresh.trunk.view(fresh.trunk._opt_state["v"], name), trunk.view(trunk._opt_state["v"], name))
     assert torch.equal(ls2.logit_scale, ls.logit_scale)
     assert torch.equal(torch.rand(4), want_torch) and np.array_equal(np.random.rand(4), want_np)  # RNG streams resume
+
+
+def test_optimizer_pt_loads_into_torch_adamw_and_back(tmp_path):
+    """optimizer.pt is exchangeable with the reference trainer: its ``optimizer.load_state_dict`` (trainers/base.py:300-301) on
+    the AdamW that ``configure_optimizer`` (optimizer.py:7-47, restated here) builds accepts our file, continues from our
+    moments, and the state dict it writes loads back into the fused optimizer."""
+    model, _, _ = _tiny()
+    trunk = model.trunk
+    g = torch.Generator().manual_seed(5)
+    trunk._opt_state = dict(step=3, m=torch.randn(trunk._n_total, generator=g), v=torch.rand(trunk._n_total, generator=g),
+                            hyper=dict(lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01))
+    ours = trunk.optimizer_state_dict(prefix="trunk.")
+    # configure_optimizer's grouping on named_parameters() of the BiEncoder
+    named = dict(model.named_parameters())
+    decay = sorted(n for n, p in named.items() if p.squeeze().ndim >= 2 and "bias" not in n)
+    no_decay = sorted(n for n in named if n not in decay)
+    opt = torch.optim.AdamW([{"params": [named[n] for n in decay], "weight_decay": 0.01, "lr": 2e-4},
+                             {"params": [named[n] for n in no_decay], "weight_decay": 0.0, "lr": 2e-4}], betas=(0.9, 0.999), eps=1e-8)
+    opt.load_state_dict(ours)
+    name = "trunk.encoder.layers.0.attn.Wqkv.weight"
+    st = opt.state[named[name]]
+    assert float(st["step"]) == 3.0 and torch.equal(st["exp_avg"], trunk.view(trunk._opt_state["m"], name[len("trunk."):]))
+    back = opt.state_dict()
+    fresh, _, _ = _tiny()
+    fresh.trunk.load_optimizer_state_dict(back, prefix="trunk.")
+    assert fresh.trunk._opt_state["step"] == 3 and fresh.trunk._opt_state["hyper"]["lr"] == 2e-4
+    for n in trunk._offsets:
+        assert torch.equal(fresh.trunk.view(fresh.trunk._opt_state["v"], n), trunk.view(trunk._opt_state["v"], n))
+
+
+def test_torch_optimizer_two_steps_and_zero_grad_set_to_none():
+    """after ``optimizer.zero_grad(set_to_none=True)`` the gradient views were gone and later steps skipped
+    every parameter.  The views are re-bound by ``_ensure_grad_views`` (called at the start of each backward) and the flat
+    buffer is zeroed when they were found dropped.  CPU check of the plumbing (the kernels are not involved)."""
+    model, _, _ = _tiny()
+    trunk = model.trunk
+    opt = torch.optim.SGD(trunk.parameters(), lr=0.5)
+    w = trunk.view(trunk._flat, "encoder.layers.0.attn.Wqkv.weight")
+    for step in range(2):
+        trunk._ensure_grad_views()                      # what _TrunkFn.backward does first
+        trunk._flat_grad.add_(1.0)                      # stand-in for the kernels' accumulation
+        before = w.clone()
+        opt.step()
+        assert torch.allclose(w, before - 0.5), step    # the step saw exactly this step's gradient (not a stale sum)
+        opt.zero_grad(set_to_none=True)
+        assert next(trunk.parameters()).grad is None
+    trunk._ensure_grad_views()
+    assert float(trunk._flat_grad.abs().sum()) == 0.0 and next(trunk.parameters()).grad is not None
+
+
+def test_load_state_dict_invalidates_the_bf16_shadow():
+    """nn.Module.load_state_dict writes the master through the views; the shadow version must move."""
+    model, _, _ = _tiny()
+    v0 = model.trunk._master_version
+    model.load_state_dict({k: torch.zeros_like(v) for k, v in model.state_dict().items()})
+    assert model.trunk._master_version > v0 and float(model.trunk._flat.abs().sum()) == 0.0
+
+
+def test_apply_keeps_adam_moments():
+    model, _, _ = _tiny()
+    trunk = model.trunk
+    trunk._opt_state = dict(step=2, m=torch.ones(trunk._n_total), v=torch.ones(trunk._n_total))
+    model.to(torch.device("cpu"))
+    model.double()  # any _apply: the master stays fp32 and the moments survive
+    assert trunk._opt_state is not None and trunk._opt_state["step"] == 2 and trunk._opt_state["m"].dtype == torch.float32
 
 
 @pytest.mark.skipif(not ref_loader.available(), reason="the reference tree exists in the build container only")

@@ -52,6 +52,27 @@ def _worker(rank, ws, port, out_dir):
     t = FakeTrunk()
     allreduce_gradients(t, t)  # the same tower twice (tower1 is tower2) must be reduced once
     assert torch.allclose(t._g, torch.full((11,), sum(range(1, ws + 1)) / ws))
+    # bucketed reduction (parallel.GradientBucketReducer): layer buckets in backward order + the remainder = one all-reduce
+    from contrastors_b200.parallel import GradientBucketReducer
+
+    class FakeLayered(FakeTrunk):
+        _n_total = 64
+
+        def __init__(self):
+            self._g = torch.arange(64, dtype=torch.float32) * (rank + 1)
+
+        def layer_grad_slices(self):
+            return [(8, 24), (24, 40)]  # two "layers"; [0, 8) = embeddings, [40, 64) = 1-D parameters
+
+    lt = FakeLayered()
+    red = GradientBucketReducer(lt)
+    red.arm()
+    assert lt._bucket_reducer is red
+    red.layer_done(1)
+    red.layer_done(0)
+    red.finish()
+    assert lt._bucket_reducer is None and red.wait() == 1.0 / ws
+    assert torch.equal(lt._g, torch.arange(64, dtype=torch.float32) * sum(range(1, ws + 1)))
     np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([1]))
     dist.destroy_process_group()
 
