@@ -26,6 +26,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "cx_host.h"
 #include "cx_ptx.cuh"
 
@@ -58,25 +60,58 @@ using namespace cx;
 // 64 x 512 tokens x 12 heads, L2 flushed: forward 138 / 127 / 110.6 / 113.6 us; backward (incl. delta, zero fill, dQ
 // finalize) 415 / 376 us.  (Also tried and dropped: P through shared memory in the sub-tile kernel 131 us; 3/8 and 4/8
 // polynomial exponentials there 145 / 150 us; holding back the second CTA of each SM to de-phase the pair: no gain.)
-constexpr int kFwdDefaultMode = 6;
-constexpr int kBwdDefaultMode = 2;
+constexpr int kFwdDefaultMode = 8;  // two threads per row (round 2: 103 us vs 112 at 64 x 512 x 12, 131 vs 139 at 256 x 197 x 12)
+constexpr int kBwdDefaultMode = 3;  // transposed scores (round 2: 351 us vs 376, 457 vs 488)
 constexpr uint32_t kPoly38 = 0x52;  // column-pair pattern (period 8) routed to the polynomial
-static int attn_mode(const char* name, int dflt) {
+static int parse_mode(const char* name, int dflt) {
   const char* e = getenv(name);
   if (!e || !*e) return dflt;
   const int v = atoi(e);
   return (v == 1 || v == 2 || v == 3 || (v >= 6 && v <= 9)) ? v : dflt;
 }
+// the environment is read once per process (thread-safe static initialisation), not on every call; A/B sessions and the
+// parity tests of the non-default generations switch at run time through cx_attn_select_kernels
+static std::atomic<int> g_fwd_override{0}, g_bwd_override{0};
+static int fwd_mode() {
+  static const int m = parse_mode("CX_ATTN_FWD", kFwdDefaultMode);
+  const int o = g_fwd_override.load(std::memory_order_relaxed);
+  return o ? o : m;
+}
+static int bwd_mode() {
+  static const int m = parse_mode("CX_ATTN_BWD", kBwdDefaultMode);
+  const int o = g_bwd_override.load(std::memory_order_relaxed);
+  return o ? o : m;
+}
+
+extern "C" int cx_attn_select_kernels(int fwd_generation, int bwd_generation) {
+  auto ok = [](int v) { return v == 0 || v == 1 || v == 2 || v == 3 || (v >= 6 && v <= 9); };
+  CX_REQUIRE(ok(fwd_generation) && ok(bwd_generation), "cx_attn_select_kernels: unknown kernel generation (0 = default)");
+  g_fwd_override.store(fwd_generation, std::memory_order_relaxed);
+  g_bwd_override.store(bwd_generation, std::memory_order_relaxed);
+  return 0;
+}
 
 extern "C" int cx_debug_attn_trace(void* buf) {
+#ifdef CX_DEBUG_HOOKS
   CX_CUDA_CHECK(cudaMemcpyToSymbol(g_attn_trace, &buf, sizeof(buf)));
   return 0;
+#else
+  (void)buf;
+  CX_REQUIRE(false, "cx_debug_attn_trace: this library was built without CX_DEBUG_HOOKS (python -m contrastors_b200.build --debug-hooks)");
+#endif
 }
 
 // timing ablations for profiling sessions (results are WRONG when set): CX_ATTN_ABLATE bit mask, see the kernels
 static int attn_ablate() {
-  const char* e = getenv("CX_ATTN_ABLATE");
-  return (e && *e) ? atoi(e) : 0;
+#ifdef CX_DEBUG_HOOKS
+  static const int a = [] {
+    const char* e = getenv("CX_ATTN_ABLATE");
+    return (e && *e) ? atoi(e) : 0;
+  }();
+  return a;
+#else
+  return 0;  // release builds never ablate (the hook made the library return wrong results by environment variable)
+#endif
 }
 
 extern "C" int cx_attn_fwd(const void* qkv, const int32_t* cu_seqlens, void* out, float* lse, int total_tokens, int nseq,
@@ -89,18 +124,24 @@ extern "C" int cx_attn_fwd(const void* qkv, const int32_t* cu_seqlens, void* out
   int rc = make_tmap_2d(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, (uint64_t)3 * H * Dh, (uint64_t)total_tokens,
                         (uint64_t)3 * H * Dh * 2, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
-    CX_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::kTotal));
-    CX_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd2_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2Smem::kTotal));
-    CX_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2Smem::kTotal));
-    CX_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd4Smem::kTotal));
-    CX_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd5Smem::kTotal));
-    CX_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd3_kernel<kPoly38>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2Smem::kTotal));
-    configured = true;
-  }
+  // once per process, thread-safe (forward runs on the Python thread, backward on autograd's worker thread)
+  static std::once_flag configured;
+  static cudaError_t cfg_err = cudaSuccess;
+  std::call_once(configured, [] {
+    auto set = [](const void* f, int bytes) {
+      const cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      if (cfg_err == cudaSuccess) cfg_err = e;
+    };
+    set((const void*)attn_fwd_kernel, FwdSmem::kTotal);
+    set((const void*)attn_fwd2_kernel<true, 0>, Fwd2Smem::kTotal);
+    set((const void*)attn_fwd3_kernel<0>, Fwd2Smem::kTotal);
+    set((const void*)attn_fwd4_kernel, Fwd4Smem::kTotal);
+    set((const void*)attn_fwd5_kernel, Fwd5Smem::kTotal);
+    set((const void*)attn_fwd3_kernel<kPoly38>, Fwd2Smem::kTotal);
+  });
+  CX_CUDA_CHECK(cfg_err);
   dim3 grid((max_seqlen + 127) / 128, H, nseq);
-  const int mode = attn_mode("CX_ATTN_FWD", kFwdDefaultMode);
+  const int mode = fwd_mode();
   const int ablate = attn_ablate();
   if (mode == 1)
     attn_fwd_kernel<<<grid, kFwdThreads, FwdSmem::kTotal, stream>>>(tm, cu_seqlens, (__nv_bfloat16*)out, lse, total_tokens, H,
@@ -150,15 +191,20 @@ extern "C" int cx_attn_bwd(const void* qkv, const void* out, const void* dout, c
   rc = make_tmap_2d(&tmDQ, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dq_acc, (uint64_t)H * Dh, (uint64_t)T, (uint64_t)H * Dh * 4, 32,
                     128, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
-    CX_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::kTotal));
-    CX_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::kTotal));
-    CX_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd3Smem::kTotal));
-    configured = true;
-  }
+  static std::once_flag configured;
+  static cudaError_t cfg_err = cudaSuccess;
+  std::call_once(configured, [] {
+    auto set = [](const void* f, int bytes) {
+      const cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      if (cfg_err == cudaSuccess) cfg_err = e;
+    };
+    set((const void*)attn_bwd_kernel, BwdSmem::kTotal);
+    set((const void*)attn_bwd2_kernel, BwdSmem::kTotal);
+    set((const void*)attn_bwd3_kernel, Bwd3Smem::kTotal);
+  });
+  CX_CUDA_CHECK(cfg_err);
   dim3 grid((max_seqlen + 127) / 128, H, nseq);
-  const int bmode = attn_mode("CX_ATTN_BWD", kBwdDefaultMode);
+  const int bmode = bwd_mode();
   if (bmode == 1)
     attn_bwd_kernel<<<grid, kBwdThreads, BwdSmem::kTotal, stream>>>(tmQKV, tmDO, tmDQ, cu_seqlens, lse, delta,
                                                                    (__nv_bfloat16*)dqkv, T, H, softmax_scale);

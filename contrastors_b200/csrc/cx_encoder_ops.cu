@@ -838,11 +838,8 @@ static int ln_bwd_launch(int grid, size_t smem, cudaStream_t st, const __nv_bflo
                          const int64_t* type_ids, const __nv_bfloat16* type_emb, const __nv_bfloat16* g1, const __nv_bfloat16* g2,
                          const float* gamma, const float* stats, __nv_bfloat16* dz, float* dword, float* dtype_emb, float* partials,
                          int rows, int d, int64_t padding_idx, const __nv_bfloat16* gres, DropParams dp, __nv_bfloat16* da_out) {
-  static bool configured = false;
-  if (!configured) {
-    CX_CUDA_CHECK(cudaFuncSetAttribute(add_layernorm_bwd_kernel<EMBED, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4));
-    configured = true;
-  }
+  auto kern = add_layernorm_bwd_kernel<EMBED, NV>;
+  CX_SET_SMEM_ONCE(kern, 8 * 3 * 1024 * 4);
   add_layernorm_bwd_kernel<EMBED, NV><<<grid, 256, smem, st>>>(a, b, ids, type_ids, type_emb, g1, g2, gamma, stats, dz, dword, dtype_emb,
                                                                partials, rows, d, padding_idx, gres, dp, da_out);
   CX_LAUNCH_CHECK();

@@ -28,11 +28,7 @@ static int launch_pair(const GemmArgs& g, const CUtensorMap& tmA, const CUtensor
                        const CUtensorMap& tmD) {
   auto kern = gemm_kernel<256, A_MN, B_MN, MODE, OUT_F32, ACCUM, true>;
   constexpr int smem = GemmSmem<256, true>::kTotal;
-  static bool configured = false;
-  if (!configured) {
-    CX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  CX_SET_SMEM_ONCE(kern, smem);
   const int tile_n = (MODE == EPI_SWIGLU) ? 128 : 256;
   const int tiles = ((g.M + 255) / 256) * ((g.N + tile_n - 1) / tile_n) * g.splits;
   int clusters = sm_count() / 2;
@@ -60,11 +56,7 @@ static int launch_one(const GemmArgs& g, const CUtensorMap& tmA, const CUtensorM
   if (BLOCK_N == 256 && gemm_use_pair(g)) return launch_pair<MODE, OUT_F32, ACCUM, A_MN, B_MN>(g, tmA, tmB, tmC, tmD);
   auto kern = gemm_kernel<BLOCK_N, A_MN, B_MN, MODE, OUT_F32, ACCUM>;
   constexpr int smem = GemmSmem<BLOCK_N>::kTotal;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
-    CX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  CX_SET_SMEM_ONCE(kern, smem);  // per instantiation
   const int grid = gemm_grid(g.M, g.N, g.splits, MODE == EPI_SWIGLU ? BLOCK_N / 2 : 0);
   kern<<<grid, kGemmThreads, smem, g.stream>>>(tmA, tmB, tmC, tmD, g.M, g.N, g.K, g.splits, g.ep);
   CX_LAUNCH_CHECK();

@@ -17,7 +17,7 @@
 //   EPI_NCE_STATS  InfoNCE forward: per-row (max, sum-exp, first-argmax, label logit) partials per column tile
 //   EPI_SWIGLU     gated MLP first layer: B tile = 128 rows of fc11 (y) + the matching 128 rows of fc12 (gate);
 //                  epilogue writes out = y * silu(gate) (bf16 [M, N]) and optionally the pre-activations [y | gate]
-//   EPI_NCE_DS     InfoNCE backward stage 1: dS = coef * (softmax - onehot) (x rq_i rd_j) stored as bf16, plus
+//   EPI_NCE_DS     InfoNCE backward stage 1: dS = softmax - onehot stored UNSCALED as fp16, plus
 //                  per-thread partial of sum dS*s (the logit-scale gradient)
 #pragma once
 #include "cx_host.h"
@@ -59,7 +59,6 @@ struct EpiParams {
   __nv_bfloat16* yg_out = nullptr;   // [M, 2N] = [y | gate], nullptr = do not keep the pre-activations
   int64_t ld_yg = 0;
   int ab_f16 = 0;  // A and B operands hold IEEE fp16 instead of bf16 (kind::f16 wants one input type): fp16 dS path
-  int ds_f16 = 0;  // EPI_NCE_DS: store (softmax - onehot) UNSCALED as fp16 (11-bit mantissa) instead of coef*(...) as bf16
 };
 
 constexpr int kBlockM = 128;
@@ -293,7 +292,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const bool plain = (n0 + HALF_N <= N) && ep.rd == nullptr;
 
       // per-row InfoNCE state, in the log2 domain: t = s * log2(e)
-      float rs2 = 1.f, lse2 = 0.f, rowf = 1.f;
+      float rs2 = 1.f, lse2 = 0.f;
       int label = -1;
       float run_max = -INFINITY, run_sum = 0.f;
       int run_arg = 0;
@@ -301,10 +300,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const float rqi = (ep.rq != nullptr && row_ok) ? ep.rq[row] : 1.f;
         rs2 = ep_scale * rqi * kLog2e;
         label = (row + ep.label_offset) * ep.label_stride;
-        if (MODE == EPI_NCE_DS) {
-          lse2 = row_ok ? ep.lse[row] * kLog2e : INFINITY;  // +inf => p == 0 for rows past M
-          rowf = ep.ds_f16 ? 1.f : ep_coef * rqi;           // bf16 path stores coef * p * rq_i * rd_j
-        }
+        if (MODE == EPI_NCE_DS) lse2 = row_ok ? ep.lse[row] * kLog2e : INFINITY;  // +inf => p == 0 for rows past M
       }
 
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -476,6 +472,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         } else {
           // value transform
           if (MODE == EPI_NCE_DS) {
+            // stores (softmax - onehot) in [-1, 1] UNSCALED as fp16 (11-bit mantissa); coef, the logit scale and the per-row
+            // inverse norms of the normalised-prefix losses are applied by the two contractions (alpha and pre-normalised
+            // fp16 B operands), so one dS serves dQ and dD on every loss variant
             const bool has_label = (label >= col0 && label < col0 + 32 && row_ok);
             float tl = 0.f;
             if (plain) {
@@ -494,10 +493,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                   tl = (col0 + j + 2 == label) ? t2 : tl;
                   tl = (col0 + j + 3 == label) ? t3 : tl;
                 }
-                v[j] = __float_as_uint(p0 * rowf);
-                v[j + 1] = __float_as_uint(p1 * rowf);
-                v[j + 2] = __float_as_uint(p2 * rowf);
-                v[j + 3] = __float_as_uint(p3 * rowf);
+                v[j] = __float_as_uint(p0);
+                v[j + 1] = __float_as_uint(p1);
+                v[j + 2] = __float_as_uint(p2);
+                v[j + 3] = __float_as_uint(p3);
               }
             } else {
 #pragma unroll
@@ -508,15 +507,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const float p = (col < N) ? fast_exp2(t - lse2) : 0.f;
                 dl0 = fmaf(p, t, dl0);
                 tl = (col == label) ? t : tl;
-                v[j] = __float_as_uint(p * rowf * ((ep.ds_f16 || ep.rd == nullptr) ? 1.f : rdj));
+                v[j] = __float_as_uint(p);
               }
             }
             if (has_label) {  // subtract the one-hot: rare (one chunk per row per pass)
               dl0 -= tl;
-              const float one = rowf * ((ep.ds_f16 || ep.rd == nullptr) ? 1.f : ep.rd[label]);
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (col0 + j == label) v[j] = __float_as_uint(__uint_as_float(v[j]) - one);
+                if (col0 + j == label) v[j] = __float_as_uint(__uint_as_float(v[j]) - 1.f);
             }
           } else {
 #pragma unroll
@@ -554,7 +552,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 w;
-              if (MODE == EPI_NCE_DS && ep.ds_f16) {
+              if (MODE == EPI_NCE_DS) {
                 w.x = pack_f16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
                 w.y = pack_f16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
                 w.z = pack_f16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));

@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <mutex>
 #include <string>
 
 #include "../../include/contrastors_b200.h"
@@ -32,6 +33,16 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
     cudaError_t _e = cudaGetLastError();                                                               \
     if (_e != cudaSuccess) return ::cx::fail(CX_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(_e)); \
     ::cx::count_launch();                                                                              \
+  } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per process and per kernel instantiation, safe from any thread
+// (the forward runs on the Python thread, the backward on autograd's worker thread): a `static bool` here was a data race.
+#define CX_SET_SMEM_ONCE(kern, bytes)                                                                                 \
+  do {                                                                                                                \
+    static std::once_flag _once;                                                                                      \
+    static cudaError_t _err = cudaSuccess;                                                                            \
+    std::call_once(_once, [&] { _err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); }); \
+    CX_CUDA_CHECK(_err);                                                                                              \
   } while (0)
 
 // 2D row-major tensor map: `inner` contiguous elements per row, `outer` rows, `row_stride_bytes` between rows.

@@ -3,9 +3,11 @@
 // Replaces the reference's unfused chain  matmul -> LogitScale -> F.cross_entropy -> argmax  and its autograd
 // backward (/root/reference/src/contrastors/loss.py:105-130, modeling_biencoder.py:37-38).  The [n x m] logits never
 // exist in HBM in fp32: the forward keeps them in TMEM and reduces them to per-row statistics in the GEMM epilogue;
-// the backward recomputes them, emits dS = coef*(softmax - onehot) as bf16 into a workspace that stays L2-resident
-// (n*m*2 bytes), and contracts it twice (dQ = dS D, dD = dS^T Q) with the same GEMM core (MN-major operands, so no
-// transposes are materialised).
+// the backward recomputes them, emits dS = softmax - onehot (in [-1, 1], UNSCALED) as fp16 into a workspace (n*m*2 bytes,
+// L2-resident at the 8-GPU per-rank shape), and contracts it twice (dQ = dS D^, dD = dS^T Q^) with the same GEMM core
+// (MN-major operands, so no transposes are materialised) against fp16 copies of the operands that carry the per-row inverse
+// norms of the normalised-prefix losses (Matryoshka / CLIP); coef and the logit scale ride in the contractions' alpha.
+// One dS and one code path serve every loss variant at fp16's 11-bit mantissa (1e-3 parity needs more than bf16's 8).
 #include <math.h>
 
 #include "cx_gemm.cuh"
@@ -21,9 +23,9 @@ struct NceWorkspace {
   float* dlogit_part;
   float* block_part;     // [2 * kMaxCombineBlocks]
   unsigned int* ticket;  // [1]
-  __nv_bfloat16* ds;
+  __half* ds;
   int64_t ld_ds;
-  __half* qh;  // fp16 copies of q / d for the backward contractions (exact for |x| >= 2^-14)
+  __half* qh;  // fp16 copies of q * rq / d * rd for the backward contractions (exact for 2^-14 <= |x| <= 65504; saturating)
   __half* dh;
   int64_t ld_h;
   size_t bytes;
@@ -47,7 +49,7 @@ static NceWorkspace carve(void* base, int n, int m, int k) {
   w.block_part = reinterpret_cast<float*>(take((size_t)2 * kMaxCombineBlocks * 4));
   w.ticket = reinterpret_cast<unsigned int*>(take(256));
   w.ld_ds = (int64_t)align_up((size_t)m, 8);
-  w.ds = reinterpret_cast<__nv_bfloat16*>(take((size_t)n * w.ld_ds * 2));
+  w.ds = reinterpret_cast<__half*>(take((size_t)n * w.ld_ds * 2));
   w.ld_h = (int64_t)align_up((size_t)k, 8);
   w.qh = reinterpret_cast<__half*>(take((size_t)n * w.ld_h * 2));
   w.dh = reinterpret_cast<__half*>(take((size_t)m * w.ld_h * 2));
@@ -170,25 +172,29 @@ __global__ void rows_to_bf16_kernel(const float* __restrict__ x, int64_t ldx, __
   }
 }
 
-// bf16 -> fp16 row copy, 8 elements per thread (rows are 16-byte aligned with k % 8 == 0 on the fast path)
+// y (fp16) = sat(x (bf16) * inv_norm[row]), 8 elements per thread (rows are 16-byte aligned with k % 8 == 0 on the fast
+// path).  Saturating: an embedding entry beyond +-65504 (a logit beyond 1e6 at any useful scale) stays finite.
 __global__ void bf16_to_f16_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __half* __restrict__ y, int64_t ldy,
-                                        int rows, int k, int vec_ok) {
+                                        const float* __restrict__ inv_norm, int rows, int k, int vec_ok) {
   const int per_row = (k + 7) / 8;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)rows * per_row) return;
   const int r = (int)(i / per_row), c = (int)(i % per_row) * 8;
+  const float inv = inv_norm != nullptr ? inv_norm[r] : 1.f;
   const __nv_bfloat16* xr = x + (size_t)r * ldx + c;
   __half* yr = y + (size_t)r * ldy + c;
+  auto sat = [](float v) { return fminf(fmaxf(v, -65504.f), 65504.f); };
   if (vec_ok && c + 8 <= k) {
     const uint4 in = *reinterpret_cast<const uint4*>(xr);
     const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&in);
     uint4 out;
     __half2* h2 = reinterpret_cast<__half2*>(&out);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) h2[j] = __floats2half2_rn(__low2float(b2[j]), __high2float(b2[j]));
+    for (int j = 0; j < 4; ++j) h2[j] = __floats2half2_rn(sat(__low2float(b2[j]) * inv), sat(__high2float(b2[j]) * inv));
     *reinterpret_cast<uint4*>(yr) = out;
   } else {
-    for (int j = 0; j < 8 && c + j < k; ++j) yr[j] = __float2half_rn(__bfloat162float(xr[j]));
+    for (int j = 0; j < 8 && c + j < k; ++j) yr[j] = __float2half_rn(sat(__bfloat162float(xr[j]) * inv));
+    for (int j = 0; j < 8 && c + j >= k && c + j < (int)ldy; ++j) yr[j] = __float2half_rn(0.f);  // zero the row padding
   }
 }
 
@@ -268,7 +274,7 @@ extern "C" int cx_infonce_bwd(const void* q, int64_t ldq, const void* d, int64_t
   CX_REQUIRE(n > 0 && m > 0 && k_dim > 0, "cx_infonce_bwd: empty problem");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   NceWorkspace w = carve(align256(workspace), n, m, k_dim);
-  // stage 1: dS (bf16) = coef * (softmax - onehot) [* rq_i rd_j]
+  // stage 1: dS (fp16) = softmax - onehot, unscaled; the logit-scale gradient partials carry coef
   GemmArgs g{};
   g.A = q; g.B = d; g.C = w.ds;
   g.M = n; g.N = m; g.K = k_dim;
@@ -279,11 +285,6 @@ extern "C" int cx_infonce_bwd(const void* q, int64_t ldq, const void* d, int64_t
   g.ep.scale = scale; g.ep.scale_dev = scale_dev; g.ep.rq = rq; g.ep.rd = rd;
   g.ep.label_offset = label_offset; g.ep.label_stride = label_stride;
   g.ep.lse = lse; g.ep.coef = coef; g.ep.coef_dev = coef_dev;
-  // Plain (pre-normalised) inputs: the workspace holds UNSCALED fp16 (softmax - onehot) in [-1, 1] (11-bit mantissa) and
-  // coef is folded into the contractions' alpha.  With per-row norms the values are scaled by rq*rd, whose range is
-  // the caller's, so that path keeps bf16 (fp32 exponent range) and coef in the stored value.
-  const bool f16 = (rq == nullptr && rd == nullptr);
-  g.ep.ds_f16 = f16 ? 1 : 0;
   g.ep.dlogit_part = w.dlogit_part;
   g.stream = stream;
   // every CTA of the stage-1 launch writes one partial; the array is zeroed first so the (launch-mode dependent) CTA
@@ -293,45 +294,40 @@ extern "C" int cx_infonce_bwd(const void* q, int64_t ldq, const void* d, int64_t
   if (rc) return rc;
   nce_dlogit_kernel<<<1, 32, 0, stream>>>(w.dlogit_part, kMaxGrid, stats);
   CX_LAUNCH_CHECK();
-  const void* qB = q;
-  const void* dB = d;
-  int64_t ldqB = ldq, lddB = ldd;
-  if (f16) {
+  // fp16 B operands of the two contractions: q^ = q * rq, d^ = d * rd (rq / rd null = 1)
+  {
     const int threads = 256;
     const int64_t per_row = (k_dim + 7) / 8;
     const int vq = (ldq % 8 == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0) ? 1 : 0;
     const int vd = (ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(d) & 15) == 0) ? 1 : 0;
     bf16_to_f16_rows_kernel<<<(unsigned)(((int64_t)n * per_row + threads - 1) / threads), threads, 0, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(q), ldq, w.qh, w.ld_h, n, k_dim, vq);
+        reinterpret_cast<const __nv_bfloat16*>(q), ldq, w.qh, w.ld_h, rq, n, k_dim, vq);
     CX_LAUNCH_CHECK();
     bf16_to_f16_rows_kernel<<<(unsigned)(((int64_t)m * per_row + threads - 1) / threads), threads, 0, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(d), ldd, w.dh, w.ld_h, m, k_dim, vd);
+        reinterpret_cast<const __nv_bfloat16*>(d), ldd, w.dh, w.ld_h, rd, m, k_dim, vd);
     CX_LAUNCH_CHECK();
   }
-  if (f16) {
-    qB = w.qh; dB = w.dh; ldqB = w.ld_h; lddB = w.ld_h;
-  }
-  // stage 2a: dQ[n,k] = scale * dS[n,m] (K-major A) x D[m,k] (MN-major B), split-K over m
+  // stage 2a: dQ^[n,k] = scale * coef * dS[n,m] (K-major A) x D^[m,k] (MN-major B), split-K over m
   GemmArgs a{};
-  a.A = w.ds; a.B = dB; a.C = dq;
+  a.A = w.ds; a.B = w.dh; a.C = dq;
   a.M = n; a.N = k_dim; a.K = m;
   a.a_mn = false; a.b_mn = true;
-  a.lda = w.ld_ds; a.ldb = lddB; a.ldc = lddq;
+  a.lda = w.ld_ds; a.ldb = w.ld_h; a.ldc = lddq;
   a.out_f32 = true; a.accumulate = false; a.splits = 0;
-  a.mode = EPI_STORE; a.ep.alpha = f16 ? scale * coef : scale; a.ep.alpha_dev = scale_dev; a.ep.alpha_dev2 = f16 ? coef_dev : nullptr;
-  a.ep.ab_f16 = f16 ? 1 : 0;
+  a.mode = EPI_STORE; a.ep.alpha = scale * coef; a.ep.alpha_dev = scale_dev; a.ep.alpha_dev2 = coef_dev;
+  a.ep.ab_f16 = 1;
   a.stream = stream;
   rc = launch_gemm(a);
   if (rc) return rc;
-  // stage 2b: dD[m,k] = scale * dS^T (MN-major A: stored [n,m]) x Q[n,k] (MN-major B)
+  // stage 2b: dD^[m,k] = scale * coef * dS^T (MN-major A: stored [n,m]) x Q^[n,k] (MN-major B)
   GemmArgs b{};
-  b.A = w.ds; b.B = qB; b.C = dd;
+  b.A = w.ds; b.B = w.qh; b.C = dd;
   b.M = m; b.N = k_dim; b.K = n;
   b.a_mn = true; b.b_mn = true;
-  b.lda = w.ld_ds; b.ldb = ldqB; b.ldc = lddd;
+  b.lda = w.ld_ds; b.ldb = w.ld_h; b.ldc = lddd;
   b.out_f32 = true; b.accumulate = accumulate_dd != 0; b.splits = 0;
-  b.mode = EPI_STORE; b.ep.alpha = f16 ? scale * coef : scale; b.ep.alpha_dev = scale_dev; b.ep.alpha_dev2 = f16 ? coef_dev : nullptr;
-  b.ep.ab_f16 = f16 ? 1 : 0;
+  b.mode = EPI_STORE; b.ep.alpha = scale * coef; b.ep.alpha_dev = scale_dev; b.ep.alpha_dev2 = coef_dev;
+  b.ep.ab_f16 = 1;
   b.stream = stream;
   return launch_gemm(b);
 }

@@ -130,9 +130,9 @@ class _FusedInfoNCE(torch.autograd.Function):
                 gd = torch.empty(m, ldk, device=dev, dtype=torch.float32)[:, :k]
                 ops.infonce_bwd(q_bf, d_bf, k, 1.0, scale_dev, saved_rq[i], saved_rd[i], spec.label_offset,
                                 spec.label_stride, saved_lse[i], coef, coef_dev, gq, gd, False, stats, ctx.ws_buf)
-                if spec.normalize:
-                    ops.l2norm_bwd(q32, gq, saved_rq[i], k, out=dq, g_prescaled=True, accumulate=True)
-                    ops.l2norm_bwd(d32, gd, saved_rd[i], k, out=dd, g_prescaled=True, accumulate=True)
+                if spec.normalize:  # gq / gd are gradients w.r.t. the normalised prefixes: chain through F.normalize
+                    ops.l2norm_bwd(q32, gq, saved_rq[i], k, out=dq, g_prescaled=False, accumulate=True)
+                    ops.l2norm_bwd(d32, gd, saved_rd[i], k, out=dd, g_prescaled=False, accumulate=True)
                 else:
                     dq[:, :k] += gq
                     dd[:, :k] += gd

@@ -340,6 +340,11 @@ def embed_head_bwd(pooled, gout, save, hamming, normalize):
     return g
 
 
+def attn_select_kernels(fwd_generation=0, bwd_generation=0):
+    """A/B switch between attention kernel generations (0 = default); process-wide."""
+    _lib.check(_lib.load().cx_attn_select_kernels(int(fwd_generation), int(bwd_generation)), "cx_attn_select_kernels")
+
+
 def attn_fwd(qkv, cu_seqlens, max_seqlen, H, Dh, softmax_scale):
     """qkv [T, 3*H*Dh] bf16 (RoPE applied) -> (out [T, H*Dh] bf16, lse [H, T] fp32)."""
     T = qkv.shape[0]

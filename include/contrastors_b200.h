@@ -68,11 +68,14 @@ CX_API int cx_gemm_swiglu(const void* x, const void* w1, void* act_out, void* yg
  * Forward writes: lse[n] (fp32), argmax[n] (int32, first max wins), label_logit[n], and
  *   stats[0] = sum_i (lse_i - s_i,label_i)  (caller divides by n and applies the world-size factor)
  *   stats[1] = number of rows whose argmax == label.
- * Backward: dS_ij = coef * (exp(s_ij - lse_i) - [j == label_i]) in bf16 (never leaves L2-sized workspace), then
- *   dq[n,k_dim] = scale * rq_i * sum_j dS_ij rd_j d_j   (fp32, ldq_out)
- *   dd[m,k_dim] = scale * rd_j * sum_i dS_ij rq_i q_i   (fp32, ldd_out; accumulate_dd != 0 adds into dd)
- *   stats[2]  = sum_ij dS_ij * s_ij   (= d loss / d log(scale))
- * When rq/rd are given the caller finishes the chain rule through F.normalize (cx_l2norm_bwd, g_prescaled = 1).
+ * Backward: dS_ij = exp(s_ij - lse_i) - [j == label_i], UNSCALED in [-1, 1], as fp16 in the workspace; then
+ *   dq[n,k_dim] = coef * scale * sum_j dS_ij (rd_j d_j)   (fp32, ldq_out)  = d loss / d (rq_i q_i)
+ *   dd[m,k_dim] = coef * scale * sum_i dS_ij (rq_i q_i)   (fp32, ldd_out; accumulate_dd != 0 adds into dd)
+ *   stats[2]  = coef * sum_ij dS_ij * s_ij   (= d loss / d log(scale))
+ * i.e. the gradients with respect to the (normalised) rows the logits were formed from; when rq/rd are given the caller
+ * finishes the chain rule through F.normalize (cx_l2norm_bwd, g_prescaled = 0).  The contractions read fp16 copies of
+ * rq_i q_i / rd_j d_j (exact for bf16 values in [2^-14, 65504], saturating beyond: the label_stride >= 1 and finite-operand
+ * contract of this entry point; the reference's all-zero labels for ungathered documents at world size > 1 are rejected).
  * workspace: cx_infonce_workspace_bytes(n, m, k_dim) bytes of device memory, reusable across calls on one stream. */
 CX_API size_t cx_infonce_workspace_bytes(int n, int m, int k_dim);
 CX_API int cx_infonce_fwd(const void* q, int64_t ldq, const void* d, int64_t ldd, int n, int m, int k_dim, float scale,
@@ -180,7 +183,12 @@ CX_API int cx_attn_bwd(const void* qkv, const void* out, const void* dout, const
                 void* dqkv, float* dq_acc, float* delta, int total_tokens, int nseq, int max_seqlen, int H, int Dh,
                 float softmax_scale, cx_stream_t stream);
 
-/* Profiling hook: buf = device int64 [n_ctas, 64] (or NULL to switch off).  While set, the pipelined attention kernels
+/* A/B switch between kernel generations of the attention forward / backward (0 = the default; the generations and what was
+ * measured for each are listed in csrc/cx_attn.cu).  Process-wide; used by tools/bench_attn.py and the parity tests of the
+ * non-default generation. */
+CX_API int cx_attn_select_kernels(int fwd_generation, int bwd_generation);
+
+/* Profiling hook (only in builds with -DCX_DEBUG_HOOKS; an error otherwise): buf = device int64 [n_ctas, 64] (or NULL to switch off).  While set, the pipelined attention kernels
  * record clock64() stamps of their pipeline events per CTA (tools/trace_attn.py decodes them).  Never set in production. */
 CX_API int cx_debug_attn_trace(void* buf);
 

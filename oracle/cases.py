@@ -33,11 +33,18 @@ ENCODER_CASES = {
     "tiny3": dict(vocab=512, n_embd=192, n_head=3, n_inner=512, n_layer=3, seq=130, batch=2, wseed=6, seed=42,
                   rope_base=10000.0, lens=[130, 77]),
 }
+# BASELINE shape: nomic-bert-base, inputs as the reference's own parity test draws them (tests/test_flash_bert.py:52-57:
+# batch 4, seqlen 512, ragged lengths in [256, 512], seed 0)
+ENCODER_BASE_CASE = dict(vocab=30528, n_embd=768, n_head=12, n_inner=3072, n_layer=12, seq=512, batch=4, wseed=0, seed=0,
+                         rope_base=1000.0)
 VIT_CASES = {
     "tiny": dict(n_embd=128, n_head=2, n_inner=256, n_layer=2, img=64, patch=16, act="quick_gelu", batch=3, wseed=8, seed=61),
     "tiny_gelu": dict(n_embd=192, n_head=3, n_inner=384, n_layer=2, img=96, patch=32, act="gelu", batch=2, wseed=9, seed=62),
 }
 GRADCACHE_CASE = dict(n=8, chunk=3, din=16, dout=32, scale=20.0, seed=51)
+# unsaturated variant (loss ~ 1, not 1e-3) whose tower computes in fp32 even under autocast, so the GPU run differs from the
+# reference's fp32 CPU run only by the bf16 rounding of the embeddings entering the fused loss: a tight driver check
+GRADCACHE_SOFT_CASE = dict(n=8, chunk=3, din=16, dout=32, scale=4.0, seed=52, fp32=True)
 
 
 def make_infonce_inputs(case):
@@ -86,6 +93,7 @@ class TinyTower(torch.nn.Module):
     def __init__(self, case):
         super().__init__()
         rs = np.random.RandomState(case["seed"] + 7)
+        self.fp32 = bool(case.get("fp32", False))
         self.fc1 = torch.nn.Linear(case["din"], case["dout"])
         self.fc2 = torch.nn.Linear(case["dout"], case["dout"], bias=False)
         with torch.no_grad():
@@ -98,6 +106,10 @@ class TinyTower(torch.nn.Module):
         return nullcontext()
 
     def forward(self, input_ids):
+        if self.fp32:
+            with torch.autocast(device_type=input_ids.device.type, enabled=False):
+                h = torch.tanh(self.fc1(input_ids.float()))
+                return {"embedding": torch.nn.functional.normalize(self.fc2(h), dim=-1)}
         h = torch.tanh(self.fc1(input_ids))
         return {"embedding": torch.nn.functional.normalize(self.fc2(h), dim=-1)}
 

@@ -113,10 +113,11 @@ def trunk_forward(sd, cfg: EncoderConfig, input_ids, attention_mask=None, token_
     tt = torch.zeros_like(input_ids) if token_type_ids is None else token_type_ids
     h = h + g("embeddings.token_type_embeddings.weight")[tt]
     h = layer_norm(h, g("emb_ln.weight"), g("emb_ln.bias"), cfg.layer_norm_epsilon)
+    dev = input_ids.device  # CPU for the oracle proper; the "plain bf16 run of the same graph" arm of the tests may sit on the GPU
     if attention_mask is None:
-        attention_mask = torch.ones(B, S, dtype=torch.long)
-    bias = torch.zeros(B, 1, 1, S, dtype=dtype).masked_fill(attention_mask[:, None, None, :] == 0, float("-inf"))
-    cos, sin = rotary_cos_sin(S, cfg.head_dim, cfg.rotary_emb_base, dtype)
+        attention_mask = torch.ones(B, S, dtype=torch.long, device=dev)
+    bias = torch.zeros(B, 1, 1, S, dtype=dtype, device=dev).masked_fill(attention_mask[:, None, None, :] == 0, float("-inf"))
+    cos, sin = (t.to(dev) for t in rotary_cos_sin(S, cfg.head_dim, cfg.rotary_emb_base, dtype))
     H, Dh = cfg.n_head, cfg.head_dim
     for i in range(cfg.n_layer):
         p = f"encoder.layers.{i}."

@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 from oracle import ref_loader  # noqa: E402
-from oracle.cases import (INFONCE_CASES, DUAL_CASES, MATRYOSHKA_CASES, ENCODER_CASES, GRADCACHE_CASE,  # noqa: E402
+from oracle.cases import (INFONCE_CASES, DUAL_CASES, MATRYOSHKA_CASES, ENCODER_CASES, GRADCACHE_CASE, GRADCACHE_SOFT_CASE,  # noqa: E402
                           make_infonce_inputs, make_encoder_inputs, make_gradcache_inputs, encoder_cfg,
                           TinyTower)
 from oracle.encoder import random_state_dict  # noqa: E402
@@ -319,5 +319,18 @@ def main():
     gen_vit()
 
 
+def gen_gradcache_soft():
+    """round 2: the unsaturated fp32-tower GradCache fixture (does not touch the other fixtures)."""
+    port = 29490
+    for ws in (1, 2):
+        out = _run(_gradcache_worker, ws, dict(GRADCACHE_SOFT_CASE, ws=ws), port)
+        port += 1
+        np.savez_compressed(os.path.join(GOLDEN, f"gradcache_soft_ws{ws}.npz"), **out)
+        print("gradcache_soft", ws, {k: v.item() for k, v in out.items() if "loss" in k})
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "gradcache_soft":
+        gen_gradcache_soft()
+    else:
+        main()

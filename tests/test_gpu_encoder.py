@@ -67,6 +67,48 @@ def test_embedding_and_grads_vs_oracle(name, hamming):
         crit(trunk.view(trunk.flat_grad(), k), sd32[k].grad, sd16[k].grad, "grad " + k)
 
 
+def test_base_size_tower_vs_oracle():
+    """nomic-bert-base at the shape the bench times (768 wide, 12 heads, 12 layers, 3072 inner, S = 512): the composed sm_100a
+    tower -- pair-CTA 256x256 GEMMs, the 12-head attention grid, the 3072-wide SwiGLU epilogue, fused add-LayerNorm, varlen
+    packing -- against the fp32 CPU oracle by the reference's own criterion (tests/test_flash_bert.py:52-57,77-82: batch 4,
+    seqlen 512, ragged lengths in [256, 512], seed 0; error <= 3x the error of a plain bf16 run of the same graph), for the
+    embedding and EVERY parameter gradient.  The plain-bf16 arm runs the oracle graph in bf16 on the GPU (as the reference's
+    HF-bf16 arm does); the fp32 arm is the CPU oracle."""
+    from oracle.cases import ENCODER_BASE_CASE
+    case = dict(ENCODER_BASE_CASE)
+    torch.manual_seed(case["seed"])
+    lens = torch.randint(case["seq"] // 2, case["seq"] + 1, (case["batch"],))
+    ids_t = torch.randint(0, 30000, (case["batch"], case["seq"]))
+    mask_t = (torch.arange(case["seq"])[None, :] < lens[:, None]).long()
+    g_t = torch.randn(case["batch"], case["n_embd"])
+    model, ocfg, sd = _build(case)
+
+    sd32 = {k: v.clone().requires_grad_() for k, v in sd.items()}
+    e32 = biencoder_forward(sd32, ocfg, ids_t, mask_t)
+    (e32 * g_t).sum().backward()
+    sd16 = {k: v.clone().cuda().requires_grad_() for k, v in sd.items()}
+    e16 = biencoder_forward(sd16, ocfg, ids_t.cuda(), mask_t.cuda(), dtype=torch.bfloat16).float()
+    (e16 * g_t.cuda()).sum().backward()
+
+    out = model(ids_t.cuda(), attention_mask=mask_t.cuda(), seq_lens=lens)["embedding"]
+    (out * g_t.cuda()).sum().backward()
+
+    report = {}
+
+    def crit(mine, ref32, ref16, what):
+        err = (mine.float().cpu() - ref32).abs().max().item()
+        base = (ref16.float().cpu() - ref32).abs().max().item()
+        report[what] = (err, base)
+        assert err <= 3.0 * base + 1e-6 * ref32.abs().max().item(), (what, err, base)
+
+    crit(out.detach(), e32.detach(), e16.detach(), "embedding")
+    trunk = model.trunk
+    for k in sd:
+        crit(trunk.view(trunk.flat_grad(), k), sd32[k].grad, sd16[k].grad, "grad " + k)
+    worst = max(report.items(), key=lambda kv: kv[1][0] / max(kv[1][1], 1e-30))
+    print(f"base-size parity: {len(report)} tensors, worst ratio {worst[1][0] / max(worst[1][1], 1e-30):.2f}x bf16 error at {worst[0]}")
+
+
 def test_seq_lens_hint_and_dense_paths_agree():
     case = ENCODER_CASES["tiny"]
     model, ocfg, sd = _build(case)

@@ -147,10 +147,9 @@ def test_matryoshka_vs_oracle(name):
     loss = matryoshka_clip_loss(qt, dt, ls, case["dims"], case["weights"])
     loss.backward()
     rel_close(loss.item(), o["loss"])
-    # normalised-prefix path stores dS as bf16 (the precision of the reference's own autocast backward); at n = 8
-    # nothing averages the 2^-9 rounding down, hence 4e-3 here (1e-3 holds at realistic sizes, see the C-ABI test)
-    rel_close(qt.grad.cpu().numpy(), o["dq"], rel=4e-3)
-    rel_close(dt.grad.cpu().numpy(), o["dd"], rel=4e-3)
+    # (round 1 held this path to 4e-3: dS was stored as bf16 there; it is fp16 (p - onehot) on every path now)
+    rel_close(qt.grad.cpu().numpy(), o["dq"])
+    rel_close(dt.grad.cpu().numpy(), o["dd"])
     z = golden(f"matryoshka_{name}.npz")
     assert abs(loss.item() - float(z["r0_loss"])) <= 2e-2 * float(z["r0_loss"])
 
@@ -167,9 +166,83 @@ def test_symmetric_clip_loss_vs_oracle():
     loss = symmetric_clip_loss(tt, vt, ls)
     loss.backward()
     rel_close(loss.item(), o["loss"], floor=1e-2)
-    rel_close(tt.grad.cpu().numpy(), o["dtext"], rel=4e-3)
-    rel_close(vt.grad.cpu().numpy(), o["dvision"], rel=4e-3)
+    rel_close(tt.grad.cpu().numpy(), o["dtext"])
+    rel_close(vt.grad.cpu().numpy(), o["dvision"])
     rel_close(ls.logit_scale.grad.item(), o["dlogit"], rel=3e-3, floor=1e-2)
+
+
+def _unit_rows_with_positives(rs, n, m, dim, stride, offset, gain=0.15):
+    q = rs.randn(n, dim)
+    d = rs.randn(m, dim)
+    d[(np.arange(n) + offset) * stride] += gain * q  # unsaturated softmax: fp32 (p - onehot) cancellation does not dominate
+    return q.astype(np.float32), d.astype(np.float32)
+
+
+def test_config4_matryoshka_dims_768_512_256_128_vs_oracle():
+    """BASELINE configs[3]: Matryoshka dims {768, 512, 256, 128}, weights 1 (configs/train/contrastive_matryoshka.yaml), n = 256
+    local queries against m = 256 documents, un-normalised hamming-style embeddings: loss, dQ, dD at 1e-3 of the float64 oracle
+    on the same bf16-rounded inputs; per-prefix accuracy bit-exact."""
+    from contrastors_b200 import LogitScale, matryoshka_clip_loss
+    rs = np.random.RandomState(404)
+    n, dim, dims, weights, scale = 256, 768, [768, 512, 256, 128], [1.0, 1.0, 1.0, 1.0], 50.0
+    q, d = _unit_rows_with_positives(rs, n, n, dim, 1, 0, gain=0.25)
+    q, d = O.bf16_round(q * 1.7), O.bf16_round(d * 0.6)   # LayerNorm-scale rows: the norms matter
+    o = O.matryoshka_loss_fwd_bwd(q, d, scale, dims, weights)
+    qt = torch.tensor(q, device="cuda", requires_grad=True)
+    dt = torch.tensor(d, device="cuda", requires_grad=True)
+    ls = LogitScale(logit_scale=scale, trainable_logit_scale=True).cuda()
+    logged = {}
+
+    class T:
+        def log(self, m_, step=None):
+            logged.update(m_)
+
+    loss = matryoshka_clip_loss(qt, dt, ls, dims, weights, tracker=T(), dataset="x")
+    loss.backward()
+    rel_close(loss.item(), o["loss"])
+    rel_close(qt.grad.cpu().numpy(), o["dq"])
+    rel_close(dt.grad.cpu().numpy(), o["dd"])
+    rel_close(ls.logit_scale.grad.item(), o["dlogit"], rel=3e-3, floor=sum(p["dlogit_abs"] for p in o["per_dim"]) * 1e-1)
+    for dim_k, per in zip(dims, o["per_dim"]):
+        assert abs(logged[f"accuracy/accuracy_x_matryoshka_{dim_k}"] - per["accuracy"]) < 1e-7, dim_k
+
+
+def test_config3_symmetric_loss_rank_shard_512_by_4096_vs_oracle():
+    """BASELINE configs[2] shape class: one rank's half of the symmetric CLIP loss with N = 512 local rows against M = 4096
+    gathered rows (world size 8, this rank = 3): normalisation in the kernel, label offset rank*N, mult = ws / 2.  The
+    public symmetric_clip_loss at ws = 1 (M = N = 512) is checked beside it."""
+    from contrastors_b200 import LogitScale, symmetric_clip_loss
+    from contrastors_b200.loss import _NceSpec, _fused_infonce
+    rs = np.random.RandomState(303)
+    n, ws, rank, dim, scale = 512, 8, 3, 768, 1.0 / 0.07
+    m = n * ws
+    v, t_all = _unit_rows_with_positives(rs, n, m, dim, 1, rank * n, gain=0.3)
+    v, t_all = O.bf16_round(v * 2.5), O.bf16_round(t_all * 0.4)
+    vn, tn = O.l2_normalize(v), O.l2_normalize(t_all)
+    o = O.clip_loss_fwd_bwd(vn, tn, scale, rank, ws, grad_out=0.5)
+    want_dv = O.l2_normalize_bwd(v, o["dq"])
+    want_dt = O.l2_normalize_bwd(t_all, o["dd"])
+    vt = torch.tensor(v, device="cuda", requires_grad=True)
+    tt = torch.tensor(t_all, device="cuda", requires_grad=True)
+    ls = LogitScale(logit_scale=scale, trainable_logit_scale=True).cuda()
+    spec = _NceSpec(label_offset=rank * n, label_stride=1, mult=ws / 2.0, gather=False, normalize=True)
+    loss = _fused_infonce(vt, tt, ls, spec)
+    loss.backward()
+    rel_close(loss.item(), 0.5 * o["loss"], floor=1e-2)
+    rel_close(vt.grad.cpu().numpy(), want_dv)
+    rel_close(tt.grad.cpu().numpy(), want_dt)
+    assert np.array_equal(spec.out[dim]["argmax"].cpu().numpy().astype(np.int64), o["argmax"])
+    # public API, ws = 1
+    t1 = t_all[:n].copy()
+    o1 = O.dual_encoder_loss_fwd_bwd([t1], [v], scale)[0]
+    vt1 = torch.tensor(v, device="cuda", requires_grad=True)
+    tt1 = torch.tensor(t1, device="cuda", requires_grad=True)
+    ls1 = LogitScale(logit_scale=scale, trainable_logit_scale=True).cuda()
+    loss1 = symmetric_clip_loss(tt1, vt1, ls1)
+    loss1.backward()
+    rel_close(loss1.item(), o1["loss"], floor=1e-2)
+    rel_close(tt1.grad.cpu().numpy(), o1["dtext"])
+    rel_close(vt1.grad.cpu().numpy(), o1["dvision"])
 
 
 def test_full_size_properties():
@@ -204,19 +277,19 @@ def test_full_size_properties():
 
 def test_grad_cache_driver_vs_reference_golden():
     """grad_cache_loss with a generic torch tower (the reference's driver contract, loss.py:135-213) against the loss and
-    parameter gradients the reference's own grad_cache_loss produced (tests/golden/gradcache_ws1.npz, fp32 CPU run).
-    The tower's Linear layers run under bf16 autocast here exactly as the reference's do on a GPU, and the loss of this
-    fixture is deeply saturated (1e-3), so agreement with the fp32 CPU golden is limited to ~10 % of the largest entry."""
+    parameter gradients the reference's own grad_cache_loss produced.  Fixture gradcache_soft_ws1.npz (round 2): unsaturated
+    loss (~1.5) and a tower that computes in fp32 under autocast, so the only difference from the reference's fp32 CPU run is
+    the bf16 rounding of the embeddings entering the fused loss: 1 % (round 1's saturated fixture needed 15 %)."""
     from contrastors_b200 import LogitScale, grad_cache_loss
-    from oracle.cases import GRADCACHE_CASE, TinyTower, make_gradcache_inputs
-    case = dict(GRADCACHE_CASE, ws=1)
-    z = golden("gradcache_ws1.npz")
+    from oracle.cases import GRADCACHE_SOFT_CASE, TinyTower, make_gradcache_inputs
+    case = dict(GRADCACHE_SOFT_CASE, ws=1)
+    z = golden("gradcache_soft_ws1.npz")
     tower = TinyTower(case).cuda()
     xq, xd = make_gradcache_inputs(case, 0)
     ls = LogitScale(logit_scale=case["scale"]).cuda()
     loss = grad_cache_loss(tower, {"input_ids": torch.tensor(xq).cuda()}, tower, {"input_ids": torch.tensor(xd).cuda()},
                            case["chunk"], ls)
-    assert abs(loss.item() - float(z["r0_loss"])) <= 0.15 * max(float(z["r0_loss"]), 1e-2) + 2e-3
+    assert abs(loss.item() - float(z["r0_loss"])) <= 1e-2 * float(z["r0_loss"])
     for k, p in tower.named_parameters():
         ref = z["r0_gc_" + k]
-        assert np.abs(p.grad.cpu().numpy() - ref).max() <= 0.15 * np.abs(ref).max() + 1e-5, k
+        assert np.abs(p.grad.cpu().numpy() - ref).max() <= 1e-2 * np.abs(ref).max() + 1e-6, k

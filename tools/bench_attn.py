@@ -40,7 +40,7 @@ for name, nseq, S, H in [("bert_64x512", 64, 512, 12), ("vit_256x197", 256, 197,
     scale = 1.0 / math.sqrt(Dh)
     ref_out = ref_dqkv = None
     for fm, bm in MODES:
-        os.environ["CX_ATTN_FWD"], os.environ["CX_ATTN_BWD"] = str(fm), str(bm)
+        ops.attn_select_kernels(fm, bm)
         try:
             out, lse = ops.attn_fwd(qkv, cu, S, H, Dh, scale)
             dqkv = ops.attn_bwd(qkv, out, dout, lse, cu, S, H, Dh, scale)
@@ -58,5 +58,24 @@ for name, nseq, S, H in [("bert_64x512", 64, 512, 12), ("vit_256x197", 256, 197,
         except Exception as ex:  # keep going: the other generations are still informative
             res[f"{name}_fwd{fm}_bwd{bm}"] = dict(error=str(ex))
         print(name, fm, bm, res[f"{name}_fwd{fm}_bwd{bm}"], flush=True)
+    # the kernel the reference calls (layers/attention.py:158-181): FlashAttention-2 varlen qkv-packed, same shape, same box
+    try:
+        from flash_attn import flash_attn_varlen_qkvpacked_func
+        q3 = qkv.view(T, 3, H, Dh).clone().requires_grad_()
+        o = flash_attn_varlen_qkvpacked_func(q3, cu, S, 0.0, softmax_scale=scale, causal=False)
+        o.backward(dout.view(T, H, Dh))
+        f = timeit(lambda: flash_attn_varlen_qkvpacked_func(q3.detach(), cu, S, 0.0, softmax_scale=scale, causal=False))
+
+        def fa2_fb():
+            q3.grad = None
+            flash_attn_varlen_qkvpacked_func(q3, cu, S, 0.0, softmax_scale=scale, causal=False).backward(dout.view(T, H, Dh))
+        fb = timeit(fa2_fb)
+        err = (o.detach().reshape(T, H * Dh).float() - ref_out).abs().max().item() if ref_out is not None else None
+        res[f"{name}_flash_attn2"] = dict(fwd_ms=f, fwd_tflops=4.0 * T * S * H * Dh / f / 1e9, fwd_plus_bwd_ms=fb,
+                                          bwd_ms_by_difference=fb - f, bwd_tflops=10.0 * T * S * H * Dh / max(fb - f, 1e-6) / 1e9,
+                                          max_abs_out_vs_ours=err)
+    except Exception as ex:
+        res[f"{name}_flash_attn2"] = dict(error=f"{type(ex).__name__}: {ex}"[:200])
+    print(name, "flash_attn2", res[f"{name}_flash_attn2"], flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open(f"gpurun_out/bench_attn_{TAG}.json", "w"), indent=1)
