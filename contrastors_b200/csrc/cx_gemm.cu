@@ -3,6 +3,9 @@
 
 #include <stdlib.h>
 
+#include <atomic>
+#include <mutex>
+
 namespace cx {
 
 int gemm_block_n(int N) { return (N % 256 == 0) ? 256 : 128; }
@@ -18,33 +21,57 @@ int gemm_grid(int M, int N, int splits, int tile_n) {
 // with 128 x 256 tiles is shared-memory-bandwidth bound (48 KB read by the MMA + 48 KB written by TMA per 512-cycle
 // k-block = 192 B/clk against a 128 B/clk port); the pair stages each B half once per SM pair (64 KB per k-block per SM =
 // 128 B/clk), measured +8..12 % over the single-CTA kernel (8192^3: 1.46 vs 1.30 PFLOP/s).  CX_NO_PAIR=1 disables it.
+static std::atomic<int> g_max_cluster{0};  // A/B switch (cx_gemm_select_cluster): 0 = default, else the largest cluster used
 bool gemm_use_pair(const GemmArgs& g) {
   static const bool disabled = getenv("CX_NO_PAIR") != nullptr;
-  return !disabled && g.M >= 256 && ((g.mode == EPI_SWIGLU) || g.N % 256 == 0);
+  const int cap = g_max_cluster.load(std::memory_order_relaxed);
+  return !disabled && (cap == 0 || cap >= 2) && g.M >= 256 && ((g.mode == EPI_SWIGLU) || g.N % 256 == 0);
 }
 
-template <int MODE, bool OUT_F32, bool ACCUM, bool A_MN, bool B_MN>
+// QUAD (a cluster of two CTA pairs sharing their B tile through TMA multicast, see cx_gemm.cuh): for the M = tokens GEMMs of the
+// encoder (forward, dgrad).  CX_NO_QUAD=1 falls back to plain pairs.
+bool gemm_use_quad(const GemmArgs& g) {
+  static const bool disabled = getenv("CX_NO_QUAD") != nullptr;
+  const int cap = g_max_cluster.load(std::memory_order_relaxed);
+  return !disabled && (cap == 0 || cap >= 4) && gemm_use_pair(g) && g.M % 512 == 0 &&
+         (g.mode == EPI_STORE || g.mode == EPI_SWIGLU || g.mode == EPI_SWIGLU_BWD);
+}
+
+template <int MODE, bool OUT_F32, bool ACCUM, bool A_MN, bool B_MN, int NP>
 static int launch_pair(const GemmArgs& g, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                        const CUtensorMap& tmD) {
-  auto kern = gemm_kernel<256, A_MN, B_MN, MODE, OUT_F32, ACCUM, true>;
+  auto kern = gemm_kernel<256, A_MN, B_MN, MODE, OUT_F32, ACCUM, true, NP>;
   constexpr int smem = GemmSmem<256, true>::kTotal;
   CX_SET_SMEM_ONCE(kern, smem);
   const int tile_n = (MODE == EPI_SWIGLU) ? 128 : 256;
-  const int tiles = ((g.M + 255) / 256) * ((g.N + tile_n - 1) / tile_n) * g.splits;
-  int clusters = sm_count() / 2;
-  if (tiles < clusters) clusters = tiles;
+  const int tile_m = 256 * NP;
+  const int tiles = ((g.M + tile_m - 1) / tile_m) * ((g.N + tile_n - 1) / tile_n) * g.splits;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * clusters);
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = g.stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.x = 2 * NP;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  int clusters = sm_count() / (2 * NP);
+  if (NP > 1) {
+    // 4-CTA clusters must fit inside a GPC: ask the driver how many can be co-resident (once per instantiation)
+    static std::once_flag once;
+    static int max_clusters = 0;
+    std::call_once(once, [&] {
+      cfg.gridDim = dim3(2 * NP * clusters);
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) max_clusters = n;
+      (void)cudaGetLastError();
+    });
+    if (max_clusters > 0 && max_clusters < clusters) clusters = max_clusters;
+  }
+  if (tiles < clusters) clusters = tiles;
+  cfg.gridDim = dim3(2 * NP * clusters);
   CX_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmD, g.M, g.N, g.K, g.splits, g.ep));
   CX_LAUNCH_CHECK();
   return 0;
@@ -53,7 +80,10 @@ static int launch_pair(const GemmArgs& g, const CUtensorMap& tmA, const CUtensor
 template <int BLOCK_N, bool A_MN, bool B_MN, int MODE, bool OUT_F32, bool ACCUM>
 static int launch_one(const GemmArgs& g, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                       const CUtensorMap& tmD) {
-  if (BLOCK_N == 256 && gemm_use_pair(g)) return launch_pair<MODE, OUT_F32, ACCUM, A_MN, B_MN>(g, tmA, tmB, tmC, tmD);
+  if (BLOCK_N == 256 && gemm_use_pair(g)) {
+    if ((MODE == EPI_STORE || MODE == EPI_SWIGLU || MODE == EPI_SWIGLU_BWD) && gemm_use_quad(g)) return launch_pair<MODE, OUT_F32, ACCUM, A_MN, B_MN, 2>(g, tmA, tmB, tmC, tmD);
+    return launch_pair<MODE, OUT_F32, ACCUM, A_MN, B_MN, 1>(g, tmA, tmB, tmC, tmD);
+  }
   auto kern = gemm_kernel<BLOCK_N, A_MN, B_MN, MODE, OUT_F32, ACCUM>;
   constexpr int smem = GemmSmem<BLOCK_N>::kTotal;
   CX_SET_SMEM_ONCE(kern, smem);  // per instantiation
@@ -66,7 +96,10 @@ static int launch_one(const GemmArgs& g, const CUtensorMap& tmA, const CUtensorM
 template <int BLOCK_N, int MODE, bool OUT_F32, bool ACCUM>
 static int launch_majors(const GemmArgs& g, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
                          const CUtensorMap& d) {
-  if (MODE != EPI_STORE) {  // the fused epilogues only exist for K-major operands
+  if constexpr (MODE == EPI_SWIGLU_BWD) {  // the fc2 dgrad: A = d(out) K-major, B = fc2.weight [d, I] = MN-major; CTA pairs only
+    if (g.a_mn || !g.b_mn || BLOCK_N != 256 || !gemm_use_pair(g)) return fail(CX_ERR_UNSUPPORTED, "swiglu-bwd epilogue: K-major A, MN-major B, M >= 256");
+    return launch_one<256, false, true, EPI_SWIGLU_BWD, false, false>(g, a, b, c, d);
+  } else if constexpr (MODE != EPI_STORE) {  // the other fused epilogues only exist for K-major operands
     if (g.a_mn || g.b_mn) return fail(CX_ERR_UNSUPPORTED, "fused epilogues need K-major operands");
     return launch_one<BLOCK_N, false, false, MODE, OUT_F32, ACCUM>(g, a, b, c, d);
   } else {
@@ -87,6 +120,9 @@ static int launch_bn(const GemmArgs& g, const CUtensorMap& a, const CUtensorMap&
     case EPI_SWIGLU:
       if (BLOCK_N != 256) return fail(CX_ERR_INVALID, "swiglu epilogue uses 256-column accumulators");
       return launch_majors<256, EPI_SWIGLU, false, false>(g, a, b, c, d);
+    case EPI_SWIGLU_BWD:
+      if (BLOCK_N != 256) return fail(CX_ERR_INVALID, "swiglu-bwd epilogue uses 256-column accumulators");
+      return launch_majors<256, EPI_SWIGLU_BWD, false, false>(g, a, b, c, d);
     case EPI_STORE:
       if (!g.out_f32) return launch_majors<BLOCK_N, EPI_STORE, false, false>(g, a, b, c, d);
       if (!g.accumulate) return launch_majors<BLOCK_N, EPI_STORE, true, false>(g, a, b, c, d);
@@ -129,8 +165,9 @@ int launch_gemm(const GemmArgs& g_in) {
   else rc = make_tmap_2d(&tmA, BF, 2, g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda * 2, 64, kBlockK, SW);
   if (rc) return rc;
   const bool pair = (bn == 256) && gemm_use_pair(g);
-  if (g.mode == EPI_SWIGLU) rc = make_tmap_2d(&tmB, BF, 2, g.B, (uint64_t)g.K, (uint64_t)2 * g.N, (uint64_t)g.ldb * 2, kBlockK, 128, SW);
-  else if (!g.b_mn) rc = make_tmap_2d(&tmB, BF, 2, g.B, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb * 2, kBlockK, pair ? 128u : (uint32_t)bn, SW);
+  const bool quad = pair && gemm_use_quad(g);  // each CTA fetches 64 of its 128 B rows and multicasts them
+  if (g.mode == EPI_SWIGLU) rc = make_tmap_2d(&tmB, BF, 2, g.B, (uint64_t)g.K, (uint64_t)2 * g.N, (uint64_t)g.ldb * 2, kBlockK, quad ? 64u : 128u, SW);
+  else if (!g.b_mn) rc = make_tmap_2d(&tmB, BF, 2, g.B, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb * 2, kBlockK, quad ? 64u : (pair ? 128u : (uint32_t)bn), SW);
   else rc = make_tmap_2d(&tmB, BF, 2, g.B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb * 2, 64, kBlockK, SW);
   if (rc) return rc;
   CUtensorMap tmD;
@@ -139,6 +176,10 @@ int launch_gemm(const GemmArgs& g_in) {
     if (rc) return rc;
     if (g.ep.yg_out != nullptr)
       rc = make_tmap_2d(&tmD, BF, 2, g.ep.yg_out, (uint64_t)2 * g.N, (uint64_t)g.M, (uint64_t)g.ep.ld_yg * 2, 64, kBlockM, SW);
+  } else if (g.mode == EPI_SWIGLU_BWD) {  // tmC: dyg [M, 2N] (stores), tmD: yg [M, 2N] (loads); 64-column x 128-row boxes
+    rc = make_tmap_2d(&tmC, BF, 2, g.C, (uint64_t)2 * g.N, (uint64_t)g.M, (uint64_t)g.ldc * 2, 64, kBlockM, SW);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tmD, BF, 2, g.ep.yg_out, (uint64_t)2 * g.N, (uint64_t)g.M, (uint64_t)g.ep.ld_yg * 2, 64, kBlockM, SW);
   } else if (g.mode == EPI_NCE_STATS) {
     tmC = tmA;
   } else if (g.out_f32) {
@@ -147,11 +188,18 @@ int launch_gemm(const GemmArgs& g_in) {
     rc = make_tmap_2d(&tmC, BF, 2, g.C, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldc * 2, 64, kBlockM, SW);
   }
   if (rc) return rc;
-  if (g.mode != EPI_SWIGLU || g.ep.yg_out == nullptr) tmD = tmC;
+  if (g.mode != EPI_SWIGLU_BWD && (g.mode != EPI_SWIGLU || g.ep.yg_out == nullptr)) tmD = tmC;
   return bn == 256 ? launch_bn<256>(g, tmA, tmB, tmC, tmD) : launch_bn<128>(g, tmA, tmB, tmC, tmD);
 }
 
 }  // namespace cx
+
+extern "C" int cx_gemm_select_cluster(int max_cluster_ctas) {
+  CX_REQUIRE(max_cluster_ctas == 0 || max_cluster_ctas == 1 || max_cluster_ctas == 2 || max_cluster_ctas == 4,
+             "cx_gemm_select_cluster: 0 (default), 1 (single CTA), 2 (CTA pairs) or 4 (two pairs sharing B by multicast)");
+  cx::g_max_cluster.store(max_cluster_ctas, std::memory_order_relaxed);
+  return 0;
+}
 
 extern "C" int cx_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int a_major, int b_major,
                             int64_t lda, int64_t ldb, int64_t ldc, int c_dtype, int accumulate, float alpha,
@@ -187,6 +235,28 @@ extern "C" int cx_gemm_swiglu(const void* x, const void* w1, void* act_out, void
   g.ep.act_out = reinterpret_cast<__nv_bfloat16*>(act_out);
   g.ep.ld_act = ld_act;
   g.ep.yg_out = reinterpret_cast<__nv_bfloat16*>(yg_out);
+  g.ep.ld_yg = ld_yg;
+  g.stream = static_cast<cudaStream_t>(stream);
+  return cx::launch_gemm(g);
+}
+
+// d[y | gate] = SwiGLU'(d(out) fc2) with the activation backward in the fc2-dgrad epilogue (replaces the dgrad GEMM + the
+// swiglu backward of flash-attn's `swiglu`, layers/mlp.py:75; autograd of y * silu(gate)).  dout [M, K = d], w2 = fc2.weight
+// [K = d, I] row-major, yg / dyg [M, 2 I] = [y | gate] and their gradients.
+extern "C" int cx_gemm_swiglu_bwd(const void* dout, const void* w2, const void* yg, void* dyg, int M, int I, int K, int64_t ld_dout,
+                                  int64_t ld_w2, int64_t ld_yg, int64_t ld_dyg, cx_stream_t stream) {
+  CX_REQUIRE(dout && w2 && yg && dyg, "cx_gemm_swiglu_bwd: null pointer");
+  CX_REQUIRE(I % 256 == 0 && M >= 256, "cx_gemm_swiglu_bwd: gated width a multiple of 256, at least 256 rows (cx_gemm_bf16 + cx_swiglu_bwd otherwise)");
+  CX_REQUIRE(ld_yg % 8 == 0 && ld_dyg % 8 == 0, "cx_gemm_swiglu_bwd: rows must be 16-byte aligned");
+  cx::GemmArgs g{};
+  g.A = dout; g.B = w2; g.C = dyg;
+  g.M = M; g.N = I; g.K = K;
+  g.a_mn = false; g.b_mn = true;
+  g.lda = ld_dout; g.ldb = ld_w2; g.ldc = ld_dyg;
+  g.out_f32 = false; g.accumulate = false; g.splits = 1;
+  g.mode = cx::EPI_SWIGLU_BWD;
+  g.ep.alpha = 1.f;
+  g.ep.yg_out = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(yg));
   g.ep.ld_yg = ld_yg;
   g.stream = static_cast<cudaStream_t>(stream);
   return cx::launch_gemm(g);

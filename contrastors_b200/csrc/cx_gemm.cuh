@@ -17,6 +17,10 @@
 //   EPI_NCE_STATS  InfoNCE forward: per-row (max, sum-exp, first-argmax, label logit) partials per column tile
 //   EPI_SWIGLU     gated MLP first layer: B tile = 128 rows of fc11 (y) + the matching 128 rows of fc12 (gate);
 //                  epilogue writes out = y * silu(gate) (bf16 [M, N]) and optionally the pre-activations [y | gate]
+//   EPI_SWIGLU_BWD gated MLP backward: acc = d(act) tile (the fc2 dgrad GEMM, N = gated width I); the epilogue TMA-loads the
+//                  matching [y | gate] pre-activation tiles, forms dy = da silu(g), dg = da y silu'(g) in place and TMA-stores
+//                  both into dyg [M, 2N]: the d(act) tensor never exists in HBM and the separate swiglu_bwd pass (1.0 GB of
+//                  traffic per layer at T = 32768) is gone
 //   EPI_NCE_DS     InfoNCE backward stage 1: dS = softmax - onehot stored UNSCALED as fp16, plus
 //                  per-thread partial of sum dS*s (the logit-scale gradient)
 #pragma once
@@ -25,7 +29,7 @@
 
 namespace cx {
 
-enum EpiMode { EPI_STORE = 0, EPI_NCE_STATS = 1, EPI_NCE_DS = 2, EPI_SWIGLU = 3 };
+enum EpiMode { EPI_STORE = 0, EPI_NCE_STATS = 1, EPI_NCE_DS = 2, EPI_SWIGLU = 3, EPI_SWIGLU_BWD = 4 };
 
 struct EpiParams {
   float alpha = 1.f;
@@ -67,6 +71,12 @@ constexpr int kUmmaK = 16;
 constexpr int kGemmThreads = 384;  // 4 control warps + 8 epilogue warps (2 per SMSP: TLP hides TMEM-load latency)
 constexpr int kStageCBytes = 16384;  // 128 rows x 128 B
 
+// NP = 2 (QUAD): a cluster of FOUR CTAs = two such pairs stacked in M (a 512 x 256 super tile).  The pairs need the same B
+// tile, so each B half (128 rows) is fetched ONCE per cluster: the two CTAs that hold the same half each load 64 of its rows
+// and TMA-multicast them to both.  Why: the 256 x 256 pair kernel moves 64 KB from L2 per 512-clk k-block per SM pair =
+// 6.3 KB/clk over the chip, which is the measured L2->SM cap (B300_MICROARCH.md "LTS throughput cap ~6300 B/cyc";
+// profiles/r01_gemm_final_ncu_full_raw.csv: l1tex__m_xbar2l1tex_read_bytes 10.3 TB/s at 1.64 GHz) -- the GEMM was L2-bound, not
+// tensor-bound.  Sharing B cuts that traffic by a quarter (48 KB per pair per k-block).
 // PAIR: two CTAs of a cluster cooperate on one 256 x 256 tile (tcgen05 cta_group::2): each CTA stages its own 128 rows of
 // A and 128 of the 256 B rows (so the B operand is read from shared memory once per SM pair), the leader CTA issues the
 // MMAs for both, each CTA drains the 128 x 256 half of the accumulator that lives in its own TMEM.
@@ -83,16 +93,21 @@ struct GemmSmem {
   static constexpr int kTotal = 1024 + kStages * kStageBytes + kCBufs * kStageCBytes + kBarrierBytes;
 };
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int MODE, bool OUT_F32, bool ACCUM, bool PAIR = false>
+template <int BLOCK_N, bool A_MN, bool B_MN, int MODE, bool OUT_F32, bool ACCUM, bool PAIR = false, int NP = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD, int M, int N, int K,
             int splits, EpiParams ep) {
   using S = GemmSmem<BLOCK_N, PAIR>;
   static_assert(!PAIR || BLOCK_N == 256, "CTA pairs use 256-column tiles");
+  static_assert(NP == 1 || (NP == 2 && PAIR), "a quad cluster is two CTA pairs");
+  constexpr bool QUAD = NP == 2;
   constexpr int kStages = S::kStages;
-  constexpr int TILE_M = PAIR ? 2 * kBlockM : kBlockM;  // rows per work item
-  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  constexpr int TILE_M = (PAIR ? 2 * kBlockM : kBlockM) * NP;  // rows per work item (the whole cluster's)
+  const uint32_t cluster_rank = PAIR ? cluster_ctarank() : 0u;
+  const uint32_t cta_rank = cluster_rank & 1u;      // rank within the CTA pair (0 = the leader that issues the MMAs)
+  const uint32_t pair_id = cluster_rank >> 1;       // which pair of the cluster (always 0 unless QUAD)
+  const int pair_m = (int)pair_id * 2 * kBlockM;    // row offset of this pair inside the work item
   const int tile_start = PAIR ? (int)cluster_id_x() : (int)blockIdx.x;
   const int tile_step = PAIR ? (int)num_clusters_x() : (int)gridDim.x;
   constexpr uint32_t kTmemCols = 2 * BLOCK_N;
@@ -120,17 +135,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (MODE != EPI_NCE_STATS) tma_prefetch_desc(&tmC);
-    if (MODE == EPI_SWIGLU) tma_prefetch_desc(&tmD);
+    if (MODE == EPI_SWIGLU || MODE == EPI_SWIGLU_BWD) tma_prefetch_desc(&tmD);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);   // pair: only the leader arrives (expect_tx covers both CTAs' bytes; a peer arrive per
                                     // k-block would put a cluster-scope release fence on the producer's critical path)
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], NP);  // one commit per pair leader: with multicast loads a stage is shared by both pairs
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], PAIR ? 257 : 256);  // pair: the leader's 256 epilogue threads + ONE forwarded arrive from the peer
+    }
+    if (MODE == EPI_SWIGLU_BWD) {  // one "pre-activation tiles landed" barrier per epilogue group
+      mbar_init(bars + 16, 1);
+      mbar_init(bars + 17, 1);
     }
     fence_barrier_init();
   }
@@ -154,7 +173,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       //  SLOWER on B200: 1.35 vs 1.46 PFLOP/s at 8192^3, so the ring loads are the only TMA traffic)
       for (int tile = tile_start; tile < num_tiles; tile += tile_step) {
         const int mn = tile / splits, ks = tile % splits;
-        const int m0 = (mn / n_tiles) * TILE_M + (int)cta_rank * kBlockM;
+        const int m0 = (mn / n_tiles) * TILE_M + pair_m + (int)cta_rank * kBlockM;
         const int n0 = (mn % n_tiles) * TILE_N;
         const int kb0 = (int)((long long)ks * num_kb / splits), kb1 = (int)((long long)(ks + 1) * num_kb / splits);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -174,7 +193,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             // this CTA's half of the B rows: pair rank r stages rows [n0 + 128 r, +128) (SwiGLU: r = 0 -> fc11, r = 1 -> fc12)
             const int nb = (MODE == EPI_SWIGLU) ? n0 + (int)cta_rank * N : n0 + (int)cta_rank * (BLOCK_N / 2);
-            if (!B_MN) {
+            if (QUAD) {
+              // this CTA and the CTA of the same pair rank in the other pair hold the same 128 B rows: each fetches 64 of them
+              // (8 KB: rows [64 p, +64) K-major / the p-th 64-column atom MN-major) and multicasts to both
+              const uint16_t mc = (uint16_t)((1u << cta_rank) | (1u << (2u + cta_rank)));
+              if (!B_MN) tma_load_2d_2sm_mc(sB + pair_id * 8192, &tmB, lead_bar, kb * kBlockK, nb + (int)pair_id * 64, mc);
+              else tma_load_2d_2sm_mc(sB + pair_id * 8192, &tmB, lead_bar, nb + (int)pair_id * 64, kb * kBlockK, mc);
+            } else if (!B_MN) {
               tma_load_2d_2sm(sB, &tmB, lead_bar, kb * kBlockK, nb);
             } else {
 #pragma unroll
@@ -211,7 +236,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ------------------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
     if (cta_rank == 0) {  // pair: only the leader CTA issues (for both)
       // a_format [7,10) / b_format [10,13): 1 = bf16, 0 = f16
-      const uint32_t idesc = make_idesc_bf16(TILE_M, BLOCK_N, A_MN ? 1u : 0u, B_MN ? 1u : 0u) & ~(ep.ab_f16 ? ((1u << 7) | (1u << 10)) : 0u);
+      const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * kBlockM : kBlockM, BLOCK_N, A_MN ? 1u : 0u, B_MN ? 1u : 0u) & ~(ep.ab_f16 ? ((1u << 7) | (1u << 10)) : 0u);
+      const uint16_t all_ctas = QUAD ? 0xF : 0x3;                     // a consumed stage is released in every CTA of the cluster
+      const uint16_t my_pair = (uint16_t)(0x3u << (2u * pair_id));    // the accumulator-ready signal stays inside the pair
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -240,8 +267,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               else umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             }
             if (PAIR) {
-              umma_commit_2cta(&empty_bar[stage]);
-              if (kb == kb1 - 1) umma_commit_2cta(&tfull_bar[acc]);
+              umma_commit_2cta(&empty_bar[stage], all_ctas);
+              if (kb == kb1 - 1) umma_commit_2cta(&tfull_bar[acc], my_pair);
             } else {
               umma_commit(&empty_bar[stage]);
               if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
@@ -276,6 +303,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }                                                                \
   cb = (kPing == 2) ? (cb ^ 1) : 0;
     int it = 0;
+    uint32_t ld_phase = 0;  // EPI_SWIGLU_BWD: parity of this group's pre-activation-load barrier
     float dl0 = 0.f, dl1 = 0.f, dl2 = 0.f, dl3 = 0.f;  // sum p*t (log2 domain) for the logit-scale gradient
     const float ep_scale = ep.scale * (ep.scale_dev != nullptr ? *ep.scale_dev : 1.f);
     const float ep_coef = ep.coef * (ep.coef_dev != nullptr ? *ep.coef_dev : 1.f);
@@ -285,7 +313,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t acc_phase = (it >> 1) & 1;
       const int mn = tile / splits;
       const int mt = mn / n_tiles, nt = mn % n_tiles;
-      const int m0 = mt * TILE_M + (int)cta_rank * kBlockM, n0 = (MODE == EPI_SWIGLU) ? nt * TILE_N + hf * (TILE_N / 2) : nt * BLOCK_N + hf * HALF_N;
+      const int m0 = mt * TILE_M + pair_m + (int)cta_rank * kBlockM, n0 = (MODE == EPI_SWIGLU) ? nt * TILE_N + hf * (TILE_N / 2) : nt * BLOCK_N + hf * HALF_N;
       const int row = m0 + row_in_tile;
       const bool row_ok = row < M;
       // fast path: no column masks and no per-column scale anywhere in this tile
@@ -303,6 +331,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (MODE == EPI_NCE_DS) lse2 = row_ok ? ep.lse[row] * kLog2e : INFINITY;  // +inf => p == 0 for rows past M
       }
 
+      if (MODE == EPI_SWIGLU_BWD && etid == 0) {
+        // request this tile's first [y | gate] tiles while its MMAs are still running: the staging pair is free once the previous
+        // tile's last stores have read it
+        tma_store_wait_read<0>();
+        mbar_arrive_expect_tx(bars + 16 + hf, 2 * kStageCBytes);
+        tma_load_2d(stage_base, &tmD, bars + 16 + hf, n0, m0);
+        tma_load_2d(stage_base + kStageCBytes, &tmD, bars + 16 + hf, N + n0, m0);
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N + hf * HALF_N;
@@ -352,6 +388,56 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (etid == 0) {
             if (pass == 0) tma_store_2d(&tmC, stage_c, n0, m0);
             else tma_store_2d(&tmD, stage_c, (pass == 2 ? N : 0) + n0, m0);
+            tma_store_commit();
+          }
+        }
+      } else if (MODE == EPI_SWIGLU_BWD) {
+        // this group owns d(act) columns [n0, n0 + 128): two 64-column steps, each transforming one y tile and one gate tile
+        // (128 rows x 128 B, swizzled exactly as TMA wrote them) IN PLACE; a thread only ever touches its own row
+        uint8_t* const buf_y = stage_base;
+        uint8_t* const buf_g = stage_base + kStageCBytes;
+        uint64_t* const ld_bar = bars + 16 + hf;
+#pragma unroll 1
+        for (int pr = 0; pr < 2; ++pr) {
+          const int col0 = n0 + pr * 64;
+          if (pr > 0 && etid == 0) {  // the first step's tiles were requested before the accumulator wait
+            tma_store_wait_read<0>();
+            mbar_arrive_expect_tx(ld_bar, 2 * kStageCBytes);
+            tma_load_2d(buf_y, &tmD, ld_bar, col0, m0);
+            tma_load_2d(buf_g, &tmD, ld_bar, N + col0, m0);
+          }
+          uint32_t v1[32], v2[32];
+          tmem_ld_32x32(taddr + pr * 64, v1);
+          tmem_ld_32x32(taddr + pr * 64 + 32, v2);
+          mbar_wait(ld_bar, ld_phase);
+          ld_phase ^= 1u;
+          tmem_ld_wait();
+          uint8_t* const ry = buf_y + row_in_tile * 128;
+          uint8_t* const rg = buf_g + row_in_tile * 128;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int off = (q ^ (row_in_tile & 7)) << 4;
+            const uint4 y4 = *reinterpret_cast<const uint4*>(ry + off);
+            const uint4 g4 = *reinterpret_cast<const uint4*>(rg + off);
+            const uint32_t yw[4] = {y4.x, y4.y, y4.z, y4.w}, gw[4] = {g4.x, g4.y, g4.z, g4.w};
+            uint32_t oy[4], og[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 yv = unpack_bf16x2(yw[e]), gv = unpack_bf16x2(gw[e]);
+              const int j = (q & 3) * 8 + 2 * e;
+              const float d0 = __uint_as_float(q < 4 ? v1[j] : v2[j]) * ep_alpha, d1 = __uint_as_float(q < 4 ? v1[j + 1] : v2[j + 1]) * ep_alpha;
+              const float s0 = __fdividef(1.f, 1.f + fast_exp2(-gv.x * kLog2e)), s1 = __fdividef(1.f, 1.f + fast_exp2(-gv.y * kLog2e));
+              oy[e] = pack_bf16x2(d0 * gv.x * s0, d1 * gv.y * s1);
+              og[e] = pack_bf16x2(d0 * yv.x * (s0 * (1.f + gv.x * (1.f - s0))), d1 * yv.y * (s1 * (1.f + gv.y * (1.f - s1))));
+            }
+            *reinterpret_cast<uint4*>(ry + off) = make_uint4(oy[0], oy[1], oy[2], oy[3]);
+            *reinterpret_cast<uint4*>(rg + off) = make_uint4(og[0], og[1], og[2], og[3]);
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1 + hf, 128);
+          if (etid == 0) {
+            tma_store_2d(&tmC, buf_y, col0, m0);
+            tma_store_2d(&tmC, buf_g, N + col0, m0);
             tma_store_commit();
           }
         }
@@ -583,7 +669,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // peer CTA: gather its 256 epilogue threads locally, then ONE remote arrive (256 remote arrives per tile would
         // serialise on the cluster interconnect)
         named_bar_sync(3, 256);
-        if (threadIdx.x == 128) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+        if (threadIdx.x == 128) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), cluster_rank & ~1u));
       } else if (PAIR) {
         mbar_arrive(&tempty_bar[acc]);
       } else {

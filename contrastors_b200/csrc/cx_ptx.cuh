@@ -252,12 +252,21 @@ __device__ __forceinline__ void umma_f16_ss_2cta(uint32_t d_tmem, uint64_t a_des
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// commit: arrive on the mbarrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
-  const uint16_t mask = 3;
+// commit: arrive on the mbarrier at this offset in every CTA of `mask` (default: BOTH CTAs of the pair 0/1)
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t mask = 3) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"(mask)
                : "memory");
+}
+// 2-SM TMA load MULTICAST to the CTAs of `cta_mask` (same CTA-relative smem offset in each); the transaction bytes of every
+// destination are credited to the mbarrier at the same offset in that destination's pair LEADER (the address carries the
+// cleared peer bit, as in tma_load_2d_2sm)
+__device__ __forceinline__ void tma_load_2d_2sm_mc(void* smem_dst, const CUtensorMap* m, uint32_t leader_bar_addr, int32_t c0, int32_t c1,
+                                                   uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar_addr), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
 }
 
 // ---------------------------------------------------------------- descriptors

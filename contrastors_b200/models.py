@@ -267,9 +267,11 @@ class _TrunkFn(torch.autograd.Function):
             r = ops.add_layernorm_bwd(m, h1, g_a, g_b, v(P, p + "norm2.weight"), st2, v(G, p + "norm2.weight"),
                                       v(G, p + "norm2.bias"), p_drop=pdrop, seed=site(2 + 2 * i))
             dz2, dm = r if pdrop > 0 else (r, r)
-            da = ops.gemm(dm, v(W, p + "mlp.fc2.weight"), b_major=MAJOR_MN)
+            if cfg.n_inner % 256 == 0 and dm.shape[0] >= 256:  # SwiGLU backward fused into the fc2-dgrad epilogue
+                dyg = ops.gemm_swiglu_bwd(dm, v(W, p + "mlp.fc2.weight"), yg)
+            else:
+                dyg = ops.swiglu_bwd(ops.gemm(dm, v(W, p + "mlp.fc2.weight"), b_major=MAJOR_MN), yg)
             ops.gemm(dm, a, a_major=MAJOR_MN, b_major=MAJOR_MN, out=v(G, p + "mlp.fc2.weight"), accumulate=True)
-            dyg = ops.swiglu_bwd(da, yg)
             w1 = _w1(model, W, i)
             dh1 = ops.gemm(dyg, w1, b_major=MAJOR_MN)
             ops.gemm(dyg, h1, a_major=MAJOR_MN, b_major=MAJOR_MN, out=_w1(model, G, i), accumulate=True)

@@ -66,6 +66,11 @@ def _require_cuda(*ts):
             raise RuntimeError("contrastors_b200 ops run on a B200 only: got a CPU tensor (no CPU fallback exists)")
 
 
+def gemm_select_cluster(max_cluster_ctas=0):
+    """A/B switch of the GEMM launch mode (0 = default, 1 = single CTA, 2 = CTA pairs, 4 = pairs sharing B by multicast)."""
+    _lib.check(_lib.load().cx_gemm_select_cluster(int(max_cluster_ctas)), "cx_gemm_select_cluster")
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_major=MAJOR_K, b_major=MAJOR_K, out=None, out_dtype=torch.bfloat16,
          accumulate=False, alpha=1.0):
     """C[M,N] (+)= alpha * A (x) B on tcgen05.  a: [M,K] (K-major) or [K,M] (MN-major); b: [N,K] or [K,N]."""
@@ -119,6 +124,23 @@ def gemm_swiglu(x, w1, keep_preact=True):
     if ev is not None:
         TIMER.end("gemm", 2.0 * M * 2 * I * K, ev)
     return act, yg
+
+
+def gemm_swiglu_bwd(dout, w2, yg):
+    """dyg [M, 2I] = gradient of [y | gate] given dout [M, d] (gradient of the MLP output) and fc2.weight w2 [d, I]: the fc2 input
+    gradient stays in TMEM and the SwiGLU backward runs in the GEMM epilogue."""
+    _require_cuda(dout, w2, yg)
+    M, K = dout.shape
+    I = w2.shape[1]
+    assert w2.shape[0] == K and yg.shape == (M, 2 * I)
+    dyg = torch.empty_like(yg)
+    lib = _lib.load()
+    ev = TIMER.begin("gemm") if TIMER is not None else None
+    _lib.check(lib.cx_gemm_swiglu_bwd(dout.data_ptr(), w2.data_ptr(), yg.data_ptr(), dyg.data_ptr(), M, I, K, dout.stride(0),
+                                      w2.stride(0), yg.stride(0), dyg.stride(0), _stream()), "cx_gemm_swiglu_bwd")
+    if ev is not None:
+        TIMER.end("gemm", 2.0 * M * I * K, ev)
+    return dyg
 
 
 def rows_to_bf16(x: torch.Tensor, k=None, normalize=False, want_inv_norm=False):

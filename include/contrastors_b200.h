@@ -37,6 +37,10 @@ CX_API int cx_version(void);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches evidence) */
 CX_API unsigned long long cx_launch_count(void);
 
+/* A/B switch of the GEMM launch mode, process-wide: the largest cluster the launcher may use (0 = default = 4: two CTA pairs
+ * sharing their B tile by TMA multicast when M % 512 == 0; 2 = CTA pairs (cta_group::2); 1 = one CTA per tile). */
+CX_API int cx_gemm_select_cluster(int max_cluster_ctas);
+
 /* ---- dense contraction on tcgen05 (replaces torch.matmul / FusedDense = cuBLASLt:
  *      layers/attention.py:82-85,112,243  layers/mlp.py:24,61,68-83  loss.py:109)
  * C[M,N] (+)= alpha * A (x) B, bf16 operands, fp32 accumulate in TMEM.
@@ -45,6 +49,13 @@ CX_API unsigned long long cx_launch_count(void);
  *   c_dtype CX_BF16 or CX_F32; accumulate != 0 (fp32 only) adds into C with TMA reduce-add. */
 CX_API int cx_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int a_major, int b_major, int64_t lda,
                  int64_t ldb, int64_t ldc, int c_dtype, int accumulate, float alpha, cx_stream_t stream);
+
+/* Gated-MLP backward through the activation, fused into the fc2 dgrad GEMM: dyg[M, 2I] = [ da * silu(g) | da * y * silu'(g) ]
+ * with da = dout[M, K] x w2[K, I] kept in TMEM (never written to HBM) and yg = [y | g] the pre-activations saved by
+ * cx_gemm_swiglu.  Replaces the autograd of flash-attn's swiglu + the fc2 input-gradient GEMM
+ * (/root/reference/src/contrastors/layers/mlp.py:68-83).  I % 256 == 0, M >= 256. */
+CX_API int cx_gemm_swiglu_bwd(const void* dout, const void* w2, const void* yg, void* dyg, int M, int I, int K, int64_t ld_dout,
+                       int64_t ld_w2, int64_t ld_yg, int64_t ld_dyg, cx_stream_t stream);
 
 /* ---- QKV projection with the rotary embedding fused into the GEMM epilogue (layers/attention.py:112-133 =
  * Wqkv GEMM + apply_rotary_emb x2 + torch.stack): qkv[T, n_out] = x w^T; heads (64 columns) inside [0, rope_cols) are

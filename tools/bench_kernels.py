@@ -26,19 +26,40 @@ def timeit(fn, iters=10, warm=3):
 
 
 res = {}
-for (M, N, K, am, bm, f32) in [(32768, 2304, 768, 0, 0, False), (32768, 768, 768, 0, 0, False), (32768, 6144, 768, 0, 0, False),
-                               (32768, 768, 3072, 0, 0, False), (32768, 768, 2304, 0, 1, False), (2304, 768, 32768, 1, 1, True),
-                               (6144, 768, 32768, 1, 1, True), (8192, 8192, 8192, 0, 0, False)]:
+SHAPES = [(32768, 2304, 768, 0, 0, False), (32768, 768, 768, 0, 0, False), (32768, 768, 3072, 0, 0, False),
+          (32768, 3072, 768, 0, 1, False), (32768, 768, 6144, 0, 1, False), (32768, 768, 2304, 0, 1, False), (32768, 768, 768, 0, 1, False),
+          (2304, 768, 32768, 1, 1, True), (6144, 768, 32768, 1, 1, True), (8192, 8192, 8192, 0, 0, False)]
+for (M, N, K, am, bm, f32) in SHAPES:
     a = torch.randn((M, K) if am == 0 else (K, M), device="cuda").to(torch.bfloat16)
     b = torch.randn((N, K) if bm == 0 else (K, N), device="cuda").to(torch.bfloat16)
     out = torch.empty(M, N, device="cuda", dtype=torch.float32 if f32 else torch.bfloat16)
-    ms = timeit(lambda: ops.gemm(a, b, a_major=am, b_major=bm, out=out))
+    ent = {}
+    for cl in (2, 4):  # CTA pairs vs two pairs sharing B by TMA multicast (M % 512 == 0 only; otherwise both are pair mode)
+        ops.gemm_select_cluster(cl)
+        ms = timeit(lambda: ops.gemm(a, b, a_major=am, b_major=bm, out=out))
+        ent[f"cluster{cl}_ms"] = ms
+        ent[f"cluster{cl}_tflops"] = 2 * M * N * K / ms / 1e9
+    ops.gemm_select_cluster(0)
     A = a if am == 0 else a.t()
     B = b.t() if bm == 0 else b
     ms_t = timeit(lambda: torch.matmul(A, B))
-    res[f"gemm_{M}x{N}x{K}_a{am}b{bm}{'_f32' if f32 else ''}"] = dict(ms=ms, tflops=2 * M * N * K / ms / 1e9, torch_ms=ms_t,
-                                                                      torch_tflops=2 * M * N * K / ms_t / 1e9)
+    ent.update(torch_ms=ms_t, torch_tflops=2 * M * N * K / ms_t / 1e9)
+    res[f"gemm_{M}x{N}x{K}_a{am}b{bm}{'_f32' if f32 else ''}"] = ent
     print(list(res.items())[-1], flush=True)
+# fc1 + SwiGLU (inference form and training form that also stores the pre-activations)
+x = torch.randn(32768, 768, device="cuda").to(torch.bfloat16)
+w1 = (torch.randn(6144, 768, device="cuda") / 28).to(torch.bfloat16)
+for keep in (False, True):
+    ent = {}
+    for cl in (2, 4):
+        ops.gemm_select_cluster(cl)
+        ms = timeit(lambda: ops.gemm_swiglu(x, w1, keep_preact=keep))
+        ent[f"cluster{cl}_ms"] = ms
+        ent[f"cluster{cl}_tflops"] = 2 * 32768 * 6144 * 768 / ms / 1e9
+    ops.gemm_select_cluster(0)
+    res[f"gemm_swiglu_32768x3072x768_keep{int(keep)}"] = ent
+    print(list(res.items())[-1], flush=True)
+del x, w1, a, b, out
 
 n, m, dim = 2048, 16384, 768
 g = torch.Generator().manual_seed(1234)
