@@ -24,7 +24,7 @@ SIGNATURES = {
     "cx_launch_count": (C.c_ulonglong, []),
     "cx_gemm_select_cluster": (_i, [_i]),
     "cx_gemm_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i, _i, _f, _vp]),
-    "cx_gemm_qkv_rope": (_i, [_vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _vp, _vp, _vp, _i, _vp]),
+    "cx_gemm_qkv_rope": (_i, [_vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _vp, _vp, _i, _vp]),
     "cx_gemm_swiglu_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _vp]),
     "cx_gemm_swiglu": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _vp]),
     "cx_infonce_workspace_bytes": (_sz, [_i, _i, _i]),

@@ -265,9 +265,8 @@ extern "C" int cx_gemm_swiglu_bwd(const void* dout, const void* w2, const void* 
 // QKV projection with the rotary embedding applied in the epilogue (replaces Wqkv GEMM + apply_rotary_emb + torch.stack,
 // layers/attention.py:112-133): qkv[T, 3*H*64] = x W^T, then q and k heads rotated by cos/sin[pos[t]].
 extern "C" int cx_gemm_qkv_rope(const void* x, const void* w, void* qkv, int T, int n_out, int K, int64_t ldx, int64_t ldw,
-                                int64_t ldo, const int32_t* pos, const float* cos_t, const float* sin_t, int rope_cols,
-                                cx_stream_t stream) {
-  CX_REQUIRE(x && w && qkv && pos && cos_t && sin_t, "cx_gemm_qkv_rope: null pointer");
+                                int64_t ldo, const int32_t* pos, const float* inv_freq, int rope_cols, cx_stream_t stream) {
+  CX_REQUIRE(x && w && qkv && pos && inv_freq, "cx_gemm_qkv_rope: null pointer");
   CX_REQUIRE(n_out % 64 == 0 && rope_cols % 64 == 0 && rope_cols <= n_out, "cx_gemm_qkv_rope: heads are 64 columns wide");
   cx::GemmArgs g{};
   g.A = x; g.B = w; g.C = qkv;
@@ -277,7 +276,7 @@ extern "C" int cx_gemm_qkv_rope(const void* x, const void* w, void* qkv, int T, 
   g.out_f32 = false; g.accumulate = false; g.splits = 1;
   g.mode = cx::EPI_STORE;
   g.ep.alpha = 1.f;
-  g.ep.rope_pos = pos; g.ep.rope_cos = cos_t; g.ep.rope_sin = sin_t; g.ep.rope_cols = rope_cols;
+  g.ep.rope_pos = pos; g.ep.rope_inv_freq = inv_freq; g.ep.rope_cols = rope_cols;
   g.stream = static_cast<cudaStream_t>(stream);
   return cx::launch_gemm(g);
 }

@@ -51,11 +51,14 @@ struct EpiParams {
   float* label_logit = nullptr;  // [M]
   float* dlogit_part = nullptr;  // [gridDim.x]
   // EPI_STORE bf16 with rotary embedding fused (QKV projection): columns [0, rope_cols) are heads of 64 whose halves
-  // (x1 = first 32, x2 = last 32) are rotated by cos/sin[rope_pos[row]][0..32)   (layers/embedding.py:685-706)
+  // (x1 = first 32, x2 = last 32) are rotated by the angle rope_pos[row] * rope_inv_freq[j], j < 32 (layers/embedding.py:
+  // 685-706).  The angle is formed in fp32 exactly as the reference's cos/sin cache does (outer(t, inv_freq)); cos/sin come
+  // from the SFU (sin.approx / cos.approx: |err| < 1e-4 at positions <= 8192, far inside the bf16 rounding the reference applies to
+  // its cached tables).  Round 1 gathered them from fp32 tables per row: 32 uncoalesced loads per thread per head, 219 us vs
+  // 89 + 35 us for GEMM + standalone rotary; computing them costs 128 SFU ops per thread per tile under the next tile's MMAs.
   const float* bias = nullptr;  // EPI_STORE bf16: out = alpha * acc + bias[col]  (FusedDense: layers/attention.py:82-85, mlp.py:24)
   const int* rope_pos = nullptr;
-  const float* rope_cos = nullptr;
-  const float* rope_sin = nullptr;
+  const float* rope_inv_freq = nullptr;  // [32] = base^(-2j/64)
   int rope_cols = 0;
   // EPI_SWIGLU (N = number of gated output columns)
   __nv_bfloat16* act_out = nullptr;  // [M, N]
@@ -443,13 +446,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       } else if (MODE == EPI_STORE && !OUT_F32) {
         // bf16 store path: one staging row (128 B) = 64 columns = two TMEM chunks = one attention head when RoPE is on
-        const float* cs = nullptr;
-        const float* sn = nullptr;
-        if (ep.rope_pos != nullptr && row_ok) {
-          const int ps = ep.rope_pos[row];
-          cs = ep.rope_cos + (size_t)ps * 32;
-          sn = ep.rope_sin + (size_t)ps * 32;
-        }
+        float rpos = 0.f;
+        const bool rope_row = ep.rope_pos != nullptr && row_ok;
+        if (rope_row) rpos = (float)ep.rope_pos[row];
 #pragma unroll 1
         for (int pr = 0; pr < NC / 2; ++pr) {
           uint32_t v1[32], v2[32];
@@ -458,11 +457,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tmem_ld_wait();
           const int col0 = n0 + pr * 64;
           uint32_t pk1[16], pk2[16];
-          if (cs != nullptr && col0 < ep.rope_cols) {
+          if (rope_row && col0 < ep.rope_cols) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const float2 c2 = *reinterpret_cast<const float2*>(cs + 2 * j);
-              const float2 s2 = *reinterpret_cast<const float2*>(sn + 2 * j);
+              const float2 f2 = __ldg(reinterpret_cast<const float2*>(ep.rope_inv_freq) + j);  // same address in every thread
+              const float g0 = rpos * f2.x, g1 = rpos * f2.y;
+              const float2 c2 = make_float2(__cosf(g0), __cosf(g1));
+              const float2 s2 = make_float2(__sinf(g0), __sinf(g1));
               const float a0 = __uint_as_float(v1[2 * j]) * ep_alpha, a1 = __uint_as_float(v1[2 * j + 1]) * ep_alpha;
               const float b0 = __uint_as_float(v2[2 * j]) * ep_alpha, b1 = __uint_as_float(v2[2 * j + 1]) * ep_alpha;
               pk1[j] = pack_bf16x2(a0 * c2.x - b0 * s2.x, a1 * c2.y - b1 * s2.y);

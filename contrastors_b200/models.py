@@ -125,7 +125,8 @@ class NomicBertModel(FlatParamModule):
             dim = self.config.head_dim
             inv_freq = 1.0 / (self.config.rotary_emb_base ** (torch.arange(0, dim, 2, dtype=torch.float32) / dim))
             freqs = torch.outer(torch.arange(n, dtype=torch.float32), inv_freq)  # fp32, as embedding.py / HF :1148-1183
-            self._rope = (torch.cos(freqs).to(self._flat.device), torch.sin(freqs).to(self._flat.device))
+            self._rope = (torch.cos(freqs).to(self._flat.device), torch.sin(freqs).to(self._flat.device),
+                          inv_freq.to(self._flat.device).contiguous())
         return self._rope
 
     # ---------------------------------------------------------------- forward
@@ -195,7 +196,7 @@ class _TrunkFn(torch.autograd.Function):
         v = model.view
         H, Dh, d = cfg.n_head, cfg.head_dim, cfg.n_embd
         scale = 1.0 / math.sqrt(Dh)
-        cos_t, sin_t = model.rope_tables(packed.max_seqlen)
+        cos_t, sin_t, inv_freq = model.rope_tables(packed.max_seqlen)
         eps = cfg.layer_norm_epsilon
         # dropout: one 64-bit seed per tower call drawn from torch's CPU generator -- RandContext replays that generator
         # for GradCache's second pass, so the re-forward regenerates exactly the same keep masks (rand_state.py)
@@ -209,11 +210,9 @@ class _TrunkFn(torch.autograd.Function):
         saved = []
         for i in range(cfg.n_layer):
             p = f"encoder.layers.{i}."
-            # (cx_gemm_qkv_rope fuses the rotation into the epilogue but its per-row cos/sin gather costs more than this
-            #  standalone 7 TB/s pass: measured 219 us vs 89 + 35 us at T = 32768 (tools/bench_qkv_rope.py), so the
-            #  two-kernel form stays)
-            qkv = ops.gemm(h, v(W, p + "attn.Wqkv.weight"))
-            ops.rope_inplace(qkv, packed.pos, cos_t, sin_t, H, Dh)
+            # Wqkv GEMM with the rotation of the q / k heads in its epilogue (cos/sin evaluated there from pos * inv_freq):
+            # no separate rotary pass over qkv
+            qkv = ops.gemm_qkv_rope(h, v(W, p + "attn.Wqkv.weight"), packed.pos, inv_freq, 2 * d)
             attn, lse = ops.attn_fwd(qkv, packed.cu, packed.max_seqlen, H, Dh, scale)
             o = ops.gemm(attn, v(W, p + "attn.out_proj.weight"))
             h1, st1 = ops.add_layernorm_fwd(o, h, v(P, p + "norm1.weight"), v(P, p + "norm1.bias"), eps, p_drop=pdrop,
@@ -249,7 +248,7 @@ class _TrunkFn(torch.autograd.Function):
         v = model.view
         H, Dh = cfg.n_head, cfg.head_dim
         scale = 1.0 / math.sqrt(Dh)
-        cos_t, sin_t = model.rope_tables(packed.max_seqlen)
+        cos_t, sin_t, _ = model.rope_tables(packed.max_seqlen)
         if head is not None:
             pooled, head_save = ctx.head_state
             gp = ops.embed_head_bwd(pooled, g_out.contiguous().float(), head_save, head["hamming"], head["normalize"])

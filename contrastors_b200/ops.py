@@ -94,8 +94,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_major=MAJOR_K, b_major=MAJOR_K, 
     return out
 
 
-def gemm_qkv_rope(x, w, pos, cos_t, sin_t, rope_cols):
-    """qkv = x w^T with RoPE applied to the q and k heads in the GEMM epilogue."""
+def gemm_qkv_rope(x, w, pos, inv_freq, rope_cols):
+    """qkv = x w^T with RoPE applied to the q and k heads in the GEMM epilogue (inv_freq: fp32 [32])."""
     _require_cuda(x, w)
     T, K = x.shape
     n_out = w.shape[0]
@@ -103,7 +103,7 @@ def gemm_qkv_rope(x, w, pos, cos_t, sin_t, rope_cols):
     lib = _lib.load()
     ev = TIMER.begin("gemm") if TIMER is not None else None
     _lib.check(lib.cx_gemm_qkv_rope(x.data_ptr(), w.data_ptr(), out.data_ptr(), T, n_out, K, x.stride(0), w.stride(0),
-                                    out.stride(0), pos.data_ptr(), cos_t.data_ptr(), sin_t.data_ptr(), rope_cols, _stream()),
+                                    out.stride(0), pos.data_ptr(), inv_freq.data_ptr(), rope_cols, _stream()),
                "cx_gemm_qkv_rope")
     if ev is not None:
         TIMER.end("gemm", 2.0 * T * n_out * K, ev)

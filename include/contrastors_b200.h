@@ -59,10 +59,10 @@ CX_API int cx_gemm_swiglu_bwd(const void* dout, const void* w2, const void* yg, 
 
 /* ---- QKV projection with the rotary embedding fused into the GEMM epilogue (layers/attention.py:112-133 =
  * Wqkv GEMM + apply_rotary_emb x2 + torch.stack): qkv[T, n_out] = x w^T; heads (64 columns) inside [0, rope_cols) are
- * rotated NeoX-style by cos/sin[pos[t]] (fp32 tables [max_pos, 32]). */
+ * rotated NeoX-style by the angles pos[t] * inv_freq[j] (inv_freq: 32 fp32 values base^(-2j/64); the angle is formed in fp32 as
+ * the reference's cos/sin cache does, cos/sin evaluated in the epilogue). */
 CX_API int cx_gemm_qkv_rope(const void* x, const void* w, void* qkv, int T, int n_out, int K, int64_t ldx, int64_t ldw,
-                     int64_t ldo, const int32_t* pos, const float* cos_t, const float* sin_t, int rope_cols,
-                     cx_stream_t stream);
+                     int64_t ldo, const int32_t* pos, const float* inv_freq, int rope_cols, cx_stream_t stream);
 
 /* ---- gated-MLP first layer with the SwiGLU fused into the GEMM epilogue (layers/mlp.py:68-75: fc11, fc12, swiglu)
  * w1 [2I, K] = [fc11; fc12] (nn.Linear layout); act_out[M, I] = (x fc11^T) * silu(x fc12^T), bf16;

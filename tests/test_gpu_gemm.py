@@ -152,7 +152,7 @@ def test_gemm_qkv_rope_epilogue_matches_gemm_then_rope():
     cos_t, sin_t = torch.cos(fr).cuda(), torch.sin(fr).cuda()
     x = torch.randn(T, d, device="cuda").to(torch.bfloat16)
     w = (torch.randn(3 * d, d, device="cuda") / d ** 0.5).to(torch.bfloat16)
-    fused = ops.gemm_qkv_rope(x, w, pos, cos_t, sin_t, 2 * d)
+    fused = ops.gemm_qkv_rope(x, w, pos, inv.cuda(), 2 * d)
     ref = (x.float() @ w.float().t()).view(T, 3, H, Dh)
     c = cos_t[pos.long()][:, None, :]
     s = sin_t[pos.long()][:, None, :]

@@ -28,6 +28,7 @@ pos = (torch.arange(T, device="cuda") % S).to(torch.int32)
 inv = 1.0 / (10000.0 ** (torch.arange(0, Dh, 2, dtype=torch.float32) / Dh))
 fr = torch.outer(torch.arange(S, dtype=torch.float32), inv)
 cos_t, sin_t = torch.cos(fr).cuda(), torch.sin(fr).cuda()
+inv_freq = inv.cuda().contiguous()
 
 
 def separate():
@@ -37,8 +38,8 @@ def separate():
 
 
 a = separate()
-b = ops.gemm_qkv_rope(x, w, pos, cos_t, sin_t, 2 * d)
+b = ops.gemm_qkv_rope(x, w, pos, inv_freq, 2 * d)
 print("max abs diff", (a.float() - b.float()).abs().max().item())
 print("gemm only      %.1f us" % (1e3 * timeit(lambda: ops.gemm(x, w))))
 print("gemm + rope    %.1f us" % (1e3 * timeit(separate)))
-print("fused epilogue %.1f us" % (1e3 * timeit(lambda: ops.gemm_qkv_rope(x, w, pos, cos_t, sin_t, 2 * d))))
+print("fused epilogue %.1f us" % (1e3 * timeit(lambda: ops.gemm_qkv_rope(x, w, pos, inv_freq, 2 * d))))
