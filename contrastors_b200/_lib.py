@@ -62,9 +62,7 @@ SIGNATURES = {
     "cx_cls_select_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "cx_cls_select_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "cx_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
-    "cx_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
-    "cx_debug_attn_trace": (_i, [_vp]),
-    "cx_attn_select_kernels": (_i, [_i, _i]),
+    "cx_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp]),
 }
 
 

@@ -1,6 +1,8 @@
 // Attention backward kernels (included by cx_attn.cu inside namespace cx; see the overview there).
 #pragma once
 
+constexpr int kBwd2Threads = 512;
+
 // ============================================================================================== backward
 // delta[h, t] = sum_d dO[t,h,d] * O[t,h,d]; 8 threads per (t, h) row of 64, 16-byte loads
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
@@ -26,656 +28,11 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __n
   }
 }
 
-constexpr int kBwdThreads = 384;  // 4 control warps + 2 x 4 worker warps (each group owns 64 of the 128 key columns)
-struct BwdSmem {
-  static constexpr int kTile = 128 * kDh * 2;   // 16 KB
-  static constexpr int kK = 0;                  // K_j  (B of S, B of dQ as MN-major)
-  static constexpr int kV = kK + kTile;         // V_j  (B of dP)
-  static constexpr int kQ = kV + kTile;         // 2 stages: Q_i (A of S, B of dK as MN-major)
-  static constexpr int kDO = kQ + 2 * kTile;    // 2 stages: dO_i (A of dP, B of dV as MN-major)
-  static constexpr int kP = kDO + 2 * kTile;    // P  [128 q x 128 keys] bf16 (A of dV, MN-major)
-  static constexpr int kDS = kP + 32768;        // dS [128 q x 128 keys] bf16 (A of dK MN-major, A of dQ K-major)
-  static constexpr int kDQ = kDS + 32768;       // fp32 staging for the dQ reduce-add: 2 x [128 x 32] (128 B rows)
-  static constexpr int kBars = kDQ + 2 * 16384;
-  static constexpr int kTotal = kBars + 256 + 1024;
-};
-
-// TMEM columns: S [0,128)  dP [128,256)  dV [256,320)  dK [320,384)  dQ [384,448)
-__global__ void __launch_bounds__(kBwdThreads, 1)
-attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                const __grid_constant__ CUtensorMap tmDQ, const int* __restrict__ cu_seqlens,
-                const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T,
-                int H, float softmax_scale) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BwdSmem::kBars);
-  uint64_t* kv_full = bars;        // [1]
-  uint64_t* q_full = bars + 1;     // [2]  (Q_i and dO_i of a stage)
-  uint64_t* q_empty = bars + 3;    // [2]
-  uint64_t* sdp_full = bars + 5;   // [1]  S and dP of the current tile are in TMEM
-  uint64_t* pds_full = bars + 6;   // [1]  P and dS are in smem (128 arrivals)
-  uint64_t* dq_full = bars + 7;    // [1]  dQ partial of the current tile is in TMEM
-  uint64_t* dq_free = bars + 8;    // [1]  dQ TMEM drained by the epilogue warps (128 arrivals)
-  uint64_t* acc_full = bars + 9;   // [1]  dK / dV complete
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int seq = blockIdx.z, head = blockIdx.y;
-  const int seq_begin = cu_seqlens[seq];
-  const int len = cu_seqlens[seq + 1] - seq_begin;
-  const int k0 = blockIdx.x * 128;
-  if (k0 >= len) return;
-  const int nq = (len + 127) / 128;
-  const float scale2 = softmax_scale * kLog2e;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQKV);
-    tma_prefetch_desc(&tmDO);
-    tma_prefetch_desc(&tmDQ);
-  }
-  if (warp == 1 && lane == 0) {
-    mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&q_full[i], 1);
-      mbar_init(&q_empty[i], 1);
-    }
-    mbar_init(sdp_full, 1);
-    mbar_init(pds_full, 256);
-    mbar_init(dq_full, 1);
-    mbar_init(dq_free, 256);
-    mbar_init(acc_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc<512>(tmem_ptr);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-  const int col_q = (0 * H + head) * kDh, col_k = (1 * H + head) * kDh, col_v = (2 * H + head) * kDh;
-  const int col_o = head * kDh;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(kv_full, 2 * BwdSmem::kTile);
-      tma_load_2d(smem + BwdSmem::kK, &tmQKV, kv_full, col_k, seq_begin + k0);
-      tma_load_2d(smem + BwdSmem::kV, &tmQKV, kv_full, col_v, seq_begin + k0);
-      for (int i = 0; i < nq; ++i) {
-        const int st = i & 1;
-        mbar_wait(&q_empty[st], ((i >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&q_full[st], 2 * BwdSmem::kTile);
-        tma_load_2d(smem + BwdSmem::kQ + st * BwdSmem::kTile, &tmQKV, &q_full[st], col_q, seq_begin + i * 128);
-        tma_load_2d(smem + BwdSmem::kDO + st * BwdSmem::kTile, &tmDO, &q_full[st], col_o, seq_begin + i * 128);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t id_kk = make_idesc_bf16(128, 128, 0, 0);  // S, dP: A K-major, B K-major, N = 128
-      constexpr uint32_t id_mm = make_idesc_bf16(128, 64, 1, 1);   // dV, dK: A MN-major (P^T / dS^T), B MN-major, N = 64
-      constexpr uint32_t id_km = make_idesc_bf16(128, 64, 0, 1);   // dQ: A K-major (dS), B MN-major (K_j), N = 64
-      const uint32_t k_addr = smem_u32(smem + BwdSmem::kK), v_addr = smem_u32(smem + BwdSmem::kV);
-      const uint32_t q_addr = smem_u32(smem + BwdSmem::kQ), do_addr = smem_u32(smem + BwdSmem::kDO);
-      const uint32_t p_addr = smem_u32(smem + BwdSmem::kP), ds_addr = smem_u32(smem + BwdSmem::kDS);
-      mbar_wait(kv_full, 0);
-      for (int i = 0; i < nq; ++i) {
-        const int st = i & 1;
-        mbar_wait(&q_full[st], (i >> 1) & 1);
-        tc_fence_after();
-        // S = Q_i K_j^T ; dP = dO_i V_j^T      (K = Dh = 64: 4 k-steps each)
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          umma_f16_ss(tmem_base + 0, make_smem_desc_sw128(q_addr + st * BwdSmem::kTile + kk * 32, 0, 1024),
-                      make_smem_desc_sw128(k_addr + kk * 32, 0, 1024), id_kk, kk > 0 ? 1u : 0u);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          umma_f16_ss(tmem_base + 128, make_smem_desc_sw128(do_addr + st * BwdSmem::kTile + kk * 32, 0, 1024),
-                      make_smem_desc_sw128(v_addr + kk * 32, 0, 1024), id_kk, kk > 0 ? 1u : 0u);
-        umma_commit(sdp_full);
-        // wait for P / dS in smem
-        mbar_wait(pds_full, i & 1);
-        tc_fence_after();
-        // dV += P^T dO_i ; dK += dS^T Q_i   (contraction over the 128 query rows: 8 k-steps of 16 rows = +2048 B;
-        //                                      A atoms (64 keys each) are 16 KB apart => LBO = 16384)
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_f16_ss(tmem_base + 256, make_smem_desc_sw128(p_addr + kk * 2048, 16384, 1024),
-                      make_smem_desc_sw128(do_addr + st * BwdSmem::kTile + kk * 2048, 8192, 1024), id_mm,
-                      (i > 0 || kk > 0) ? 1u : 0u);
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_f16_ss(tmem_base + 320, make_smem_desc_sw128(ds_addr + kk * 2048, 16384, 1024),
-                      make_smem_desc_sw128(q_addr + st * BwdSmem::kTile + kk * 2048, 8192, 1024), id_mm,
-                      (i > 0 || kk > 0) ? 1u : 0u);
-        // dQ_i(partial) = dS K_j   (contraction over 128 keys: A K-major two 64-key blocks, B = K_j MN-major)
-        mbar_wait(dq_free, (i & 1) ^ 1);
-        tc_fence_after();
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_f16_ss(tmem_base + 384, make_smem_desc_sw128(ds_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024),
-                      make_smem_desc_sw128(k_addr + kk * 2048, 8192, 1024), id_km, kk > 0 ? 1u : 0u);
-        umma_commit(dq_full);
-        umma_commit(&q_empty[st]);
-      }
-      umma_commit(acc_full);
-    }
-  } else if (warp >= 4) {
-    const int ew = warp & 3;
-    const int grp = (warp - 4) >> 2;  // column group: keys [grp*64, grp*64+64) of the tile; dQ columns [grp*32, +32)
-    const int r = ew * 32 + lane;     // query row within the tile (S/dP/dQ) or key row within the tile (dK/dV)
-    const int etid = (threadIdx.x - 128) & 127;
-    const uint32_t lane_base = static_cast<uint32_t>(ew * 32) << 16;
-    const int kv_valid = min(128, len - k0);
-    const bool full = kv_valid == 128;
-    uint8_t* p_smem = smem + BwdSmem::kP + grp * 16384;    // this group's 64-key block of P / dS
-    uint8_t* ds_smem = smem + BwdSmem::kDS + grp * 16384;
-    uint8_t* dq_smem = smem + BwdSmem::kDQ + grp * 16384;
-    for (int i = 0; i < nq; ++i) {
-      const int q_row = i * 128 + r;
-      const bool row_ok = q_row < len;
-      const float lse2 = row_ok ? lse[(size_t)head * T + seq_begin + q_row] * kLog2e : INFINITY;  // +inf => P = 0
-      const float dl = row_ok ? delta[(size_t)head * T + seq_begin + q_row] * softmax_scale : 0.f;  // pre-scaled
-      mbar_wait(sdp_full, i & 1);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t vs[32], vd[32];
-        tmem_ld_32x32(tmem_base + lane_base + grp * 64 + c * 32, vs);
-        tmem_ld_32x32(tmem_base + lane_base + 128 + grp * 64 + c * 32, vd);
-        tmem_ld_wait();
-        if (!full) {
-#pragma unroll
-          for (int t = 0; t < 32; ++t)
-            if (grp * 64 + c * 32 + t >= kv_valid) vs[t] = 0xff800000u;  // -inf => P = 0
-        }
-        uint8_t* dp = p_smem + r * 128;
-        uint8_t* dd = ds_smem + r * 128;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float p[8], ds[8];
-#pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            p[t] = fast_exp2(fmaf(__uint_as_float(vs[8 * q + t]), scale2, -lse2));
-            ds[t] = p[t] * fmaf(__uint_as_float(vd[8 * q + t]), softmax_scale, -dl);
-          }
-          uint4 w, x;
-          w.x = pack_bf16x2(p[0], p[1]);
-          w.y = pack_bf16x2(p[2], p[3]);
-          w.z = pack_bf16x2(p[4], p[5]);
-          w.w = pack_bf16x2(p[6], p[7]);
-          x.x = pack_bf16x2(ds[0], ds[1]);
-          x.y = pack_bf16x2(ds[2], ds[3]);
-          x.z = pack_bf16x2(ds[4], ds[5]);
-          x.w = pack_bf16x2(ds[6], ds[7]);
-          const int chunk = c * 4 + q;
-          *reinterpret_cast<uint4*>(dp + ((chunk ^ (r & 7)) << 4)) = w;
-          *reinterpret_cast<uint4*>(dd + ((chunk ^ (r & 7)) << 4)) = x;
-        }
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(pds_full);
-      // drain this tile's dQ partial (this group's 32 columns): TMEM -> fp32 smem stage -> TMA reduce-add into dq_acc
-      mbar_wait(dq_full, i & 1);
-      tc_fence_after();
-      {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + lane_base + 384 + grp * 32, v);
-        tmem_ld_wait();
-        if (etid == 0) tma_store_wait_read<0>();
-        named_bar_sync(1 + grp, 128);
-        uint8_t* dst = dq_smem + r * 128;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          uint4 w = make_uint4(row_ok ? v[4 * q] : 0u, row_ok ? v[4 * q + 1] : 0u, row_ok ? v[4 * q + 2] : 0u,
-                               row_ok ? v[4 * q + 3] : 0u);
-          *reinterpret_cast<uint4*>(dst + ((q ^ (r & 7)) << 4)) = w;
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(1 + grp, 128);
-        if (etid == 0) {
-          tma_reduce_add_2d(&tmDQ, dq_smem, col_o + grp * 32, seq_begin + i * 128);
-          tma_store_commit();
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(dq_free);
-    }
-    // dV (group 0) / dK (group 1): TMEM -> bf16 -> dqkv rows of this key tile
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    const int k_row = k0 + r;
-    const bool krow_ok = k_row < len;
-    __nv_bfloat16* dst = dqkv + ((size_t)(seq_begin + k_row) * 3 + (grp == 0 ? 2 : 1)) * H * kDh + (size_t)head * kDh;
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + lane_base + 256 + grp * 64 + c * 32, v);
-      tmem_ld_wait();
-      if (krow_ok) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
-          w.y = pack_bf16x2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
-          w.z = pack_bf16x2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
-          w.w = pack_bf16x2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
-          *reinterpret_cast<uint4*>(dst + c * 32 + q * 8) = w;
-        }
-      }
-    }
-    if (etid == 0) tma_store_wait<0>();
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------- backward, pipelined
-// Same tiling and smem/TMEM layout as attn_bwd_kernel, but the five contractions of consecutive query tiles overlap with
-// the exponentials:  the MMA thread issues S(i+1) as soon as P(i) has left the registers (S columns are free again) and
-// dP(i+1) as soon as dS(i) is in smem, so the tensor core runs dV(i) / dK(i) / dQ(i) while the 8 worker warps compute
-// the next tile's exponentials; a separate 4-warp group drains the dQ partials (TMEM -> smem -> TMA reduce-add), so the
-// workers never wait for it.  16 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 workers, 12-15 dQ drain.
-constexpr int kBwd2Threads = 512;
-
-__global__ void __launch_bounds__(kBwd2Threads, 1)
-attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                 const __grid_constant__ CUtensorMap tmDQ, const int* __restrict__ cu_seqlens,
-                 const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T,
-                 int H, float softmax_scale, int ablate) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BwdSmem::kBars);
-  uint64_t* kv_full = bars;        // [1]
-  uint64_t* q_full = bars + 1;     // [2]  Q_i and dO_i of a stage landed
-  uint64_t* q_empty = bars + 3;    // [2]  every MMA reading the stage has completed
-  uint64_t* s_full = bars + 5;     // S(i) in TMEM
-  uint64_t* dp_full = bars + 6;    // dP(i) in TMEM
-  uint64_t* p_ready = bars + 7;    // P(i) in smem, S columns free (256 arrivals)
-  uint64_t* ds_ready = bars + 8;   // dS(i) in smem, dP columns free (256 arrivals)
-  uint64_t* p_free = bars + 9;     // dV(i) has finished reading P(i)
-  uint64_t* dq_full = bars + 10;   // dQ(i) partial in TMEM; also: dK(i), dQ(i) have finished reading dS(i)
-  uint64_t* dq_free = bars + 11;   // dQ TMEM columns drained (128 arrivals)
-  uint64_t* acc_full = bars + 12;  // dK / dV complete
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int seq = blockIdx.z, head = blockIdx.y;
-  const int seq_begin = cu_seqlens[seq];
-  const int len = cu_seqlens[seq + 1] - seq_begin;
-  const int k0 = blockIdx.x * 128;
-  if (k0 >= len) return;
-  const int nq = (len + 127) / 128;
-  const float scale2 = softmax_scale * kLog2e;
-  long long* tr = g_attn_trace;
-  if (tr != nullptr) {
-    tr += ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 64;
-    if (threadIdx.x == 0) {
-      uint32_t smid;
-      unsigned long long gt;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-      tr[0] = clock64();
-      tr[1] = smid;
-      tr[2] = (long long)gt;
-    }
-  }
-
-  const int col_q = (0 * H + head) * kDh, col_k = (1 * H + head) * kDh, col_v = (2 * H + head) * kDh;
-  const int col_o = head * kDh;
-  if (warp == 0 && lane == 0) {
-    // the producer lane initialises the barriers itself and starts the first loads before the CTA-wide sync, so the TMA
-    // round trip (~2000 clk) overlaps the TMEM allocation and the rest of the set-up
-    mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&q_full[i], 1);
-      mbar_init(&q_empty[i], 1);
-    }
-    mbar_init(s_full, 1);
-    mbar_init(dp_full, 1);
-    mbar_init(p_ready, 256);
-    mbar_init(ds_ready, 256);
-    mbar_init(p_free, 1);
-    mbar_init(dq_full, 1);
-    mbar_init(dq_free, 128);
-    mbar_init(acc_full, 1);
-    fence_barrier_init();
-    mbar_arrive_expect_tx(kv_full, 2 * BwdSmem::kTile);
-    tma_load_2d(smem + BwdSmem::kK, &tmQKV, kv_full, col_k, seq_begin + k0);
-    tma_load_2d(smem + BwdSmem::kV, &tmQKV, kv_full, col_v, seq_begin + k0);
-    mbar_arrive_expect_tx(&q_full[0], 2 * BwdSmem::kTile);
-    tma_load_2d(smem + BwdSmem::kQ, &tmQKV, &q_full[0], col_q, seq_begin);
-    tma_load_2d(smem + BwdSmem::kDO, &tmDO, &q_full[0], col_o, seq_begin);
-    tma_prefetch_desc(&tmDQ);
-  }
-  if (warp == 2) tmem_alloc<512>(tmem_ptr);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;  // S [0,128)  dP [128,256)  dV [256,320)  dK [320,384)  dQ [384,448)
-  if (threadIdx.x == 0) trace_put(tr, 3);
-
-  // TMA and MMA warps run converged and elect one lane around the asynchronous instructions (see attn_fwd2_kernel)
-  if (warp == 0) {
-    for (int i = 1; i < nq; ++i) {  // K, V and the first query tile were issued during set-up
-      const int st = i & 1;
-      mbar_wait(&q_empty[st], ((i >> 1) & 1) ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&q_full[st], 2 * BwdSmem::kTile);
-        tma_load_2d(smem + BwdSmem::kQ + st * BwdSmem::kTile, &tmQKV, &q_full[st], col_q, seq_begin + i * 128);
-        tma_load_2d(smem + BwdSmem::kDO + st * BwdSmem::kTile, &tmDO, &q_full[st], col_o, seq_begin + i * 128);
-      }
-      __syncwarp();
-    }
-  } else if (warp == 1) {
-    constexpr uint32_t id_kk = make_idesc_bf16(128, 128, 0, 0);  // S, dP: A K-major, B K-major, N = 128
-    constexpr uint32_t id_mm = make_idesc_bf16(128, 64, 1, 1);   // dV, dK: A MN-major (P^T / dS^T), B MN-major, N = 64
-    constexpr uint32_t id_km = make_idesc_bf16(128, 64, 0, 1);   // dQ: A K-major (dS), B MN-major (K_j), N = 64
-    // base descriptors; descriptor of (base + off) = base descriptor + (off >> 4)
-    const uint64_t kd = make_smem_desc_sw128(smem_u32(smem + BwdSmem::kK), 0, 1024);          // K_j  K-major (B of S)
-    const uint64_t vd = make_smem_desc_sw128(smem_u32(smem + BwdSmem::kV), 0, 1024);          // V_j  K-major (B of dP)
-    const uint64_t qd = make_smem_desc_sw128(smem_u32(smem + BwdSmem::kQ), 0, 1024);          // Q_i  K-major (A of S)
-    const uint64_t dod = make_smem_desc_sw128(smem_u32(smem + BwdSmem::kDO), 0, 1024);        // dO_i K-major (A of dP)
-    const uint64_t km = make_smem_desc_sw128(smem_u32(smem + BwdSmem::kK), 8192, 1024);       // K_j  MN-major (B of dQ)
-    const uint64_t qm = make_smem_desc_sw128(smem_u32(smem + BwdSmem::kQ), 8192, 1024);       // Q_i  MN-major (B of dK)
-    const uint64_t dom = make_smem_desc_sw128(smem_u32(smem + BwdSmem::kDO), 8192, 1024);     // dO_i MN-major (B of dV)
-    const uint64_t pm = make_smem_desc_sw128(smem_u32(smem + BwdSmem::kP), 16384, 1024);      // P    MN-major (A of dV)
-    const uint64_t dsm = make_smem_desc_sw128(smem_u32(smem + BwdSmem::kDS), 16384, 1024);    // dS   MN-major (A of dK)
-    const uint64_t dsk = make_smem_desc_sw128(smem_u32(smem + BwdSmem::kDS), 0, 1024);        // dS   K-major  (A of dQ)
-    const int nmma = (ablate & 16) ? 1 : 8;
-    mbar_wait(kv_full, 0);
-    mbar_wait(&q_full[0], 0);
-    tc_fence_after();
-    if (lane == 0) trace_put(tr, 4);
-    if (elect_one()) {
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) umma_f16_ss(tmem_base + 0, qd + ((kk * 32) >> 4), kd + ((kk * 32) >> 4), id_kk, kk > 0 ? 1u : 0u);
-      umma_commit(s_full);
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) umma_f16_ss(tmem_base + 128, dod + ((kk * 32) >> 4), vd + ((kk * 32) >> 4), id_kk, kk > 0 ? 1u : 0u);
-      umma_commit(dp_full);
-    }
-    __syncwarp();
-    for (int i0 = 0; i0 < nq; i0 += 2) {
-#pragma unroll
-      for (int st = 0; st < 2; ++st) {  // st = i & 1 is a compile-time constant after unrolling
-        const int i = i0 + st;
-        if (i < nq) {                   // warp-uniform
-          constexpr int kT = BwdSmem::kTile;
-          const int ns = st ^ 1;
-          const bool more = i + 1 < nq;
-          mbar_wait(p_ready, i & 1);
-          if (more) mbar_wait(&q_full[ns], ((i + 1) >> 1) & 1);
-          tc_fence_after();
-          if (lane == 0 && i < 4) trace_put(tr, 40 + 2 * i);
-          if (elect_one()) {
-            if (ablate & 32) {  // interleave the k-steps of the two independent accumulation chains
-#pragma unroll
-              for (int kk = 0; kk < 8; ++kk) {
-                if (more && (kk & 1) == 0)
-                  umma_f16_ss(tmem_base + 0, qd + ((ns * kT + (kk >> 1) * 32) >> 4), kd + (((kk >> 1) * 32) >> 4), id_kk, kk > 0 ? 1u : 0u);
-                umma_f16_ss(tmem_base + 256, pm + ((kk * 2048) >> 4), dom + ((st * kT + kk * 2048) >> 4), id_mm,
-                            (i > 0 || kk > 0) ? 1u : 0u);
-                if (more && kk == 6) umma_commit(s_full);
-              }
-              umma_commit(p_free);
-            } else {
-            if (more) {  // S(i+1) = Q_{i+1} K_j^T: the score columns are free again
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                umma_f16_ss(tmem_base + 0, qd + ((ns * kT + kk * 32) >> 4), kd + ((kk * 32) >> 4), id_kk, kk > 0 ? 1u : 0u);
-              umma_commit(s_full);
-            }
-            // dV += P^T dO_i  (contraction over the 128 query rows: 8 k-steps of 16 rows = +2048 B; A atoms 16 KB apart)
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk)
-              if (kk < nmma)
-                umma_f16_ss(tmem_base + 256, pm + ((kk * 2048) >> 4), dom + ((st * kT + kk * 2048) >> 4), id_mm,
-                            (i > 0 || kk > 0) ? 1u : 0u);
-            umma_commit(p_free);
-            }
-          }
-          __syncwarp();
-          mbar_wait(ds_ready, i & 1);
-          if (i > 0) mbar_wait(dq_free, (i - 1) & 1);
-          tc_fence_after();
-          if (lane == 0 && i < 4) trace_put(tr, 41 + 2 * i);
-          if (elect_one()) {
-          if (ablate & 32) {  // interleaved: dP(i+1) k, dK(i) 2k, dQ(i) 2k, dK(i) 2k+1, dQ(i) 2k+1
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-              if (more && (kk & 1) == 0)
-                umma_f16_ss(tmem_base + 128, dod + ((ns * kT + (kk >> 1) * 32) >> 4), vd + (((kk >> 1) * 32) >> 4), id_kk, kk > 0 ? 1u : 0u);
-              umma_f16_ss(tmem_base + 320, dsm + ((kk * 2048) >> 4), qm + ((st * kT + kk * 2048) >> 4), id_mm, (i > 0 || kk > 0) ? 1u : 0u);
-              umma_f16_ss(tmem_base + 384, dsk + (((kk >> 2) * 16384 + (kk & 3) * 32) >> 4), km + ((kk * 2048) >> 4), id_km, kk > 0 ? 1u : 0u);
-              if (more && kk == 6) umma_commit(dp_full);
-            }
-            umma_commit(dq_full);
-            umma_commit(&q_empty[st]);
-          } else {
-            if (more) {  // dP(i+1) = dO_{i+1} V_j^T
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                umma_f16_ss(tmem_base + 128, dod + ((ns * kT + kk * 32) >> 4), vd + ((kk * 32) >> 4), id_kk, kk > 0 ? 1u : 0u);
-              umma_commit(dp_full);
-            }
-            // dK += dS^T Q_i
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk)
-              if (kk < nmma)
-                umma_f16_ss(tmem_base + 320, dsm + ((kk * 2048) >> 4), qm + ((st * kT + kk * 2048) >> 4), id_mm,
-                            (i > 0 || kk > 0) ? 1u : 0u);
-            // dQ_i(partial) = dS K_j   (contraction over 128 keys: A K-major two 64-key blocks, B = K_j MN-major)
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk)
-              if (kk < nmma)
-                umma_f16_ss(tmem_base + 384, dsk + (((kk >> 2) * 16384 + (kk & 3) * 32) >> 4), km + ((kk * 2048) >> 4), id_km,
-                            kk > 0 ? 1u : 0u);
-            umma_commit(dq_full);
-            umma_commit(&q_empty[st]);
-          }
-          }
-          __syncwarp();
-        }
-      }
-    }
-    if (elect_one()) umma_commit(acc_full);
-    __syncwarp();
-    if (lane == 0) trace_put(tr, 5);
-  } else if (warp >= 4 && warp < 12) {
-    // ---------------------------------------------------------------- workers: two threads per query row
-    const int ew = warp & 3;
-    const int grp = (warp - 4) >> 2;  // keys [grp*64, grp*64+64) of the tile
-    const int r = ew * 32 + lane;     // query row within the tile (S/dP) or key row within the tile (dK/dV epilogue)
-    const uint32_t lane_base = static_cast<uint32_t>(ew * 32) << 16;
-    const int kv_valid = min(128, len - k0) - grp * 64;  // valid keys among this thread's 64
-    const bool full = kv_valid >= 64;
-    uint8_t* dp = smem + BwdSmem::kP + grp * 16384 + r * 128;    // this thread's 128-byte row of P
-    uint8_t* dd = smem + BwdSmem::kDS + grp * 16384 + r * 128;   // ... and of dS
-    const float2 sc2 = make_float2(scale2, scale2), ss2 = make_float2(softmax_scale, softmax_scale);
-    const float* lse_h = lse + (size_t)head * T + seq_begin;
-    const float* dl_h = delta + (size_t)head * T + seq_begin;
-    float lse_n = (r < len) ? lse_h[r] : INFINITY;
-    float dl_n = (r < len) ? dl_h[r] : 0.f;
-    for (int i = 0; i < nq; ++i) {
-      const float nlse2 = -lse_n * kLog2e;           // -inf for rows past the sequence end => P = 0
-      const float ndl = -dl_n * softmax_scale;
-      {
-        const int nr = (i + 1) * 128 + r;            // prefetch the next tile's row statistics
-        lse_n = (nr < len) ? lse_h[nr] : INFINITY;
-        dl_n = (nr < len) ? dl_h[nr] : 0.f;
-      }
-      const float2 nl2 = make_float2(nlse2, nlse2), nd2 = make_float2(ndl, ndl);
-      // ---- X: P = exp2(S * scale2 - lse2) -> bf16 registers -> smem
-      uint32_t pp[32];
-      mbar_wait(s_full, i & 1);
-      tc_fence_after();
-      if (threadIdx.x == 128 && i < 4) trace_put(tr, 8 + 4 * i);
-      {
-        uint32_t va[32], vb[32];
-        if (!(ablate & 8)) {
-          tmem_ld_32x32(tmem_base + lane_base + grp * 64, va);
-          tmem_ld_32x32(tmem_base + lane_base + grp * 64 + 32, vb);
-          tmem_ld_wait();
-        } else {  // timing ablation: no score read (results are wrong)
-#pragma unroll
-          for (int t = 0; t < 32; ++t) va[t] = vb[t] = __float_as_uint(0.01f * (float)(t + lane));
-        }
-        if (!full) {
-#pragma unroll
-          for (int t = 0; t < 32; ++t) {
-            if (t >= kv_valid) va[t] = 0xff800000u;  // -inf => P = 0
-            if (32 + t >= kv_valid) vb[t] = 0xff800000u;
-          }
-        }
-#pragma unroll
-        for (int t = 0; t < 16; ++t) {
-          const float2 xa = ffma2(make_float2(__uint_as_float(va[2 * t]), __uint_as_float(va[2 * t + 1])), sc2, nl2);
-          pp[t] = (ablate & 2) ? pack_bf16x2(xa.x, xa.y) : pack_bf16x2(fast_exp2(xa.x), fast_exp2(xa.y));
-        }
-#pragma unroll
-        for (int t = 0; t < 16; ++t) {
-          const float2 xb = ffma2(make_float2(__uint_as_float(vb[2 * t]), __uint_as_float(vb[2 * t + 1])), sc2, nl2);
-          pp[16 + t] = (ablate & 2) ? pack_bf16x2(xb.x, xb.y) : pack_bf16x2(fast_exp2(xb.x), fast_exp2(xb.y));
-        }
-      }
-      if (i > 0) mbar_wait(p_free, (i - 1) & 1);  // dV(i-1) has finished reading the P buffer
-      if (!(ablate & 4)) {
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch)
-          *reinterpret_cast<uint4*>(dp + ((ch ^ (r & 7)) << 4)) = make_uint4(pp[4 * ch], pp[4 * ch + 1], pp[4 * ch + 2], pp[4 * ch + 3]);
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(p_ready);
-      if (threadIdx.x == 128 && i < 4) trace_put(tr, 9 + 4 * i);
-      // ---- Y: dS = P * (dP * scale - delta * scale) -> smem
-      mbar_wait(dp_full, i & 1);
-      tc_fence_after();
-      if (i > 0) mbar_wait(dq_full, (i - 1) & 1);  // dK(i-1), dQ(i-1) have finished reading the dS buffer
-      if (threadIdx.x == 128 && i < 4) trace_put(tr, 10 + 4 * i);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t vd[32];
-        if (!(ablate & 8)) {
-          tmem_ld_32x32(tmem_base + lane_base + 128 + grp * 64 + c * 32, vd);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int t = 0; t < 32; ++t) vd[t] = __float_as_uint(0.01f * (float)(t + lane));
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint32_t w[4];
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float2 pv = unpack_bf16x2(pp[c * 16 + q * 4 + t]);
-            const float2 g = ffma2(make_float2(__uint_as_float(vd[8 * q + 2 * t]), __uint_as_float(vd[8 * q + 2 * t + 1])), ss2, nd2);
-            const float2 ds = fmul2(pv, g);
-            w[t] = pack_bf16x2(ds.x, ds.y);
-          }
-          const int ch = c * 4 + q;
-          if (!(ablate & 4)) *reinterpret_cast<uint4*>(dd + ((ch ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(ds_ready);
-      if (threadIdx.x == 128 && i < 4) trace_put(tr, 11 + 4 * i);
-    }
-    // dV (group 0) / dK (group 1): TMEM -> bf16 -> dqkv rows of this key tile
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    if (threadIdx.x == 128) trace_put(tr, 24);
-    // dV (group 0) / dK (group 1) -> bf16 -> the (dead) P buffer, one swizzled 128-byte row per thread; then each group
-    // copies its tile out with row-contiguous 16-byte stores (see attn_fwd2_kernel)
-    uint8_t* stg = smem + BwdSmem::kP + grp * 16384;
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + lane_base + 256 + grp * 64 + c * 32, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint4 w;
-        w.x = pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
-        w.y = pack_bf16x2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
-        w.z = pack_bf16x2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
-        w.w = pack_bf16x2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
-        *reinterpret_cast<uint4*>(stg + r * 128 + (((c * 4 + q) ^ (r & 7)) << 4)) = w;
-      }
-    }
-    named_bar_sync(2 + grp, 128);
-    {
-      const int tid = (threadIdx.x - 128) & 127;
-      const int rows_ok = min(128, len - k0);
-      uint8_t* obase = reinterpret_cast<uint8_t*>(dqkv + ((size_t)(seq_begin + k0) * 3 + (grp == 0 ? 2 : 1)) * H * kDh + (size_t)head * kDh);
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int idx = it * 128 + tid, row = idx >> 3, ch = idx & 7;
-        if (row < rows_ok)
-          *reinterpret_cast<uint4*>(obase + (size_t)row * 3 * H * kDh * 2 + ch * 16) =
-              *reinterpret_cast<const uint4*>(stg + row * 128 + ((ch ^ (row & 7)) << 4));
-      }
-    }
-  } else if (warp >= 12) {
-    // ---------------------------------------------------------------- dQ drain: one thread per query row, 64 columns
-    const int ew = warp & 3;
-    const int r = ew * 32 + lane;
-    const int etid = threadIdx.x - 384;
-    const uint32_t lane_base = static_cast<uint32_t>(ew * 32) << 16;
-    uint8_t* stage = smem + BwdSmem::kDQ;  // two [128 x 32] fp32 boxes (128-byte rows, 128B swizzle)
-    for (int i = 0; i < nq; ++i) {
-      const bool row_ok = i * 128 + r < len;
-      mbar_wait(dq_full, i & 1);
-      tc_fence_after();
-      if (etid == 0 && i < 4) trace_put(tr, 28 + 3 * i);
-      uint32_t va[32], vb[32];
-      tmem_ld_32x32(tmem_base + lane_base + 384, va);
-      tmem_ld_32x32(tmem_base + lane_base + 384 + 32, vb);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(dq_free);  // the next tile's dQ MMA may overwrite the columns
-      if (etid == 0) tma_store_wait_read<0>();  // the previous reduce-add has finished reading the stage
-      named_bar_sync(1, 128);
-      if (etid == 0 && i < 4) trace_put(tr, 29 + 3 * i);
-      uint8_t* d0 = stage + r * 128;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        *reinterpret_cast<uint4*>(d0 + ((q ^ (r & 7)) << 4)) =
-            make_uint4(row_ok ? va[4 * q] : 0u, row_ok ? va[4 * q + 1] : 0u, row_ok ? va[4 * q + 2] : 0u, row_ok ? va[4 * q + 3] : 0u);
-        *reinterpret_cast<uint4*>(d0 + 16384 + ((q ^ (r & 7)) << 4)) =
-            make_uint4(row_ok ? vb[4 * q] : 0u, row_ok ? vb[4 * q + 1] : 0u, row_ok ? vb[4 * q + 2] : 0u, row_ok ? vb[4 * q + 3] : 0u);
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(1, 128);
-      if (etid == 0 && !(ablate & 1)) {  // (ablation bit 1: the dQ partial is dropped)
-        tma_reduce_add_2d(&tmDQ, stage, col_o, seq_begin + i * 128);
-        tma_reduce_add_2d(&tmDQ, stage + 16384, col_o + 32, seq_begin + i * 128);
-        tma_store_commit();
-      }
-      if (etid == 0 && i < 4) trace_put(tr, 30 + 3 * i);
-    }
-    if (etid == 0) tma_store_wait_read<0>();  // the stage must outlive the TMA reads; the adds complete by kernel end
-    if (etid == 0) trace_put(tr, 48);
-  }
-  if (threadIdx.x == 128) trace_put(tr, 25);
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
-  }
-  if (threadIdx.x == 0) trace_put(tr, 50);
-}
-
 // ---------------------------------------------------------------------------------------------- backward, transposed scores
-// EXPERIMENTAL (CX_ATTN_BWD=3; written after the last GPU minute of round 1: it compiles, it has NOT run on hardware yet).
-// attn_bwd2_kernel is bound by the shared-memory port (368 KB per 128 x 128 tile: MMA operands + P / dS stores + dQ staging).
+// One CTA = (sequence, head, 128 keys); loops over query tiles.  The straightforward formulation (S = Q K^T, P and dS through
+// shared memory as the A operands of dV += P^T dO and dK += dS^T Q) is bound by the shared-memory port: 368 KB per 128 x 128
+// tile (MMA operands + P / dS stores + dQ staging), 2900 clk against 1664 clk of tensor time (round 1: 376 us at 64 x 512 x
+// 12 incl. delta and finalize; this kernel 351 us; FlashAttention-2 on the same box 547 us).
 // Here the scores are computed TRANSPOSED, S^T = K_j Q_i^T and dP^T = V_j dO_i^T (lane = key, column = query), so that P^T and
 // dS^T -- the A operands of dV += P^T dO and dK += dS^T Q -- are written back into tensor memory (bf16 pairs, over the
 // thread's own first 32 score columns) and those two contractions read only their B operand from shared memory (a TS MMA
@@ -702,7 +59,7 @@ __global__ void __launch_bounds__(kBwd2Threads, 1)
 attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                  const __grid_constant__ CUtensorMap tmDQ, const int* __restrict__ cu_seqlens,
                  const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T,
-                 int H, float softmax_scale) {
+                 int H, float softmax_scale, const float* __restrict__ rope_inv_freq) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Bwd3Smem::kBars);
@@ -943,19 +300,56 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     mbar_wait(acc_full, 0);
     tc_fence_after();
     uint8_t* stg = smem + Bwd3Smem::kDS + grp * 16384;
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + lane_base + 256 + grp * 64 + c * 32, v);
+    if (grp == 1 && rope_inv_freq != nullptr) {
+      // dK with the transposed rotary embedding (the keys were rotated before the scores were formed): a thread owns one key
+      // row, i.e. both halves (x1 = columns [0,32), x2 = [32,64)) of the head; the key's position is its row index in the sequence
+      //   d x1 = g1 cos + g2 sin,  d x2 = g2 cos - g1 sin      (forward: o1 = x1 cos - x2 sin, o2 = x2 cos + x1 sin)
+      uint32_t v1[32], v2[32];
+      tmem_ld_32x32(tmem_base + lane_base + 256 + 64, v1);
+      tmem_ld_32x32(tmem_base + lane_base + 256 + 64 + 32, v2);
       tmem_ld_wait();
+      const float posf = (float)(k0 + r);
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const float2 f2 = __ldg(reinterpret_cast<const float2*>(rope_inv_freq + j));
+        const float a0 = posf * f2.x, a1 = posf * f2.y;
+        const float c0 = __cosf(a0), s0 = __sinf(a0), c1 = __cosf(a1), s1 = __sinf(a1);
+        const float g10 = __uint_as_float(v1[j]), g11 = __uint_as_float(v1[j + 1]);
+        const float g20 = __uint_as_float(v2[j]), g21 = __uint_as_float(v2[j + 1]);
+        v1[j] = __float_as_uint(g10 * c0 + g20 * s0);
+        v1[j + 1] = __float_as_uint(g11 * c1 + g21 * s1);
+        v2[j] = __float_as_uint(g20 * c0 - g10 * s0);
+        v2[j + 1] = __float_as_uint(g21 * c1 - g11 * s1);
+      }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        uint4 w;
-        w.x = pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
-        w.y = pack_bf16x2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
-        w.z = pack_bf16x2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
-        w.w = pack_bf16x2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
-        *reinterpret_cast<uint4*>(stg + r * 128 + (((c * 4 + q) ^ (r & 7)) << 4)) = w;
+        uint4 w1, w2;
+        w1.x = pack_bf16x2(__uint_as_float(v1[8 * q + 0]), __uint_as_float(v1[8 * q + 1]));
+        w1.y = pack_bf16x2(__uint_as_float(v1[8 * q + 2]), __uint_as_float(v1[8 * q + 3]));
+        w1.z = pack_bf16x2(__uint_as_float(v1[8 * q + 4]), __uint_as_float(v1[8 * q + 5]));
+        w1.w = pack_bf16x2(__uint_as_float(v1[8 * q + 6]), __uint_as_float(v1[8 * q + 7]));
+        w2.x = pack_bf16x2(__uint_as_float(v2[8 * q + 0]), __uint_as_float(v2[8 * q + 1]));
+        w2.y = pack_bf16x2(__uint_as_float(v2[8 * q + 2]), __uint_as_float(v2[8 * q + 3]));
+        w2.z = pack_bf16x2(__uint_as_float(v2[8 * q + 4]), __uint_as_float(v2[8 * q + 5]));
+        w2.w = pack_bf16x2(__uint_as_float(v2[8 * q + 6]), __uint_as_float(v2[8 * q + 7]));
+        *reinterpret_cast<uint4*>(stg + r * 128 + ((q ^ (r & 7)) << 4)) = w1;
+        *reinterpret_cast<uint4*>(stg + r * 128 + (((4 + q) ^ (r & 7)) << 4)) = w2;
+      }
+    } else {
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + lane_base + 256 + grp * 64 + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
+          w.y = pack_bf16x2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
+          w.z = pack_bf16x2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
+          w.w = pack_bf16x2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
+          *reinterpret_cast<uint4*>(stg + r * 128 + (((c * 4 + q) ^ (r & 7)) << 4)) = w;
+        }
       }
     }
     named_bar_sync(2 + grp, 128);

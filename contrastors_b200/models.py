@@ -248,7 +248,7 @@ class _TrunkFn(torch.autograd.Function):
         v = model.view
         H, Dh = cfg.n_head, cfg.head_dim
         scale = 1.0 / math.sqrt(Dh)
-        cos_t, sin_t, _ = model.rope_tables(packed.max_seqlen)
+        cos_t, sin_t, inv_freq = model.rope_tables(packed.max_seqlen)
         if head is not None:
             pooled, head_save = ctx.head_state
             gp = ops.embed_head_bwd(pooled, g_out.contiguous().float(), head_save, head["hamming"], head["normalize"])
@@ -279,7 +279,7 @@ class _TrunkFn(torch.autograd.Function):
             dz1, do = r if pdrop > 0 else (r, r)
             dattn = ops.gemm(do, v(W, p + "attn.out_proj.weight"), b_major=MAJOR_MN)
             ops.gemm(do, attn, a_major=MAJOR_MN, b_major=MAJOR_MN, out=v(G, p + "attn.out_proj.weight"), accumulate=True)
-            dqkv = ops.attn_bwd(qkv, attn, dattn, lse, packed.cu, packed.max_seqlen, H, Dh, scale, packed.pos, cos_t, sin_t)
+            dqkv = ops.attn_bwd(qkv, attn, dattn, lse, packed.cu, packed.max_seqlen, H, Dh, scale, packed.pos, cos_t, sin_t, inv_freq)
             dh = ops.gemm(dqkv, v(W, p + "attn.Wqkv.weight"), b_major=MAJOR_MN)
             ops.gemm(dqkv, h, a_major=MAJOR_MN, b_major=MAJOR_MN, out=v(G, p + "attn.Wqkv.weight"), accumulate=True)
             if reducer is not None:

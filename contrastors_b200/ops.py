@@ -362,11 +362,6 @@ def embed_head_bwd(pooled, gout, save, hamming, normalize):
     return g
 
 
-def attn_select_kernels(fwd_generation=0, bwd_generation=0):
-    """A/B switch between attention kernel generations (0 = default); process-wide."""
-    _lib.check(_lib.load().cx_attn_select_kernels(int(fwd_generation), int(bwd_generation)), "cx_attn_select_kernels")
-
-
 def attn_fwd(qkv, cu_seqlens, max_seqlen, H, Dh, softmax_scale):
     """qkv [T, 3*H*Dh] bf16 (RoPE applied) -> (out [T, H*Dh] bf16, lse [H, T] fp32)."""
     T = qkv.shape[0]
@@ -382,8 +377,9 @@ def attn_fwd(qkv, cu_seqlens, max_seqlen, H, Dh, softmax_scale):
     return out, lse
 
 
-def attn_bwd(qkv, out, dout, lse, cu_seqlens, max_seqlen, H, Dh, softmax_scale, pos=None, cos_t=None, sin_t=None):
-    """Returns dqkv [T, 3*H*Dh] bf16; with pos/cos/sin the RoPE transpose is applied to dq and dk."""
+def attn_bwd(qkv, out, dout, lse, cu_seqlens, max_seqlen, H, Dh, softmax_scale, pos=None, cos_t=None, sin_t=None, inv_freq=None):
+    """Returns dqkv [T, 3*H*Dh] bf16; with pos/cos/sin/inv_freq the RoPE transpose is applied to dq (in the pass that converts
+    the fp32 dQ accumulator) and to dk (in the attention kernel's epilogue)."""
     T = qkv.shape[0]
     nseq = cu_seqlens.numel() - 1
     dqkv = torch.empty_like(qkv)
@@ -393,11 +389,12 @@ def attn_bwd(qkv, out, dout, lse, cu_seqlens, max_seqlen, H, Dh, softmax_scale, 
     ev = TIMER.begin("attn_bwd") if TIMER is not None else None
     _lib.check(lib.cx_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), cu_seqlens.data_ptr(),
                                dqkv.data_ptr(), dq_acc.data_ptr(), delta.data_ptr(), T, nseq, int(max_seqlen), H, Dh,
-                               float(softmax_scale), _stream()), "cx_attn_bwd")
+                               float(softmax_scale), _ptr(inv_freq) if pos is not None else 0, _stream()), "cx_attn_bwd")
     if pos is not None:
         _lib.check(lib.cx_dq_finalize_rope(dq_acc.data_ptr(), dqkv.data_ptr(), pos.data_ptr(), cos_t.data_ptr(),
                                            sin_t.data_ptr(), T, H, Dh, _stream()), "cx_dq_finalize_rope")
-        rope_inplace(dqkv, pos, cos_t, sin_t, H, Dh, backward=True, first_slot=1, num_slots=1)  # dk
+        if inv_freq is None:  # caller without the frequency table: separate rotary pass over the dk slot
+            rope_inplace(dqkv, pos, cos_t, sin_t, H, Dh, backward=True, first_slot=1, num_slots=1)
     else:
         _lib.check(lib.cx_dq_finalize(dq_acc.data_ptr(), dqkv.data_ptr(), T, H, Dh, _stream()), "cx_dq_finalize")
     if ev is not None:

@@ -186,22 +186,16 @@ CX_API int cx_cls_select_bwd(const float* g, void* dh, int B, int S, int d, cx_s
 /* ---- varlen non-causal attention on tcgen05 (replaces flash_attn_varlen_qkvpacked_func: layers/attention.py:158-181)
  * qkv [T,3,H,Dh] bf16 (RoPE already applied), cu_seqlens int32[nseq+1]; out [T,H,Dh] bf16; lse [H,T] fp32 (natural log).
  * Dh == 64.  Backward: dqkv [T,3,H,Dh] bf16 (dk, dv written directly; dq through the fp32 accumulator dq_acc [T,H*Dh],
- * which the caller zeroes and then finalises with cx_dq_finalize_rope or cx_dq_finalize). delta [H,T] fp32 scratch. */
+ * which the caller zeroes and then finalises with cx_dq_finalize_rope or cx_dq_finalize). delta [H,T] fp32 scratch.
+ * dk_rope_inv_freq (32 fp32 values, or NULL): when given, dk leaves the kernel already rotated back (the transpose of the
+ * rotary embedding applied to k before the forward; position = the key's index inside its sequence), so the caller runs no
+ * rotary pass over dqkv. */
 CX_API int cx_attn_fwd(const void* qkv, const int32_t* cu_seqlens, void* out, float* lse, int total_tokens, int nseq,
                 int max_seqlen, int H, int Dh, float softmax_scale, cx_stream_t stream);
 CX_API int cx_dq_finalize(const float* dq_acc, void* dqkv, int T, int H, int Dh, cx_stream_t stream);
 CX_API int cx_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const int32_t* cu_seqlens,
                 void* dqkv, float* dq_acc, float* delta, int total_tokens, int nseq, int max_seqlen, int H, int Dh,
-                float softmax_scale, cx_stream_t stream);
-
-/* A/B switch between kernel generations of the attention forward / backward (0 = the default; the generations and what was
- * measured for each are listed in csrc/cx_attn.cu).  Process-wide; used by tools/bench_attn.py and the parity tests of the
- * non-default generation. */
-CX_API int cx_attn_select_kernels(int fwd_generation, int bwd_generation);
-
-/* Profiling hook (only in builds with -DCX_DEBUG_HOOKS; an error otherwise): buf = device int64 [n_ctas, 64] (or NULL to switch off).  While set, the pipelined attention kernels
- * record clock64() stamps of their pipeline events per CTA (tools/trace_attn.py decodes them).  Never set in production. */
-CX_API int cx_debug_attn_trace(void* buf);
+                float softmax_scale, const float* dk_rope_inv_freq, cx_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -162,20 +162,11 @@ def _attn_ref(qkv, lens, H, Dh, scale):
     return torch.cat(outs, 0)
 
 
-@pytest.mark.parametrize("modes", [(0, 0), (6, 2)], ids=["default", "previous-generation"])
 @pytest.mark.parametrize("lens,H", [([128], 1), ([512, 512], 2), ([300, 17, 512, 129, 1], 3), ([197] * 4, 12), ([640, 1000], 2),
                                     ([64], 1), ([65, 191, 192, 193], 2)])
-def test_attention_fwd_bwd(lens, H, modes):
-    """Default generation = two-threads-per-row forward + transposed-score backward (first run on hardware in round 2)."""
+def test_attention_fwd_bwd(lens, H):
+    """Two-threads-per-row forward + transposed-score backward vs fp32 torch (ragged, ViT-like and > 512 lengths)."""
     from contrastors_b200 import ops
-    ops.attn_select_kernels(*modes)
-    try:
-        _attention_fwd_bwd(ops, lens, H)
-    finally:
-        ops.attn_select_kernels(0, 0)
-
-
-def _attention_fwd_bwd(ops, lens, H):
     torch.manual_seed(5)
     Dh = 64
     scale = 1.0 / math.sqrt(Dh)
@@ -198,6 +189,30 @@ def _attention_fwd_bwd(ops, lens, H):
     d = dqkv.float().view(T, 3, H, Dh)
     for i, name in enumerate(["dq", "dk", "dv"]):
         close(d[:, i], g[:, i], 2 ** -5, name)
+
+
+@pytest.mark.parametrize("lens,H", [([512, 512], 2), ([300, 17, 512, 129, 1], 3)])
+def test_attention_bwd_rotary_transpose_in_epilogue(lens, H):
+    """dk rotated back inside the attention backward's epilogue (position = row index inside the sequence, cos/sin from
+    pos * inv_freq) == the separate rotary pass over the dk slot it replaces; dq / dv are untouched by the switch."""
+    from contrastors_b200 import ops
+    torch.manual_seed(6)
+    Dh = 64
+    scale = 1.0 / math.sqrt(Dh)
+    T = sum(lens)
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device="cuda")
+    pos = ops.token_positions(cu, T)
+    inv = (1.0 / (1000.0 ** (torch.arange(0, Dh, 2, dtype=torch.float32) / Dh)))
+    fr = torch.outer(torch.arange(max(lens), dtype=torch.float32), inv)
+    cos_t, sin_t, inv_freq = torch.cos(fr).cuda(), torch.sin(fr).cuda(), inv.cuda().contiguous()
+    qkv = bf(torch.randn(T, 3 * H * Dh, device="cuda"))
+    out, lse = ops.attn_fwd(qkv, cu, max(lens), H, Dh, scale)
+    dout = bf(torch.randn(T, H * Dh, device="cuda"))
+    two = ops.attn_bwd(qkv, out, dout, lse, cu, max(lens), H, Dh, scale, pos, cos_t, sin_t, None).float().view(T, 3, H, Dh)
+    one = ops.attn_bwd(qkv, out, dout, lse, cu, max(lens), H, Dh, scale, pos, cos_t, sin_t, inv_freq).float().view(T, 3, H, Dh)
+    assert torch.equal(one[:, 2], two[:, 2])
+    close(one[:, 0], two[:, 0], 2 ** -7, "dq")   # dq: fp32 atomics in a different order only
+    close(one[:, 1], two[:, 1], 2 ** -6, "dk")   # one bf16 rounding instead of two
 
 
 def test_adamw_and_clip_match_torch():

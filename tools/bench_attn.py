@@ -26,9 +26,8 @@ def timeit(fn, iters=8, warm=2):
     return ts[len(ts) // 2]
 
 
-# usage: bench_attn.py [fwd_mode,bwd_mode ...]   (a trapped kernel poisons the context: one process per generation)
-MODES = [tuple(int(x) for x in a.split(",")) for a in sys.argv[1:]] or [(1, 1), (3, 2), (6, 2)]
-TAG = "_".join(f"{a}{b}" for a, b in MODES)
+MODES = [(8, 3)]  # the one generation left: two-threads-per-row forward, transposed-score backward
+TAG = "fwd4_bwd3"
 res = {}
 for name, nseq, S, H in [("bert_64x512", 64, 512, 12), ("vit_256x197", 256, 197, 12)]:
     Dh = 64
@@ -40,7 +39,6 @@ for name, nseq, S, H in [("bert_64x512", 64, 512, 12), ("vit_256x197", 256, 197,
     scale = 1.0 / math.sqrt(Dh)
     ref_out = ref_dqkv = None
     for fm, bm in MODES:
-        ops.attn_select_kernels(fm, bm)
         try:
             out, lse = ops.attn_fwd(qkv, cu, S, H, Dh, scale)
             dqkv = ops.attn_bwd(qkv, out, dout, lse, cu, S, H, Dh, scale)
