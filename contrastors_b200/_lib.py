@@ -62,6 +62,8 @@ SIGNATURES = {
     "cx_cls_select_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "cx_cls_select_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "cx_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
+    "cx_attn_pool_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    "cx_attn_pool_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "cx_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp]),
 }
 

@@ -766,6 +766,152 @@ __global__ void cls_select_bwd_kernel(const float* __restrict__ g, __nv_bfloat16
   dh[i] = tok == 0 ? __float2bfloat16_rn(g[(size_t)b * d + (i % d)]) : __float2bfloat16_rn(0.f);
 }
 
+// ---------------------------------------------------------------------------------------------- attention pooling (MAP)
+// Single-query multi-head attention over each sequence's keys/values (MultiHeadAttentionPooling's FlashAttentionPooling,
+// models/biencoder/modeling_biencoder.py:93-152, layers/attention.py:313-440): one learned latent query per head, shared by
+// every sequence.  kv [T, 2, H, 64] bf16 (packed tokens), q [H, 64] fp32, out [nseq, H, 64] fp32, lse [nseq, H].
+// One CTA per (sequence, head), 128 threads.  HBM-bound: kv is read once (twice in the backward).
+constexpr int kPoolThreads = 128;
+
+__device__ __forceinline__ float pool_block_reduce(float v, float* red, bool is_max) {
+  for (int o = 16; o > 0; o >>= 1) {
+    const float w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, w) : v + w;
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  v = red[0];
+  for (int i = 1; i < kPoolThreads / 32; ++i) v = is_max ? fmaxf(v, red[i]) : v + red[i];
+  return v;
+}
+
+// scores of this sequence's keys against the head's query -> sc[len] (shared), returns nothing; dot over 64 dims per key
+__device__ __forceinline__ void pool_scores(const __nv_bfloat16* __restrict__ kv, const float* qh, int begin, int len, int H, int head,
+                                            float scale, float* sc) {
+  for (int s = threadIdx.x; s < len; s += kPoolThreads) {
+    const __nv_bfloat16* kr = kv + ((size_t)(begin + s) * 2 * H + head) * 64;
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      BF8 v;
+      float f[8];
+      v.raw = *reinterpret_cast<const uint4*>(kr + c * 8);
+      v.unpack(f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmaf(f[j], qh[c * 8 + j], acc);
+    }
+    sc[s] = acc * scale;
+  }
+}
+
+__global__ void __launch_bounds__(kPoolThreads)
+attn_pool_fwd_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ kv, const int* __restrict__ cu, float* __restrict__ out,
+                     float* __restrict__ lse, int H, float scale) {
+  extern __shared__ float pool_smem[];
+  float* sc = pool_smem;  // [max_len]
+  __shared__ float red[kPoolThreads / 32];
+  __shared__ float qh[64];
+  __shared__ float part[2][64];
+  const int seq = blockIdx.x, head = blockIdx.y;
+  const int begin = cu[seq], len = cu[seq + 1] - begin;
+  if (threadIdx.x < 64) qh[threadIdx.x] = q[head * 64 + threadIdx.x];
+  __syncthreads();
+  pool_scores(kv, qh, begin, len, H, head, scale, sc);
+  __syncthreads();
+  float m = -INFINITY;
+  for (int s = threadIdx.x; s < len; s += kPoolThreads) m = fmaxf(m, sc[s]);
+  m = pool_block_reduce(m, red, true);
+  float l = 0.f;
+  for (int s = threadIdx.x; s < len; s += kPoolThreads) {
+    const float p = __expf(sc[s] - m);
+    sc[s] = p;
+    l += p;
+  }
+  l = pool_block_reduce(l, red, false);
+  __syncthreads();
+  // out[d] = sum_s p_s v[s][d] / l: thread = (key parity, dim)
+  const int d = threadIdx.x & 63, par = threadIdx.x >> 6;
+  float acc = 0.f;
+  for (int s = par; s < len; s += 2) acc = fmaf(sc[s], __bfloat162float(kv[((size_t)(begin + s) * 2 * H + H + head) * 64 + d]), acc);
+  part[par][d] = acc;
+  __syncthreads();
+  if (threadIdx.x < 64) out[((size_t)seq * H + head) * 64 + d] = (part[0][d] + part[1][d]) / l;
+  if (threadIdx.x == 0) lse[seq * H + head] = m + __logf(l);
+}
+
+// dq [H, 64] fp32 is ACCUMULATED with atomics over sequences (zero it first); dkv [T, 2, H, 64] bf16 is written.
+__global__ void __launch_bounds__(kPoolThreads)
+attn_pool_bwd_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ kv, const int* __restrict__ cu,
+                     const float* __restrict__ dout, const float* __restrict__ lse, float* __restrict__ dq,
+                     __nv_bfloat16* __restrict__ dkv, int H, float scale) {
+  extern __shared__ float pool_smem[];
+  const int seq = blockIdx.x, head = blockIdx.y;
+  const int begin = cu[seq], len = cu[seq + 1] - begin;
+  float* sc = pool_smem;          // [max_len]  scores, then d(score)
+  float* dp = pool_smem + ((len + 3) & ~3);  // [len]  p_s * <dout, v_s>, then d(score)
+  __shared__ float red[kPoolThreads / 32];
+  __shared__ float qh[64], go[64], dqh[64];
+  if (threadIdx.x < 64) {
+    qh[threadIdx.x] = q[head * 64 + threadIdx.x];
+    go[threadIdx.x] = dout[((size_t)seq * H + head) * 64 + threadIdx.x];
+    dqh[threadIdx.x] = 0.f;
+  }
+  __syncthreads();
+  pool_scores(kv, qh, begin, len, H, head, scale, sc);
+  __syncthreads();
+  const float L = lse[seq * H + head];
+  float dsum = 0.f;
+  for (int s = threadIdx.x; s < len; s += kPoolThreads) {
+    const float p = __expf(sc[s] - L);
+    const __nv_bfloat16* vr = kv + ((size_t)(begin + s) * 2 * H + H + head) * 64;
+    __nv_bfloat16* dvr = dkv + ((size_t)(begin + s) * 2 * H + H + head) * 64;
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      BF8 v, o;
+      float f[8], g[8];
+      v.raw = *reinterpret_cast<const uint4*>(vr + c * 8);
+      v.unpack(f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        dot = fmaf(f[j], go[c * 8 + j], dot);
+        g[j] = p * go[c * 8 + j];  // dv_s = p_s * dout
+      }
+      o.pack(g);
+      *reinterpret_cast<uint4*>(dvr + c * 8) = o.raw;
+    }
+    sc[s] = p;
+    dp[s] = p * dot;
+    dsum += p * dot;
+  }
+  dsum = pool_block_reduce(dsum, red, false);
+  __syncthreads();
+  for (int s = threadIdx.x; s < len; s += kPoolThreads) {
+    const float ds = (dp[s] - sc[s] * dsum) * scale;  // d loss / d (q . k_s)
+    const __nv_bfloat16* kr = kv + ((size_t)(begin + s) * 2 * H + head) * 64;
+    __nv_bfloat16* dkr = dkv + ((size_t)(begin + s) * 2 * H + head) * 64;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      BF8 o;
+      float g[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = ds * qh[c * 8 + j];
+      o.pack(g);
+      *reinterpret_cast<uint4*>(dkr + c * 8) = o.raw;
+    }
+    dp[s] = ds;
+  }
+  __syncthreads();
+  // dq[d] = sum_s ds_s k[s][d]
+  const int d = threadIdx.x & 63, par = threadIdx.x >> 6;
+  float acc = 0.f;
+  for (int s = par; s < len; s += 2) acc = fmaf(dp[s], __bfloat162float(kv[((size_t)(begin + s) * 2 * H + head) * 64 + d]), acc);
+  atomicAdd(&dqh[d], acc);
+  __syncthreads();
+  if (threadIdx.x < 64) atomicAdd(&dq[head * 64 + threadIdx.x], dqh[threadIdx.x]);
+}
+
 }  // namespace cx
 
 using namespace cx;
@@ -1088,6 +1234,31 @@ extern "C" int cx_cls_select_bwd(const float* g, void* dh, int B, int S, int d, 
   const int64_t n = (int64_t)B * S * d;
   if (n <= 0) return 0;
   cls_select_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>(g, (__nv_bfloat16*)dh, B, S, d);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cx_attn_pool_fwd(const float* q, const void* kv, const int32_t* cu_seqlens, float* out, float* lse, int nseq,
+                                int max_seqlen, int H, int Dh, float softmax_scale, cx_stream_t stream) {
+  CX_REQUIRE(q && kv && cu_seqlens && out && lse, "cx_attn_pool_fwd: null pointer");
+  CX_REQUIRE(Dh == 64, "cx_attn_pool_fwd: only head_dim 64 is implemented");
+  CX_REQUIRE(max_seqlen > 0 && max_seqlen <= 8192, "cx_attn_pool_fwd: sequences of 1..8192 tokens");
+  if (nseq <= 0) return 0;
+  const size_t smem = (size_t)((max_seqlen + 3) & ~3) * sizeof(float);
+  attn_pool_fwd_kernel<<<dim3(nseq, H), kPoolThreads, smem, STREAM>>>(q, (const __nv_bfloat16*)kv, cu_seqlens, out, lse, H, softmax_scale);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cx_attn_pool_bwd(const float* q, const void* kv, const int32_t* cu_seqlens, const float* dout, const float* lse,
+                                float* dq, void* dkv, int nseq, int max_seqlen, int H, int Dh, float softmax_scale, cx_stream_t stream) {
+  CX_REQUIRE(q && kv && cu_seqlens && dout && lse && dq && dkv, "cx_attn_pool_bwd: null pointer");
+  CX_REQUIRE(Dh == 64, "cx_attn_pool_bwd: only head_dim 64 is implemented");
+  CX_REQUIRE(max_seqlen > 0 && max_seqlen <= 4096, "cx_attn_pool_bwd: sequences of 1..4096 tokens");
+  if (nseq <= 0) return 0;
+  const size_t smem = (size_t)2 * ((max_seqlen + 3) & ~3) * sizeof(float);
+  attn_pool_bwd_kernel<<<dim3(nseq, H), kPoolThreads, smem, STREAM>>>(q, (const __nv_bfloat16*)kv, cu_seqlens, dout, lse, dq,
+                                                                     (__nv_bfloat16*)dkv, H, softmax_scale);
   CX_LAUNCH_CHECK();
   return 0;
 }

@@ -28,12 +28,15 @@ bool gemm_use_pair(const GemmArgs& g) {
   return !disabled && (cap == 0 || cap >= 2) && g.M >= 256 && ((g.mode == EPI_SWIGLU) || g.N % 256 == 0);
 }
 
-// QUAD (a cluster of two CTA pairs sharing their B tile through TMA multicast, see cx_gemm.cuh): for the M = tokens GEMMs of the
-// encoder (forward, dgrad).  CX_NO_QUAD=1 falls back to plain pairs.
+// QUAD (a cluster of two CTA pairs sharing their B tile through TMA multicast, see cx_gemm.cuh).  Measured on B200 in round 2
+// (profiles/r02b_bench_kernels_cluster2_vs_cluster4.json): correct (bitwise equal to pair mode) but 0-8 % SLOWER on every encoder
+// shape -- QKV 1231 vs 1288 TFLOP/s, out_proj 898 vs 944, fc2 1373 vs 1372, fc2-dgrad 1348 vs 1451, 8192^3 1447 vs 1523 -- so a
+// quarter less L2->SM traffic buys nothing: the pair kernel is not bound by the L2 fabric, and coupling the two pairs' stage
+// release costs more than the saved bytes.  Opt-in only (cx_gemm_select_cluster(4)); the default stays CTA pairs.
 bool gemm_use_quad(const GemmArgs& g) {
   static const bool disabled = getenv("CX_NO_QUAD") != nullptr;
   const int cap = g_max_cluster.load(std::memory_order_relaxed);
-  return !disabled && (cap == 0 || cap >= 4) && gemm_use_pair(g) && g.M % 512 == 0 &&
+  return !disabled && cap >= 4 && gemm_use_pair(g) && g.M % 512 == 0 &&
          (g.mode == EPI_STORE || g.mode == EPI_SWIGLU || g.mode == EPI_SWIGLU_BWD);
 }
 
@@ -41,7 +44,7 @@ template <int MODE, bool OUT_F32, bool ACCUM, bool A_MN, bool B_MN, int NP>
 static int launch_pair(const GemmArgs& g, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                        const CUtensorMap& tmD) {
   auto kern = gemm_kernel<256, A_MN, B_MN, MODE, OUT_F32, ACCUM, true, NP>;
-  constexpr int smem = GemmSmem<256, true>::kTotal;
+  constexpr int smem = GemmSmem<256, true, MODE>::kTotal;
   CX_SET_SMEM_ONCE(kern, smem);
   const int tile_n = (MODE == EPI_SWIGLU) ? 128 : 256;
   const int tile_m = 256 * NP;
@@ -84,13 +87,17 @@ static int launch_one(const GemmArgs& g, const CUtensorMap& tmA, const CUtensorM
     if ((MODE == EPI_STORE || MODE == EPI_SWIGLU || MODE == EPI_SWIGLU_BWD) && gemm_use_quad(g)) return launch_pair<MODE, OUT_F32, ACCUM, A_MN, B_MN, 2>(g, tmA, tmB, tmC, tmD);
     return launch_pair<MODE, OUT_F32, ACCUM, A_MN, B_MN, 1>(g, tmA, tmB, tmC, tmD);
   }
-  auto kern = gemm_kernel<BLOCK_N, A_MN, B_MN, MODE, OUT_F32, ACCUM>;
-  constexpr int smem = GemmSmem<BLOCK_N>::kTotal;
-  CX_SET_SMEM_ONCE(kern, smem);  // per instantiation
-  const int grid = gemm_grid(g.M, g.N, g.splits, MODE == EPI_SWIGLU ? BLOCK_N / 2 : 0);
-  kern<<<grid, kGemmThreads, smem, g.stream>>>(tmA, tmB, tmC, tmD, g.M, g.N, g.K, g.splits, g.ep);
-  CX_LAUNCH_CHECK();
-  return 0;
+  if constexpr (MODE == EPI_SWIGLU_BWD) {
+    return fail(CX_ERR_UNSUPPORTED, "swiglu-bwd epilogue exists for CTA pairs only");
+  } else {
+    auto kern = gemm_kernel<BLOCK_N, A_MN, B_MN, MODE, OUT_F32, ACCUM>;
+    constexpr int smem = GemmSmem<BLOCK_N>::kTotal;
+    CX_SET_SMEM_ONCE(kern, smem);  // per instantiation
+    const int grid = gemm_grid(g.M, g.N, g.splits, MODE == EPI_SWIGLU ? BLOCK_N / 2 : 0);
+    kern<<<grid, kGemmThreads, smem, g.stream>>>(tmA, tmB, tmC, tmD, g.M, g.N, g.K, g.splits, g.ep);
+    CX_LAUNCH_CHECK();
+    return 0;
+  }
 }
 
 template <int BLOCK_N, int MODE, bool OUT_F32, bool ACCUM>

@@ -74,24 +74,26 @@ constexpr int kUmmaK = 16;
 constexpr int kGemmThreads = 384;  // 4 control warps + 8 epilogue warps (2 per SMSP: TLP hides TMEM-load latency)
 constexpr int kStageCBytes = 16384;  // 128 rows x 128 B
 
-// NP = 2 (QUAD): a cluster of FOUR CTAs = two such pairs stacked in M (a 512 x 256 super tile).  The pairs need the same B
-// tile, so each B half (128 rows) is fetched ONCE per cluster: the two CTAs that hold the same half each load 64 of its rows
-// and TMA-multicast them to both.  Why: the 256 x 256 pair kernel moves 64 KB from L2 per 512-clk k-block per SM pair =
-// 6.3 KB/clk over the chip, which is the measured L2->SM cap (B300_MICROARCH.md "LTS throughput cap ~6300 B/cyc";
-// profiles/r01_gemm_final_ncu_full_raw.csv: l1tex__m_xbar2l1tex_read_bytes 10.3 TB/s at 1.64 GHz) -- the GEMM was L2-bound, not
-// tensor-bound.  Sharing B cuts that traffic by a quarter (48 KB per pair per k-block).
+// NP = 2 (QUAD, opt-in): a cluster of FOUR CTAs = two such pairs stacked in M (a 512 x 256 super tile).  The pairs need the same
+// B tile, so each B half (128 rows) is fetched ONCE per cluster: the two CTAs that hold the same half each load 64 of its rows
+// and TMA-multicast them to both (48 instead of 64 KB from L2 per pair per k-block).  Hypothesis: the pair kernel's 6.3 KB/clk
+// of L2->SM traffic (profiles/r01_gemm_final_ncu_full_raw.csv: 10.3 TB/s at 1.64 GHz) sits at the fabric's cap.  Measured in
+// round 2: it does not -- the multicast form is 0-8 % slower (see gemm_use_quad in cx_gemm.cu), so pairs stay the default.
 // PAIR: two CTAs of a cluster cooperate on one 256 x 256 tile (tcgen05 cta_group::2): each CTA stages its own 128 rows of
 // A and 128 of the 256 B rows (so the B operand is read from shared memory once per SM pair), the leader CTA issues the
 // MMAs for both, each CTA drains the 128 x 256 half of the accumulator that lives in its own TMEM.
-template <int BLOCK_N, bool PAIR = false>
+template <int BLOCK_N, bool PAIR = false, int MODE = 0>
 struct GemmSmem {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = (PAIR ? BLOCK_N / 2 : BLOCK_N) * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   // pair mode trades one pipeline stage (32 KB) for ping-pong epilogue staging (2 buffers per column half), so a TMA
   // store never has to drain before the next 64 columns are packed
-  static constexpr int kCBufs = PAIR ? 4 : 2;
-  static constexpr int kStages = PAIR ? 5 : ((BLOCK_N == 256) ? 4 : 6);
+  // EPI_SWIGLU_BWD (pairs only): the epilogue streams [y | gate] tiles through shared memory, two 64-column steps per group
+  // double-buffered = 8 x 16 KB, paid for with two pipeline stages (the kernel is bound by that stream, not by the mainloop)
+  static constexpr bool kStreamEpi = MODE == 4;
+  static constexpr int kCBufs = kStreamEpi ? 8 : (PAIR ? 4 : 2);
+  static constexpr int kStages = kStreamEpi ? 3 : (PAIR ? 5 : ((BLOCK_N == 256) ? 4 : 6));
   static constexpr int kBarrierBytes = 256;
   static constexpr int kTotal = 1024 + kStages * kStageBytes + kCBufs * kStageCBytes + kBarrierBytes;
 };
@@ -101,7 +103,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD, int M, int N, int K,
             int splits, EpiParams ep) {
-  using S = GemmSmem<BLOCK_N, PAIR>;
+  using S = GemmSmem<BLOCK_N, PAIR, MODE>;
+  static_assert(MODE != EPI_SWIGLU_BWD || PAIR, "the swiglu-backward epilogue is sized for CTA pairs");
   static_assert(!PAIR || BLOCK_N == 256, "CTA pairs use 256-column tiles");
   static_assert(NP == 1 || (NP == 2 && PAIR), "a quad cluster is two CTA pairs");
   constexpr bool QUAD = NP == 2;
@@ -150,9 +153,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], PAIR ? 257 : 256);  // pair: the leader's 256 epilogue threads + ONE forwarded arrive from the peer
     }
-    if (MODE == EPI_SWIGLU_BWD) {  // one "pre-activation tiles landed" barrier per epilogue group
-      mbar_init(bars + 16, 1);
-      mbar_init(bars + 17, 1);
+    if (MODE == EPI_SWIGLU_BWD) {  // "pre-activation tiles landed": one barrier per epilogue group and staging slot
+      for (int i = 0; i < 4; ++i) mbar_init(bars + 16 + i, 1);
     }
     fence_barrier_init();
   }
@@ -311,6 +313,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const float ep_scale = ep.scale * (ep.scale_dev != nullptr ? *ep.scale_dev : 1.f);
     const float ep_coef = ep.coef * (ep.coef_dev != nullptr ? *ep.coef_dev : 1.f);
     const float ep_alpha = ep.alpha * (ep.alpha_dev != nullptr ? *ep.alpha_dev : 1.f) * (ep.alpha_dev2 != nullptr ? *ep.alpha_dev2 : 1.f);
+    if (MODE == EPI_SWIGLU_BWD && etid == 0 && tile_start < num_tiles) {  // the first work item's [y | gate] tiles, both steps
+      const int mn1 = tile_start / splits;
+      const int m1 = (mn1 / n_tiles) * TILE_M + pair_m + (int)cta_rank * kBlockM, n1 = (mn1 % n_tiles) * BLOCK_N + hf * HALF_N;
+#pragma unroll
+      for (int pr = 0; pr < 2; ++pr) {
+        mbar_arrive_expect_tx(bars + 16 + 2 * hf + pr, 2 * kStageCBytes);
+        tma_load_2d(stage_base + (2 * pr) * kStageCBytes, &tmD, bars + 16 + 2 * hf + pr, n1 + pr * 64, m1);
+        tma_load_2d(stage_base + (2 * pr + 1) * kStageCBytes, &tmD, bars + 16 + 2 * hf + pr, N + n1 + pr * 64, m1);
+      }
+    }
     for (int tile = tile_start; tile < num_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -334,14 +346,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (MODE == EPI_NCE_DS) lse2 = row_ok ? ep.lse[row] * kLog2e : INFINITY;  // +inf => p == 0 for rows past M
       }
 
-      if (MODE == EPI_SWIGLU_BWD && etid == 0) {
-        // request this tile's first [y | gate] tiles while its MMAs are still running: the staging pair is free once the previous
-        // tile's last stores have read it
-        tma_store_wait_read<0>();
-        mbar_arrive_expect_tx(bars + 16 + hf, 2 * kStageCBytes);
-        tma_load_2d(stage_base, &tmD, bars + 16 + hf, n0, m0);
-        tma_load_2d(stage_base + kStageCBytes, &tmD, bars + 16 + hf, N + n0, m0);
-      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N + hf * HALF_N;
@@ -396,24 +400,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       } else if (MODE == EPI_SWIGLU_BWD) {
         // this group owns d(act) columns [n0, n0 + 128): two 64-column steps, each transforming one y tile and one gate tile
-        // (128 rows x 128 B, swizzled exactly as TMA wrote them) IN PLACE; a thread only ever touches its own row
-        uint8_t* const buf_y = stage_base;
-        uint8_t* const buf_g = stage_base + kStageCBytes;
-        uint64_t* const ld_bar = bars + 16 + hf;
+        // (128 rows x 128 B, swizzled exactly as TMA wrote them) IN PLACE; a thread only ever touches its own row.  Two staging
+        // slots per group (slot = step): the tiles of BOTH steps are in flight before the accumulator is waited for, and the
+        // next work item's tiles are requested as soon as a slot's stores have been read (rolling prefetch, see the tail)
 #pragma unroll 1
         for (int pr = 0; pr < 2; ++pr) {
           const int col0 = n0 + pr * 64;
-          if (pr > 0 && etid == 0) {  // the first step's tiles were requested before the accumulator wait
-            tma_store_wait_read<0>();
-            mbar_arrive_expect_tx(ld_bar, 2 * kStageCBytes);
-            tma_load_2d(buf_y, &tmD, ld_bar, col0, m0);
-            tma_load_2d(buf_g, &tmD, ld_bar, N + col0, m0);
-          }
+          uint8_t* const buf_y = stage_base + (2 * pr) * kStageCBytes;
+          uint8_t* const buf_g = buf_y + kStageCBytes;
           uint32_t v1[32], v2[32];
           tmem_ld_32x32(taddr + pr * 64, v1);
           tmem_ld_32x32(taddr + pr * 64 + 32, v2);
-          mbar_wait(ld_bar, ld_phase);
-          ld_phase ^= 1u;
+          mbar_wait(bars + 16 + 2 * hf + pr, ld_phase);
           tmem_ld_wait();
           uint8_t* const ry = buf_y + row_in_tile * 128;
           uint8_t* const rg = buf_g + row_in_tile * 128;
@@ -443,6 +441,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tma_store_2d(&tmC, buf_g, N + col0, m0);
             tma_store_commit();
           }
+        }
+        ld_phase ^= 1u;
+        if (etid == 0 && tile + tile_step < num_tiles) {
+          // rolling prefetch of the next work item's tiles: slot 0 is free once its stores (the older bulk group) have been
+          // read, slot 1 once the group just committed has
+          const int mn2 = (tile + tile_step) / splits;
+          const int m2 = (mn2 / n_tiles) * TILE_M + pair_m + (int)cta_rank * kBlockM, n2 = (mn2 % n_tiles) * BLOCK_N + hf * HALF_N;
+          tma_store_wait_read<1>();
+          mbar_arrive_expect_tx(bars + 16 + 2 * hf, 2 * kStageCBytes);
+          tma_load_2d(stage_base, &tmD, bars + 16 + 2 * hf, n2, m2);
+          tma_load_2d(stage_base + kStageCBytes, &tmD, bars + 16 + 2 * hf, N + n2, m2);
+          tma_store_wait_read<0>();
+          mbar_arrive_expect_tx(bars + 17 + 2 * hf, 2 * kStageCBytes);
+          tma_load_2d(stage_base + 2 * kStageCBytes, &tmD, bars + 17 + 2 * hf, n2 + 64, m2);
+          tma_load_2d(stage_base + 3 * kStageCBytes, &tmD, bars + 17 + 2 * hf, N + n2 + 64, m2);
         }
       } else if (MODE == EPI_STORE && !OUT_F32) {
         // bf16 store path: one staging row (128 B) = 64 columns = two TMEM chunks = one attention head when RoPE is on

@@ -399,11 +399,21 @@ def grad_cache_loss(tower1, t1_inputs, tower2, t2_inputs, chunk_size, logit_scal
     # through that tower's weights -- tower 2's last chunk when both towers share the weights
     trunk1, trunk2 = getattr(tower1, "trunk", tower1), getattr(tower2, "trunk", tower2)
     red = _grad_reducers or {}
-    second_pass = bool(tower2.training)
+
+    def _trainable(tower):  # a tower without parameters() (a bare callable) is treated as trainable, as the reference does
+        params = getattr(tower, "parameters", None)
+        return params is None or any(p.requires_grad for p in params())
+
+    # LiT (BASELINE configs[4]: frozen vision tower 1 + trainable text tower 2): the reference's pass 2 back-propagates through
+    # tower 1 unconditionally and dies with "does not require grad" on a fully frozen tower (its own comment at loss.py:169,
+    # "not sure this works for LiT"); a frozen tower has nothing to accumulate, so its pass 2 is skipped here
+    first_pass = _trainable(tower1)
+    second_pass = bool(tower2.training) and _trainable(tower2)
     r1 = red.get(id(trunk1)) if not (second_pass and trunk1 is trunk2) else None
     r2 = red.get(id(trunk2)) if second_pass else None
-    accumulate_gradients(tower1, chunked_queries, query_cache.split(chunk_size), query_rand_states,
-                         router_aux_coeff=router_aux_coeff, _grad_reducer=r1)
+    if first_pass:
+        accumulate_gradients(tower1, chunked_queries, query_cache.split(chunk_size), query_rand_states,
+                             router_aux_coeff=router_aux_coeff, _grad_reducer=r1)
     if second_pass:
         accumulate_gradients(tower2, chunked_documents, document_cache.split(chunk_size), doc_rand_states,
                              router_aux_coeff=router_aux_coeff, _grad_reducer=r2)

@@ -52,6 +52,45 @@ def forward_step(model, batch, logit_scale, matryoshka_dims=None, matryoshka_los
     return {"loss": loss}
 
 
+class BatchPrefetcher:
+    """Input edge (reference: the trainer copies each batch on the compute stream right before the step,
+    trainers/text_text.py:308,333-343).  Wraps an iterator of HOST batches (pinned tensors in the reference's collate schema) and
+    keeps one batch in flight: batch i+1 is copied host->device on a side stream while step i computes; ``next()`` makes the
+    compute stream wait for that copy only.  CPU-side entries (``*_seq_lens``, ``dataset_name``) pass through untouched."""
+
+    def __init__(self, batches, device):
+        self.it = iter(batches)
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._next = None
+        self._preload()
+
+    def _preload(self):
+        try:
+            host = next(self.it)
+        except StopIteration:
+            self._next = None
+            return
+        with torch.cuda.stream(self.stream):
+            self._next = {k: (v.to(self.device, non_blocking=True) if isinstance(v, torch.Tensor) and not k.endswith("seq_lens") else v)
+                          for k, v in host.items()}
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._next is None:
+            raise StopIteration
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_stream(self.stream)
+        batch = self._next
+        for v in batch.values():
+            if isinstance(v, torch.Tensor) and v.is_cuda:
+                v.record_stream(cur)  # allocated on the copy stream, consumed on the compute stream
+        self._preload()
+        return batch
+
+
 class _ScalarAdamW:
     """AdamW (weight_decay 0: ``logit_scale`` is in the reference's no-decay group, optimizer.py:22-23) for the 0-dim
     logit-scale parameter, as a handful of 1-element device ops: no host sync, no torch optimizer object (whose global

@@ -37,8 +37,9 @@ CX_API int cx_version(void);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches evidence) */
 CX_API unsigned long long cx_launch_count(void);
 
-/* A/B switch of the GEMM launch mode, process-wide: the largest cluster the launcher may use (0 = default = 4: two CTA pairs
- * sharing their B tile by TMA multicast when M % 512 == 0; 2 = CTA pairs (cta_group::2); 1 = one CTA per tile). */
+/* A/B switch of the GEMM launch mode, process-wide: the largest cluster the launcher may use (0 = default = 2: CTA pairs,
+ * cta_group::2; 4 = two CTA pairs sharing their B tile by TMA multicast when M % 512 == 0 -- measured slower, opt-in;
+ * 1 = one CTA per tile). */
 CX_API int cx_gemm_select_cluster(int max_cluster_ctas);
 
 /* ---- dense contraction on tcgen05 (replaces torch.matmul / FusedDense = cuBLASLt:
@@ -182,6 +183,15 @@ CX_API int cx_vit_assemble_fwd(const void* proj, const float* cls, const float* 
 CX_API int cx_vit_assemble_bwd(const void* dz, void* dproj, float* dcls, float* dpos, int B, int nP, int d, cx_stream_t stream);
 CX_API int cx_cls_select_fwd(const void* h, float* out, int B, int S, int d, cx_stream_t stream);
 CX_API int cx_cls_select_bwd(const float* g, void* dh, int B, int S, int d, cx_stream_t stream);
+
+/* ---- attention pooling: ONE learned query per head against every sequence's keys / values (FlashAttentionPooling inside
+ * MultiHeadAttentionPooling, /root/reference/src/contrastors/layers/attention.py:313-440, models/biencoder/
+ * modeling_biencoder.py:93-152).  q [H, 64] fp32 (Wq(latent)); kv [T, 2, H, 64] bf16 over packed tokens; out [nseq, H, 64] fp32;
+ * lse [nseq, H].  Backward: dkv written (bf16), dq ACCUMULATED (the caller zeroes it). */
+CX_API int cx_attn_pool_fwd(const float* q, const void* kv, const int32_t* cu_seqlens, float* out, float* lse, int nseq, int max_seqlen,
+                     int H, int Dh, float softmax_scale, cx_stream_t stream);
+CX_API int cx_attn_pool_bwd(const float* q, const void* kv, const int32_t* cu_seqlens, const float* dout, const float* lse, float* dq,
+                     void* dkv, int nseq, int max_seqlen, int H, int Dh, float softmax_scale, cx_stream_t stream);
 
 /* ---- varlen non-causal attention on tcgen05 (replaces flash_attn_varlen_qkvpacked_func: layers/attention.py:158-181)
  * qkv [T,3,H,Dh] bf16 (RoPE already applied), cu_seqlens int32[nseq+1]; out [T,H,Dh] bf16; lse [H,T] fp32 (natural log).

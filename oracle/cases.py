@@ -41,6 +41,12 @@ VIT_CASES = {
     "tiny": dict(n_embd=128, n_head=2, n_inner=256, n_layer=2, img=64, patch=16, act="quick_gelu", batch=3, wseed=8, seed=61),
     "tiny_gelu": dict(n_embd=192, n_head=3, n_inner=384, n_layer=2, img=96, patch=32, act="gelu", batch=2, wseed=9, seed=62),
 }
+# real dims of BASELINE configs[2] / configs[4]: CLIP ViT-B/16 (197 tokens x 768, 12 layers) and ViT-L/14 (257 tokens x 1024, 24
+# layers, 16 heads, inner 4096, patch 14 -> K = 588 on the patch GEMM); 2 images keep the fp32 CPU oracle in seconds
+VIT_FULL_CASES = {
+    "vit_b16": dict(n_embd=768, n_head=12, n_inner=3072, n_layer=12, img=224, patch=16, act="quick_gelu", batch=2, wseed=18, seed=71),
+    "vit_l14": dict(n_embd=1024, n_head=16, n_inner=4096, n_layer=24, img=224, patch=14, act="quick_gelu", batch=2, wseed=19, seed=72),
+}
 GRADCACHE_CASE = dict(n=8, chunk=3, din=16, dout=32, scale=20.0, seed=51)
 # unsaturated variant (loss ~ 1, not 1e-3) whose tower computes in fp32 even under autocast, so the GPU run differs from the
 # reference's fp32 CPU run only by the bf16 rounding of the embeddings entering the fused loss: a tight driver check

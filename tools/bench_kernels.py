@@ -59,7 +59,15 @@ for keep in (False, True):
     ops.gemm_select_cluster(0)
     res[f"gemm_swiglu_32768x3072x768_keep{int(keep)}"] = ent
     print(list(res.items())[-1], flush=True)
-del x, w1, a, b, out
+dm = torch.randn(32768, 768, device="cuda").to(torch.bfloat16)
+w2 = (torch.randn(768, 3072, device="cuda") / 28).to(torch.bfloat16)
+yg = torch.randn(32768, 6144, device="cuda").to(torch.bfloat16)
+ms_f = timeit(lambda: ops.gemm_swiglu_bwd(dm, w2, yg))
+ms_2 = timeit(lambda: ops.swiglu_bwd(ops.gemm(dm, w2, b_major=1), yg))
+res["gemm_swiglu_bwd_32768x3072x768"] = dict(fused_ms=ms_f, dgrad_then_swiglu_bwd_ms=ms_2, hbm_bytes=2 * 32768 * 6144 * 2 + 32768 * 768 * 2,
+                                             fused_gbs=(2 * 32768 * 6144 * 2 + 32768 * 768 * 2) / ms_f / 1e6)
+print(list(res.items())[-1], flush=True)
+del x, w1, a, b, out, dm, w2, yg
 
 n, m, dim = 2048, 16384, 768
 g = torch.Generator().manual_seed(1234)
