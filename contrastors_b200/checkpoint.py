@@ -118,15 +118,24 @@ def read_state_dict(model_dir: str) -> dict:
 
 def load_weights(model: BiEncoder, sd: dict, strict: bool = True) -> None:
     """Load a reference state dict (BiEncoder keys ``trunk.*`` or bare trunk keys) into the flat master buffer."""
-    trunk = {}
+    trunk, head = {}, {}
     for k, v in sd.items():
         if k.startswith("trunk."):
             trunk[k[len("trunk."):]] = v
         elif k.startswith(("embeddings.", "emb_ln.", "encoder.")):
             trunk[k] = v
-        elif strict:
-            raise KeyError(f"unexpected key {k!r}: this tower has no projection / pooling parameters")
+        else:
+            head[k] = v  # proj.* / selector.* (modeling_biencoder.py:270-285)
     model.trunk.load_reference_state_dict(trunk, strict=strict)
+    own = {k: p for k, p in model.named_parameters() if not k.startswith("trunk.")}
+    unexpected = [k for k in head if k not in own]
+    missing = [k for k in own if k not in head]
+    if strict and (unexpected or missing):
+        raise KeyError(f"head parameters do not match this tower: unexpected {unexpected}, missing {missing}")
+    with torch.no_grad():
+        for k, v in head.items():
+            if k in own:
+                own[k].copy_(v.to(own[k].device, own[k].dtype))
 
 
 def from_pretrained(model_dir: str, device: Optional[str] = None, strict: bool = True) -> BiEncoder:

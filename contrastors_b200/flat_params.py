@@ -102,7 +102,7 @@ class FlatParamModule(nn.Module):
         self._shadow, self._shadow_version = None, None
         if self._opt_state is not None:  # the Adam moments follow the weights (.to() / .cuda() mid-run keeps them)
             st = self._opt_state
-            self._opt_state = dict(step=st["step"], m=fn(st["m"]).float(), v=fn(st["v"]).float())
+            self._opt_state = dict(st, m=fn(st["m"]).float(), v=fn(st["v"]).float())
         self._on_apply()
         self._rebind()
         return self
@@ -166,10 +166,13 @@ class FlatParamModule(nn.Module):
         return self._shadow
 
     # ---------------------------------------------------------------- optimizer tail on the flat buffers
-    def fused_adamw_step(self, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, max_grad_norm=None, grad_scale=1.0):
+    def fused_adamw_step(self, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, max_grad_norm=None, grad_scale=1.0,
+                         extra_sq_norm=None):
         """clip_grad_norm_ + AdamW (decay on >=2-D weights only, optimizer.py:7-47) + zero_grad + bf16 refresh, fused:
         two launches over the flat buffers, no host sync (the clip coefficient stays on the device).  ``grad_scale``
-        multiplies the gradient first (1 / world_size after a SUM all-reduce = DDP's average)."""
+        multiplies the gradient first (1 / world_size after a SUM all-reduce = DDP's average).  ``extra_sq_norm`` (0-dim device
+        tensor): squared gradient norm of parameters living outside this buffer (poolers, projection) that share the global
+        clip; the 1-element clip coefficient is returned for them (None without clipping)."""
         if self._opt_state is None:
             self._opt_state = dict(step=0, m=torch.zeros_like(self._flat), v=torch.zeros_like(self._flat))
         st = self._opt_state
@@ -178,7 +181,12 @@ class FlatParamModule(nn.Module):
         coef = None
         if max_grad_norm is not None and max_grad_norm > 0:
             # the clip threshold applies to the SCALED gradient: ||s g|| <= c  <=>  ||g|| <= c / s
-            coef = ops.grad_clip_coef(self._flat_grad, max_grad_norm / grad_scale)[1:]
+            out2 = ops.grad_clip_coef(self._flat_grad, max_grad_norm / grad_scale)
+            if extra_sq_norm is None:
+                coef = out2[1:]
+            else:  # total norm over both parameter sets (torch.nn.utils.clip_grad_norm_'s 1e-6)
+                total = torch.sqrt((out2[0] * grad_scale) ** 2 + extra_sq_norm.to(out2.dtype))
+                coef = torch.clamp(max_grad_norm / (total + 1e-6), max=1.0).reshape(1)
         if self._shadow is None:
             self._shadow = torch.empty(self._n_total, device=self._flat.device, dtype=torch.bfloat16)
         nd = self._n_decay
@@ -187,6 +195,7 @@ class FlatParamModule(nn.Module):
                            betas[0], betas[1], eps, wd, st["step"], grad_scale_dev=coef, grad_scale=grad_scale, zero_grad=True)
         self._master_version += 1
         self._shadow_version = (self._master_version, _OPT_STEPS[0])  # the kernel just refreshed the shadow
+        return coef
 
     # ---------------------------------------------------------------- optimizer.pt in torch.optim.AdamW's layout
     def _optimizer_param_order(self, prefix: str):

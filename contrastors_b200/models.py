@@ -233,7 +233,10 @@ class _TrunkFn(torch.autograd.Function):
         ctx.saved, ctx.st0 = saved, st0
         if head is None:
             return h
-        pooled = ops.mean_pool_fwd(h, packed.cu)
+        if head.get("pooling", "mean") == "cls":  # ClsSelector (modeling_biencoder.py:44-49): the first token of every sequence
+            pooled = h.index_select(0, packed.cu[:-1].long()).float()
+        else:
+            pooled = ops.mean_pool_fwd(h, packed.cu)
         emb, head_save = ops.embed_head_fwd(pooled, head["hamming"], head["normalize"])
         ctx.head_state = (pooled, head_save)
         return emb
@@ -252,7 +255,11 @@ class _TrunkFn(torch.autograd.Function):
         if head is not None:
             pooled, head_save = ctx.head_state
             gp = ops.embed_head_bwd(pooled, g_out.contiguous().float(), head_save, head["hamming"], head["normalize"])
-            g_a = ops.mean_pool_bwd(gp, packed.cu, packed.total)
+            if head.get("pooling", "mean") == "cls":
+                g_a = torch.zeros(packed.total, gp.shape[1], device=gp.device, dtype=torch.bfloat16)
+                g_a.index_copy_(0, packed.cu[:-1].long(), gp.to(torch.bfloat16))
+            else:
+                g_a = ops.mean_pool_bwd(gp, packed.cu, packed.total)
         else:
             g_a = g_out.contiguous().to(torch.bfloat16)
         g_b = None
@@ -330,11 +337,12 @@ class BiEncoder(nn.Module):
     def __init__(self, config: BiEncoderConfig):
         super().__init__()
         self.config = config
-        if config.pooling != "mean":
-            raise NotImplementedError("this build implements pooling='mean' (the text towers of configs 1/2/4)")
-        if config.projection_dim:
-            raise NotImplementedError("projection_dim is None in the shipped contrastive configs")
+        if config.pooling not in ("mean", "cls"):
+            raise NotImplementedError("text tower: pooling='mean' (the shipped contrastive configs) or 'cls'; 'last' belongs to the "
+                                      "decoder towers and 'map' to the vision tower (VisionBiEncoder)")
         self.trunk = NomicBertModel(config.encoder or nomic_bert_base())
+        # proj (modeling_biencoder.py:270-273,312): after pooling / hamming / the cast to the trunk dtype, before normalize
+        self.proj = nn.Linear(self.trunk.config.n_embd, config.projection_dim) if config.projection_dim else None
         self.frozen_trunk = bool(config.freeze)
         if self.frozen_trunk:
             self.trunk.eval()
@@ -354,7 +362,8 @@ class BiEncoder(nn.Module):
     def forward(self, input_ids, attention_mask=None, is_padded_inputs=True, normalize=True, binarize=False, seq_lens=None,
                 **kwargs):
         packed = _pack(input_ids, attention_mask, seq_lens)
-        head = dict(hamming=bool(self.config.hamming), normalize=bool(normalize) and not binarize)
+        head = dict(hamming=bool(self.config.hamming), normalize=bool(normalize) and not binarize and self.proj is None,
+                    pooling=self.config.pooling)
         flat = self.trunk._flat
         if self.frozen_trunk:
             with torch.no_grad():
@@ -363,6 +372,11 @@ class BiEncoder(nn.Module):
             if not flat.requires_grad:
                 flat.requires_grad_(True)
             emb = _TrunkFn.apply(flat, self.trunk, packed, head)
+        if self.proj is not None:
+            from .poolers import linear
+            emb = linear(emb.to(torch.bfloat16), self.proj).float()  # the reference casts to the trunk dtype first (:309-310)
+            if normalize and not binarize:
+                emb = torch.nn.functional.normalize(emb, dim=-1)
         if binarize:
             emb = (emb > 0).float()
         return {"embedding": emb, "router_logits": None, "router_loss": None, "tokens_per_expert": None}

@@ -17,6 +17,7 @@ from .loss import clip_loss, gather_with_grad, grad_cache_loss, matryoshka_clip_
 import torch.distributed as dist
 
 from .parallel import GradientBucketReducer, allreduce_gradients, allreduce_scalar_grads
+from .poolers import head_parameters
 
 
 def _split_batch(batch, device):
@@ -92,8 +93,9 @@ class BatchPrefetcher:
 
 
 class _ScalarAdamW:
-    """AdamW (weight_decay 0: ``logit_scale`` is in the reference's no-decay group, optimizer.py:22-23) for the 0-dim
-    logit-scale parameter, as a handful of 1-element device ops: no host sync, no torch optimizer object (whose global
+    """AdamW for the few parameters kept outside the towers' flat buffers: the 0-dim logit scale (no decay: the reference's
+    no-decay group, optimizer.py:22-23) and pooler / projection weights (decay on >= 2-D, as configure_optimizer), as a handful of
+    small device ops: no host sync, no torch optimizer object (whose global
     post-step hook would force a re-cast of the towers' bf16 shadows)."""
 
     def __init__(self, param):
@@ -101,12 +103,14 @@ class _ScalarAdamW:
         self.m, self.v = torch.zeros_like(param), torch.zeros_like(param)
 
     @torch.no_grad()
-    def update(self, lr, betas=(0.9, 0.999), eps=1e-8):
+    def update(self, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         g = self.p.grad
         if g is None:
             return
         self.step += 1
         b1, b2 = betas
+        if weight_decay:
+            self.p.mul_(1.0 - lr * weight_decay)
         self.m.mul_(b1).add_(g, alpha=1 - b1)
         self.v.mul_(b2).addcmul_(g, g, value=1 - b2)
         denom = (self.v / (1 - b2 ** self.step)).sqrt_().add_(eps)
@@ -149,7 +153,22 @@ def training_step(model, batch, logit_scale, *, lr: float, chunk_size: Optional[
             reducer.arm()
         out["loss"].backward()
     grad_scale = reducer.wait() if reducer is not None else allreduce_gradients(model, average=False)
-    model.trunk.fused_adamw_step(lr, betas=betas, eps=eps, weight_decay=weight_decay, max_grad_norm=max_grad_norm,
-                                 grad_scale=grad_scale)
+    head = [p for p in head_parameters(model) if p.grad is not None]  # pooler / projection parameters outside the flat buffers
+    extra = None
+    if head:
+        for p in head:
+            if dist.is_initialized() and dist.get_world_size() > 1:
+                dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)
+                p.grad.mul_(1.0 / dist.get_world_size())
+        extra = torch.stack([p.grad.float().pow(2).sum() for p in head]).sum()
+    coef = model.trunk.fused_adamw_step(lr, betas=betas, eps=eps, weight_decay=weight_decay, max_grad_norm=max_grad_norm,
+                                        grad_scale=grad_scale, extra_sq_norm=extra)
+    if head:
+        opts = model.__dict__.setdefault("_cx_head_adamw", {})
+        with torch.no_grad():
+            for p in head:
+                if coef is not None:
+                    p.grad.mul_(coef.to(p.grad.dtype))
+                opts.setdefault(id(p), _ScalarAdamW(p)).update(lr, betas, eps, weight_decay if p.squeeze().ndim >= 2 else 0.0)
     _step_logit_scale(logit_scale, lr, betas, eps)
     return out["loss"].detach()

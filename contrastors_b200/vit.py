@@ -219,9 +219,16 @@ class VisionBiEncoder(nn.Module):
     def __init__(self, config: VisionBiEncoderConfig):
         super().__init__()
         self.config = config
-        if config.pooling != "cls" or config.projection_dim:
-            raise NotImplementedError("vision tower: pooling='cls', projection_dim=None (configs/train/nomic_embed_vision_v1.5.yaml)")
+        if config.pooling not in ("cls", "map"):
+            raise NotImplementedError("vision tower: pooling='cls' (CLIP) or 'map' (configs/train/nomic_embed_vision_v1.5.yaml:69)")
         self.trunk = ViTModel(config.encoder or vit_b16())
+        enc = self.trunk.config
+        if config.pooling == "map":
+            from .poolers import MultiHeadAttentionPooling
+            self.selector = MultiHeadAttentionPooling(enc.n_embd, enc.n_head, enc.n_inner, enc.activation_function, enc.layer_norm_epsilon)
+        else:
+            self.selector = None
+        self.proj = nn.Linear(enc.n_embd, config.projection_dim) if config.projection_dim else None
         self.frozen_trunk = bool(config.freeze)
         if self.frozen_trunk:
             self.trunk.eval()
@@ -234,15 +241,22 @@ class VisionBiEncoder(nn.Module):
 
     def forward(self, input_ids, attention_mask=None, is_padded_inputs=True, normalize=True, binarize=False, **kwargs):
         flat = self.trunk._flat
+        pooled_in_trunk = self.selector is None  # ClsSelector runs inside the trunk's node; MAP needs every token
         if self.frozen_trunk:
             with torch.no_grad():
-                emb = _ViTFn.apply(flat, self.trunk, input_ids, True)
+                emb = _ViTFn.apply(flat, self.trunk, input_ids, pooled_in_trunk)
         else:
             if not flat.requires_grad:
                 flat.requires_grad_(True)
-            emb = _ViTFn.apply(flat, self.trunk, input_ids, True)
-        # the reference casts the pooled vector back to the trunk dtype before normalising (modeling_biencoder.py:309-317)
+            emb = _ViTFn.apply(flat, self.trunk, input_ids, pooled_in_trunk)
+        if self.selector is not None:
+            B = input_ids.shape[0]
+            emb = self.selector(emb, B, self.trunk.config.num_patches + 1)
+        # the reference casts the pooled vector back to the trunk dtype before proj / normalize (modeling_biencoder.py:309-317)
         emb = emb + (emb.to(torch.bfloat16).float() - emb).detach()
+        if self.proj is not None:
+            from .poolers import linear
+            emb = linear(emb.to(torch.bfloat16), self.proj).float()
         if normalize and not binarize:
             emb = torch.nn.functional.normalize(emb, dim=-1)
         if binarize:
