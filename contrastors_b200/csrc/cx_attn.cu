@@ -17,6 +17,7 @@
 // The thread that ISSUES the MMAs must stay tight: the TMA / MMA warps run converged with elect.sync around the
 // asynchronous instructions only (under `if (lane == 0)` every UTCHMMA sits in an elect-and-branch loop, ~80 clk each).
 #include <math.h>
+#include <stdlib.h>
 
 #include "cx_host.h"
 #include "cx_ptx.cuh"
@@ -25,6 +26,7 @@ namespace cx {
 
 constexpr int kDh = 64;
 
+constexpr int kFwdPolyDefault = 0;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -45,10 +47,23 @@ extern "C" int cx_attn_fwd(const void* qkv, const int32_t* cu_seqlens, void* out
   int rc = make_tmap_2d(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, (uint64_t)3 * H * Dh, (uint64_t)total_tokens,
                         (uint64_t)3 * H * Dh * 2, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  CX_SET_SMEM_ONCE(attn_fwd4_kernel, Fwd4Smem::kTotal);
   dim3 grid((max_seqlen + 127) / 128, H, nseq);
-  attn_fwd4_kernel<<<grid, kFwd4Threads, Fwd4Smem::kTotal, stream>>>(tm, cu_seqlens, (__nv_bfloat16*)out, lse, total_tokens, H,
-                                                                    softmax_scale * kLog2e);
+  // share of the exponentials evaluated on the FMA pipe instead of the SFU (read once; A/B knob of the round-2 measurement)
+  static const int poly = [] {
+    const char* e = getenv("CX_ATTN_POLY");
+    const int v = (e && *e) ? atoi(e) : kFwdPolyDefault;
+    return (v == 0 || v == 4 || v == 8) ? v : kFwdPolyDefault;
+  }();
+#define CX_FWD4(P)                                                                                                      \
+  do {                                                                                                                  \
+    CX_SET_SMEM_ONCE(attn_fwd4_kernel<P>, Fwd4Smem::kTotal);                                                            \
+    attn_fwd4_kernel<P><<<grid, kFwd4Threads, Fwd4Smem::kTotal, stream>>>(tm, cu_seqlens, (__nv_bfloat16*)out, lse,     \
+                                                                         total_tokens, H, softmax_scale * kLog2e);    \
+  } while (0)
+  if (poly == 8) CX_FWD4(8);
+  else if (poly == 4) CX_FWD4(4);
+  else CX_FWD4(0);
+#undef CX_FWD4
   CX_LAUNCH_CHECK();
   return 0;
 }

@@ -23,6 +23,10 @@ struct Fwd4Smem {
   static constexpr int kTotal = kBars + 256;       // 83,200 B: two CTAs per SM
 };
 
+// kPoly: how many of the 8 column quads of each 32-column batch take the second pair of their exponentials from the FMA-pipe
+// polynomial (exp2_poly2) instead of MUFU.EX2: 0 = none, 4 = every other quad (25 % of the exponentials), 8 = all (50 %).  The
+// forward is bound by the SFU (16 exponentials / clk / SM = 1024 clk per 128 x 128 tile against 512 clk of tensor time).
+template <int kPoly>
 __global__ void __launch_bounds__(kFwd4Threads, 2)
 attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __restrict__ cu_seqlens,
                  __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int T, int H, float scale2) {
@@ -211,7 +215,8 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const int* __restric
           float2 x0 = ffma2(make_float2(__uint_as_float(v0[0]), __uint_as_float(v0[1])), sc2, nm2);
           float2 x1 = ffma2(make_float2(__uint_as_float(v0[2]), __uint_as_float(v0[3])), sc2, nm2);
           x0 = make_float2(fast_exp2(x0.x), fast_exp2(x0.y));
-          x1 = make_float2(fast_exp2(x1.x), fast_exp2(x1.y));
+          if (kPoly == 8 || (kPoly == 4 && ((t >> 1) & 1))) x1 = exp2_poly2(x1);
+          else x1 = make_float2(fast_exp2(x1.x), fast_exp2(x1.y));
           rs0 = fadd2(rs0, x0);
           rs1 = fadd2(rs1, x1);
           pp[t] = pack_bf16x2(x0.x, x0.y);

@@ -305,6 +305,132 @@ add_layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat1
   }
 }
 
+
+// LayerNorm backward, narrow form (the non-embedding case, 48 launches per GradCache chunk): a thread owns 8 columns of a row and
+// a row spans WPR warps, so a thread holds 16 column-sum accumulators instead of 16 * d / 256 and four 16-byte loads instead of
+// 4 * d / 256: ~70 registers against 219 for the warp-per-row form above at d = 768, i.e. three times the resident warps to
+// cover the HBM latency (round 1: 65 us = 3.9 TB/s = 0.59 of the measured copy peak with one 256-thread block per SM).
+// Block = RPB row slots x WPR warps (384 threads); the WPR warps of a slot combine their two row sums through shared memory and a
+// named barrier of their own, so slots never wait for each other.
+template <int WPR>
+__global__ void __launch_bounds__(384, 2)
+add_layernorm_bwd_narrow_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
+                                const float* __restrict__ gamma, const float* __restrict__ stats, __nv_bfloat16* __restrict__ dz,
+                                float* __restrict__ partials, int rows, int d, const __nv_bfloat16* __restrict__ gres, DropParams dp,
+                                __nv_bfloat16* __restrict__ da_out) {
+  constexpr int RPB = 12 / WPR;
+  extern __shared__ float sh[];  // [RPB][2][d] at the end; the first RPB * WPR * 2 floats double as the row-sum exchange
+  __shared__ float xch[2][12][2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slot = warp / WPR, wr = warp % WPR;
+  const int col = (wr * 32 + lane) * 8;
+  const bool col_ok = col < d;
+  float gm[8], dg[8], db[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    gm[i] = 1.f;
+    dg[i] = db[i] = 0.f;
+  }
+  if (col_ok && gamma != nullptr) load8f(gamma + col, gm);
+  const float inv_d = 1.f / (float)d;
+  int it = 0;
+  for (int row = blockIdx.x * RPB + slot; row < rows; row += gridDim.x * RPB, ++it) {
+    const float mean = stats[2 * (size_t)row], rstd = stats[2 * (size_t)row + 1];
+    float x[8], w[8];
+    float s1 = 0.f, s2 = 0.f;
+    if (col_ok) {
+      BF8 ra, rb, r1, r2;
+      const size_t off = (size_t)row * d + col;
+      ra.raw = *reinterpret_cast<const uint4*>(a + off);
+      if (b != nullptr) rb.raw = *reinterpret_cast<const uint4*>(b + off);
+      r1.raw = *reinterpret_cast<const uint4*>(g1 + off);
+      if (g2 != nullptr) r2.raw = *reinterpret_cast<const uint4*>(g2 + off);
+      float z[8], t[8], g[8];
+      ra.unpack(z);
+      if (dp.p > 0.f) apply_dropout8(z, dp, row, col, d);  // re-create z = dropout(a) + b
+      if (b != nullptr) {
+        rb.unpack(t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z[i] += t[i];
+      }
+      r1.unpack(g);
+      if (g2 != nullptr) {
+        r2.unpack(t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] += t[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        x[i] = (z[i] - mean) * rstd;
+        w[i] = g[i] * gm[i];
+        s1 += w[i];
+        s2 = fmaf(w[i], x[i], s2);
+        dg[i] = fmaf(g[i], x[i], dg[i]);
+        db[i] += g[i];
+      }
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (WPR > 1) {  // combine the row's WPR warps: double-buffered exchange + a named barrier private to the slot
+      float* xc = &xch[it & 1][0][0];
+      if (lane == 0) {
+        xc[(slot * WPR + wr) * 2] = s1;
+        xc[(slot * WPR + wr) * 2 + 1] = s2;
+      }
+      named_bar_sync(1 + slot, WPR * 32);
+      s1 = 0.f;
+      s2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < WPR; ++k) {
+        s1 += xc[(slot * WPR + k) * 2];
+        s2 += xc[(slot * WPR + k) * 2 + 1];
+      }
+    }
+    s1 *= inv_d;
+    s2 *= inv_d;
+    if (col_ok) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = (w[i] - s1 - x[i] * s2) * rstd;
+      const size_t off = (size_t)row * d + col;
+      if (gres != nullptr) {  // pre-norm: z also feeds the residual stream, whose gradient adds here
+        BF8 vr;
+        float t[8];
+        vr.raw = *reinterpret_cast<const uint4*>(gres + off);
+        vr.unpack(t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += t[i];
+      }
+      BF8 vo;
+      vo.pack(o);
+      *reinterpret_cast<uint4*>(dz + off) = vo.raw;
+      if (da_out != nullptr) {  // gradient of the dropped branch a: dz * keep / (1 - p)
+        if (dp.p > 0.f) apply_dropout8(o, dp, row, col, d);
+        vo.pack(o);
+        *reinterpret_cast<uint4*>(da_out + off) = vo.raw;
+      }
+    }
+  }
+  if (partials == nullptr) return;
+  // CTA reduction of the column-sum partials over the row slots (fixed order => deterministic)
+  if (col_ok) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sh[(slot * 2 + 0) * d + col + i] = dg[i];
+      sh[(slot * 2 + 1) * d + col + i] = db[i];
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < 2 * d; j += blockDim.x) {
+    const int which = j / d, c = j % d;
+    float acc = 0.f;
+#pragma unroll
+    for (int r = 0; r < RPB; ++r) acc += sh[(r * 2 + which) * d + c];
+    partials[(size_t)blockIdx.x * 2 * d + j] = acc;
+  }
+}
+
 // out_k[j] += sum over blocks of partials[b][k][j], k < np (dgamma, dbeta, and optionally the type-0 embedding row).
 // 8 threads per column split the blocks (fixed assignment + fixed shuffle tree => deterministic).
 __global__ void ln_param_grad_reduce_kernel(const float* __restrict__ partials, int nblocks, int d, int np, float* __restrict__ o0,
@@ -1010,14 +1136,26 @@ extern "C" int cx_add_layernorm_bwd(const void* a, const void* b, const void* g1
   CX_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "cx_add_layernorm_bwd: dgamma/dbeta go together");
   CX_REQUIRE(dgamma == nullptr || workspace != nullptr, "cx_add_layernorm_bwd: workspace required for parameter grads");
   if (rows <= 0) return 0;
-  const int grid = ln_bwd_grid(rows);
-  const size_t smem = (size_t)8 * 2 * d * sizeof(float);
-  int rc = ln_bwd_dispatch<false>(d, grid, smem, STREAM, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (const int64_t*)nullptr,
-                                  (const int64_t*)nullptr, (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)g1,
-                                  (const __nv_bfloat16*)g2, gamma, stats, (__nv_bfloat16*)dz, (float*)nullptr, (float*)nullptr,
-                                  dgamma ? (float*)workspace : (float*)nullptr, rows, d, (int64_t)-1, (const __nv_bfloat16*)gres, dp,
-                                  (__nv_bfloat16*)da_out);
-  if (rc) return rc;
+  // narrow form: 384-thread blocks of 12 / WPR row slots, two blocks per SM (the workspace holds one partial per block and is
+  // sized for 4 * SMs blocks)
+  const int wpr = (d + 255) / 256;  // 1..4; 3 at d = 768
+  const int rpb = 12 / wpr;
+  int grid = (rows + rpb - 1) / rpb;
+  if (grid > 2 * sm_count()) grid = 2 * sm_count();
+  const size_t smem = (size_t)rpb * 2 * d * sizeof(float);
+  float* part = dgamma ? (float*)workspace : (float*)nullptr;
+#define CX_LN_NARROW(W)                                                                                                          \
+  add_layernorm_bwd_narrow_kernel<W><<<grid, 384, smem, STREAM>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b,               \
+      (const __nv_bfloat16*)g1, (const __nv_bfloat16*)g2, gamma, stats, (__nv_bfloat16*)dz, part, rows, d,                          \
+      (const __nv_bfloat16*)gres, dp, (__nv_bfloat16*)da_out)
+  switch (wpr) {
+    case 1: CX_LN_NARROW(1); break;
+    case 2: CX_LN_NARROW(2); break;
+    case 3: CX_LN_NARROW(3); break;
+    default: CX_LN_NARROW(4); break;
+  }
+#undef CX_LN_NARROW
+  CX_LAUNCH_CHECK();
   if (dgamma) {
     ln_param_grad_reduce_kernel<<<(2 * d * 8 + 255) / 256, 256, 0, STREAM>>>((const float*)workspace, grid, d, 2, dgamma, dbeta, nullptr);
     CX_LAUNCH_CHECK();
