@@ -474,17 +474,87 @@ def run_ours(args):
     print(json.dumps(out))
 
 
+# ------------------------------------------------------------------------------------------------- image-text arm (configs[2] / [4])
+def run_image_text(args):
+    """BASELINE configs[2]: ViT-B/16 + nomic-bert-base, 224^2 images, text seq 77, global batch 32768, GradCache chunk 64, both towers
+    trainable, trainable logit scale 1 / 0.07; with --config lit it is configs[4]: a FROZEN ViT-L/14 + the trainable text tower at
+    global batch 65536.  Informational line for profiles/ (the driver's metric is the text-text line)."""
+    import torch
+    import torch.distributed as dist
+    import contrastors_b200 as cb
+    from contrastors_b200 import _lib
+    from contrastors_b200.parallel import broadcast_parameters
+    from contrastors_b200.trainer import dual_training_step
+    rank, world, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29500")
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    lit = args.config == "lit"
+    global_batch = args.global_batch or (65536 if lit else 32768)
+    n_local, seq = global_batch // world, 77
+    torch.manual_seed(0)
+    vision = cb.VisionBiEncoder(cb.VisionBiEncoderConfig(encoder=cb.vit_l14() if lit else cb.vit_b16(), freeze=lit)).to(dev)
+    text = cb.BiEncoder(cb.BiEncoderConfig(encoder=cb.nomic_bert_base())).to(dev)
+    vision.trunk.reset_parameters(seed=1)
+    text.trunk.reset_parameters(seed=0)
+    broadcast_parameters(vision, text)
+    ls = cb.LogitScale(logit_scale=1.0 / 0.07, trainable_logit_scale=True).to(dev)
+    g = torch.Generator().manual_seed(42 + rank)
+    px = torch.randn(n_local, 3, 224, 224, generator=g, dtype=torch.bfloat16).to(dev)
+    ids = torch.randint(0, 30000, (n_local, seq), generator=g).to(dev)
+    ones = torch.ones(n_local, seq, dtype=torch.int64, device=dev)
+    lens = torch.full((n_local,), seq, dtype=torch.int64)
+
+    def step():
+        return dual_training_step(vision, text, {"input_ids": px}, {"input_ids": ids, "attention_mask": ones, "seq_lens": lens}, ls,
+                                  lr=LR, chunk_size=CHUNK, weight_decay=WD, max_grad_norm=CLIP)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    n0 = _lib.launch_count()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(args.steps):
+        loss = step()
+    e.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([s.elapsed_time(e)], device=dev, dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        flops_pair = (4 if not lit else 1) * (161.7e9 if lit else 34.9e9) + 4 * 245.4e6 * seq  # GradCache: 4 forward-equivalents per trainable tower
+        v = global_batch * args.steps / (ms.item() * 1e-3)
+        print(json.dumps({"metric": f"pairs/sec at global_bs={global_batch} ({'frozen ViT-L/14 (LiT)' if lit else 'ViT-B/16'} + nomic-bert-base image-text, bf16, 224^2, text seq 77, GradCache)",
+                          "value": v, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": ms.item() / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                          "dtype": "bf16", "data": "synthetic",
+                          "config": {"workload": f"configs[{4 if lit else 2}]", "global_batch": global_batch, "per_gpu_batch": n_local,
+                                     "image": 224, "seq_len": seq, "chunk": CHUNK, "parallelism": f"dp{world}",
+                                     "loss": "clip_loss bidirectional (symmetric) at world size 1, image->text otherwise"},
+                          "gpu_launches": int(_lib.launch_count() - n0), "model_tflops_per_s": v * flops_pair / 1e12,
+                          "loss": float(loss)}))
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="text", choices=["text", "image_text", "lit"],
+                    help="text = BASELINE configs[1] (the driver's metric); image_text / lit = configs[2] / configs[4], informational")
+    ap.add_argument("--global-batch", type=int, default=0, help="override the global batch of the image-text configs")
     ap.add_argument("--no-selfcheck", action="store_true", help="skip the step-0 loss check against the CPU oracle")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference-on-the-same-GPU leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.config != "text":
+        run_image_text(args)
     else:
         run_ours(args)
 

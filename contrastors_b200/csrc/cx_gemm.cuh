@@ -440,23 +440,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tma_store_2d(&tmC, buf_y, col0, m0);
             tma_store_2d(&tmC, buf_g, N + col0, m0);
             tma_store_commit();
+            if (tile + tile_step < num_tiles) {
+              // rolling prefetch: as soon as this slot's stores have been read (a few hundred ns), request the NEXT work item's
+              // tiles of the same step into it -- they then have a whole step of this group's arithmetic to arrive
+              const int mn2 = (tile + tile_step) / splits;
+              const int m2 = (mn2 / n_tiles) * TILE_M + pair_m + (int)cta_rank * kBlockM, n2 = (mn2 % n_tiles) * BLOCK_N + hf * HALF_N + pr * 64;
+              tma_store_wait_read<0>();
+              mbar_arrive_expect_tx(bars + 16 + 2 * hf + pr, 2 * kStageCBytes);
+              tma_load_2d(buf_y, &tmD, bars + 16 + 2 * hf + pr, n2, m2);
+              tma_load_2d(buf_g, &tmD, bars + 16 + 2 * hf + pr, N + n2, m2);
+            }
           }
         }
         ld_phase ^= 1u;
-        if (etid == 0 && tile + tile_step < num_tiles) {
-          // rolling prefetch of the next work item's tiles: slot 0 is free once its stores (the older bulk group) have been
-          // read, slot 1 once the group just committed has
-          const int mn2 = (tile + tile_step) / splits;
-          const int m2 = (mn2 / n_tiles) * TILE_M + pair_m + (int)cta_rank * kBlockM, n2 = (mn2 % n_tiles) * BLOCK_N + hf * HALF_N;
-          tma_store_wait_read<1>();
-          mbar_arrive_expect_tx(bars + 16 + 2 * hf, 2 * kStageCBytes);
-          tma_load_2d(stage_base, &tmD, bars + 16 + 2 * hf, n2, m2);
-          tma_load_2d(stage_base + kStageCBytes, &tmD, bars + 16 + 2 * hf, N + n2, m2);
-          tma_store_wait_read<0>();
-          mbar_arrive_expect_tx(bars + 17 + 2 * hf, 2 * kStageCBytes);
-          tma_load_2d(stage_base + 2 * kStageCBytes, &tmD, bars + 17 + 2 * hf, n2 + 64, m2);
-          tma_load_2d(stage_base + 3 * kStageCBytes, &tmD, bars + 17 + 2 * hf, N + n2 + 64, m2);
-        }
       } else if (MODE == EPI_STORE && !OUT_F32) {
         // bf16 store path: one staging row (128 B) = 64 columns = two TMEM chunks = one attention head when RoPE is on
         float rpos = 0.f;

@@ -172,3 +172,26 @@ def training_step(model, batch, logit_scale, *, lr: float, chunk_size: Optional[
                 opts.setdefault(id(p), _ScalarAdamW(p)).update(lr, betas, eps, weight_decay if p.squeeze().ndim >= 2 else 0.0)
     _step_logit_scale(logit_scale, lr, betas, eps)
     return out["loss"].detach()
+
+
+def dual_training_step(vision, text, vision_inputs, text_inputs, logit_scale, *, lr: float, chunk_size: int = 64, betas=(0.9, 0.999),
+                       eps=1e-8, weight_decay=0.01, max_grad_norm: Optional[float] = 1.0, bidirectional: Optional[bool] = None):
+    """Image-text GradCache step (BASELINE configs[2] / [4]): ``grad_cache_loss(tower1 = vision, tower2 = text)`` as SURVEY section 8d
+    sets it up (pixels travel under the key ``input_ids``, image_text_loader.py:339), each trainable tower's flat gradient
+    all-reduced and stepped with its own fused clip + AdamW, the (trainable) logit scale stepped as in ``training_step``.  A frozen
+    tower (LiT) is skipped by both the gradient pass and the optimizer.  ``bidirectional`` defaults to the reference's validity
+    rule for ``clip_loss(bidirectional=True)``: only at world size 1 (loss.py:119-123 needs M == N)."""
+    vision.train()
+    text.train()
+    ws = dist.get_world_size() if dist.is_initialized() else 1
+    if bidirectional is None:
+        bidirectional = ws == 1
+    loss = grad_cache_loss(tower1=vision, t1_inputs=vision_inputs, tower2=text, t2_inputs=text_inputs, chunk_size=chunk_size,
+                           logit_scale=logit_scale, bidirectional=bidirectional)
+    for tower in (vision, text):
+        if not any(p.requires_grad for p in tower.trunk.parameters()):
+            continue
+        scale = allreduce_gradients(tower, average=False)
+        tower.trunk.fused_adamw_step(lr, betas=betas, eps=eps, weight_decay=weight_decay, max_grad_norm=max_grad_norm, grad_scale=scale)
+    _step_logit_scale(logit_scale, lr, betas, eps)
+    return loss.detach()
