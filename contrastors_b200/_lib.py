@@ -29,6 +29,11 @@ SIGNATURES = {
     "cx_gemm_swiglu": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _vp]),
     "cx_infonce_workspace_bytes": (_sz, [_i, _i, _i]),
     "cx_infonce_fwd": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cx_infonce_mat_workspace_bytes": (_sz, [_i, _i, _i]),
+    "cx_infonce_mat_fwd": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _vp, _f, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cx_infonce_mat_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "cx_infonce_mat_bwd": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _vp, _f, _vp, _vp, _vp, _i64, _vp,
+                                _i64, _vp, _vp, _vp, _vp]),
     "cx_infonce_bwd": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp, _f, _vp, _vp, _i64, _vp,
                             _i64, _i, _vp, _vp, _vp]),
     "cx_rows_to_bf16": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _i, _i, _vp]),

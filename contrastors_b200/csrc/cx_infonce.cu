@@ -219,6 +219,17 @@ __global__ void l2norm_bwd_kernel(const float* __restrict__ x, int64_t ldx, cons
   }
 }
 
+// host helper shared with cx_infonce_mat.cu: y (fp16) = sat(x (bf16) * inv_norm[row]) (inv_norm may be null)
+int nce_rows_to_f16(const void* x, int64_t ldx, void* y, int64_t ldy, const float* inv_norm, int rows, int k, cudaStream_t stream) {
+  const int threads = 256;
+  const int64_t per_row = (k + 7) / 8;
+  const int vec = (ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) ? 1 : 0;
+  bf16_to_f16_rows_kernel<<<(unsigned)(((int64_t)rows * per_row + threads - 1) / threads), threads, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__half*>(y), ldy, inv_norm, rows, k, vec);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace cx
 
 using namespace cx;

@@ -83,7 +83,27 @@ class _FusedInfoNCE(torch.autograd.Function):
         if spec.normalize:
             # prefix norms from the same bf16-rounded rows the MMA consumes
             q32, d32 = q_bf.float(), d_bf.float()
-        for w, k in zip(weights, dims):
+        single_pass = (spec.normalize and len(dims) > 1 and len(dims) <= 8 and len(set(dims)) == len(dims)
+                       and all(k % 64 == 0 for k in dims) and max(dims) <= width)
+        if single_pass:
+            # Matryoshka: ONE accumulation over K = max(dims); every prefix's statistics come from the running sum of segment
+            # products held in tensor memory (cx_infonce_mat_fwd): 2 N M K FLOPs instead of 2 N M sum(dims)
+            order = sorted(range(len(dims)), key=lambda i: dims[i])
+            asc = [dims[i] for i in order]
+            rq_all = torch.stack([ops.row_inv_norms(q32, k) for k in asc])
+            rd_all = torch.stack([ops.row_inv_norms(d32, k) for k in asc])
+            lse_all, arg_all, _, st_all = ops.infonce_mat_fwd(q_bf, d_bf, asc, 1.0, scale_dev, rq_all, rd_all, spec.label_offset,
+                                                              spec.label_stride)
+            ctx.mat = dict(asc=asc, order=order, rq=rq_all, rd=rd_all, lse=lse_all.contiguous())
+            pos = {i: j for j, i in enumerate(order)}
+            for i, (w, k) in enumerate(zip(weights, dims)):
+                j = pos[i]
+                loss = loss + st_all[j, 0] * (w * spec.mult / n)
+                spec.out[k] = dict(stats=st_all[j], argmax=arg_all[j], lse=lse_all[j])
+                saved_lse.append(lse_all[j])
+                saved_rq.append(rq_all[j])
+                saved_rd.append(rd_all[j])
+        for w, k in (() if single_pass else zip(weights, dims)):
             rq = rd = None
             if spec.normalize:
                 rq, rd = ops.row_inv_norms(q32, k), ops.row_inv_norms(d32, k)
@@ -94,6 +114,8 @@ class _FusedInfoNCE(torch.autograd.Function):
             saved_lse.append(lse)
             saved_rq.append(rq)
             saved_rd.append(rd)
+        if not single_pass:
+            ctx.mat = None
         ctx.spec, ctx.dims, ctx.weights = spec, dims, weights
         ctx.n, ctx.m, ctx.width = n, m, width
         ctx.local_rows = document.shape[0]
@@ -118,7 +140,31 @@ class _FusedInfoNCE(torch.autograd.Function):
             dq.zero_()
             dd.zero_()
         dlogit = torch.zeros((), device=dev, dtype=torch.float32)
-        for i, (w, k) in enumerate(zip(ctx.weights, ctx.dims)):
+        mat = ctx.mat
+        if mat is not None and 2 <= len(mat["asc"]) <= 4 and all(w_ != 0 for w_ in ctx.weights):
+            # single-accumulation Matryoshka backward (cx_infonce_mat.cu): one dS-like matrix per SEGMENT of the columns, the
+            # chain through F.normalize folded into one row / column scalar per prefix
+            asc, order = mat["asc"], mat["order"]
+            w_asc = [float(ctx.weights[i]) for i in order]
+            w_max = max(abs(w_) for w_ in w_asc)
+            coef = w_max * spec.mult / n
+            gamma = (mat["rq"][-1].mean() * mat["rd"][-1].mean()).reshape(1)          # typical rq * rd: keeps T in fp16's range
+            coef_gamma, inv_gamma = (coef_dev.reshape(1) * gamma).contiguous(), (1.0 / gamma).contiguous()
+            dq_raw, dd_raw, alpha, beta = ops.infonce_mat_bwd(q_bf, d_bf, asc, [w_ / w_max for w_ in w_asc], 1.0, scale_dev, mat["rq"],
+                                                              mat["rd"], spec.label_offset, spec.label_stride, mat["lse"], coef,
+                                                              coef_gamma, inv_gamma, width)
+            cg = coef * coef_dev
+            K = asc[-1]
+            seg = torch.bucketize(torch.arange(K, device=dev), torch.tensor(asc, device=dev), right=True)   # column -> segment
+            A = ((mat["rq"] ** 2) * alpha).flip(0).cumsum(0).flip(0) * cg      # [P, n]: sum over the prefixes that contain the segment
+            B = ((mat["rd"] ** 2) * beta).flip(0).cumsum(0).flip(0) * cg
+            dq = dq_raw
+            dd = dd_raw
+            dq[:, :K] -= q32[:, :K] * A.t()[:, seg]
+            dd[:, :K] -= d32[:, :K] * B.t()[:, seg]
+            dlogit = cg * alpha.sum()
+        for i, (w, k) in (() if (mat is not None and 2 <= len(mat["asc"]) <= 4 and all(w_ != 0 for w_ in ctx.weights))
+                          else enumerate(zip(ctx.weights, ctx.dims))):
             stats = torch.zeros(4, device=dev, dtype=torch.float32)
             coef = w * spec.mult / n
             if not spec.normalize and k == width and len(ctx.dims) == 1:
@@ -249,23 +295,50 @@ def _chunk_streams(model, chunks):
     return _CHUNK_STREAMS[key]
 
 
-def get_chunked_embeddings(model, chunks):
-    """Pass 1 of GradCache (reference loss.py:135-146): no-grad bf16 forwards, one RNG snapshot per chunk."""
+def _retain_budget(model, chunks) -> int:
+    """How many of a tower's pass-1 chunks can keep their activations for pass 2 (memory laid out for 180 GB of HBM per GPU):
+    a retained chunk runs its pass-1 forward in grad mode and pass 2 back-propagates through THAT graph instead of re-running the
+    forward -- same weights, same dropout masks, identical gradients, one forward less.  A nomic-bert-base chunk of 64 x 512 tokens
+    holds ~12 GB, so a B200 keeps ~12 of them: 0.6 % of the step at 256 chunks per tower (N = 1), 4.7 % at 32 (N = 8).
+    Towers opt in through ``saved_bytes_per_token``; CX_RETAIN_ACTIVATIONS=0 turns it off."""
+    import os
+    per_token = getattr(model, "saved_bytes_per_token", None)
+    if per_token is None or os.environ.get("CX_RETAIN_ACTIVATIONS", "1") == "0" or not chunks:
+        return 0
+    if not getattr(model, "training", False) or not any(p.requires_grad for p in model.parameters()):
+        return 0
+    t = chunks[0].get("input_ids")
+    if t is None or not t.is_cuda or t.dim() != 2:
+        return 0
+    per_chunk = int(per_token() * t.shape[0] * t.shape[1] * 1.15)
+    free, _ = torch.cuda.mem_get_info(t.device)
+    free += torch.cuda.memory_reserved(t.device) - torch.cuda.memory_allocated(t.device)
+    reserve = 3 * per_chunk + (16 << 30)  # the working chunk of pass 2, allocator slack, InfoNCE workspace, NCCL buffers
+    return max(0, min(len(chunks), int((free - reserve) // max(per_chunk, 1))))
+
+
+def get_chunked_embeddings(model, chunks, _retain: int = 0, _retained=None):
+    """Pass 1 of GradCache (reference loss.py:135-146): no-grad bf16 forwards, one RNG snapshot per chunk.  The last ``_retain``
+    chunks run in grad mode and leave their graph in ``_retained[i]`` (see ``_retain_budget``)."""
     embeddings, rand_states = [], []
     streams = _chunk_streams(model, chunks)
     main = torch.cuda.current_stream() if streams else None
     if streams:
         for s in streams:
             s.wait_stream(main)
-    with torch.no_grad():
-        for i, chunk in enumerate(chunks):
+    first_kept = len(chunks) - (_retain if _retained is not None else 0)
+    for i, chunk in enumerate(chunks):
+        keep = i >= first_kept
+        with (torch.enable_grad() if keep else torch.no_grad()):
             rand_states.append(RandContext(chunk))
             with (torch.cuda.stream(streams[i & 1]) if streams else nullcontext()):
                 with _autocast_for(chunk):
                     emb = model(**chunk)
                 if streams:
                     emb["embedding"].record_stream(main)
-            embeddings.append(emb["embedding"])
+            if keep and emb["embedding"].requires_grad:
+                _retained[i] = emb["embedding"]
+            embeddings.append(emb["embedding"].detach())
     if streams:
         for s in streams:
             main.wait_stream(s)
@@ -282,7 +355,7 @@ def _comm_stream(device):
     return _COMM_STREAMS[key]
 
 
-def _chunked_embeddings_with_gather(model, chunks, n_local):
+def _chunked_embeddings_with_gather(model, chunks, n_local, _retain: int = 0, _retained=None):
     """Pass 1 for the document tower with the cross-rank gather overlapped (north_star: "GradCache loop driven from CUDA
     streams so encoder compute overlaps the gather"): as each chunk's embeddings land they are cast to bf16 into this
     rank's slice and all-gathered on a side stream straight into their final rows of the InfoNCE K operand, while the
@@ -297,8 +370,10 @@ def _chunked_embeddings_with_gather(model, chunks, n_local):
     if streams:
         for s in streams:
             s.wait_stream(main)
-    with torch.no_grad():
-        for i, chunk in enumerate(chunks):
+    first_kept = len(chunks) - (_retain if _retained is not None else 0)
+    for i, chunk in enumerate(chunks):
+        keep = i >= first_kept
+        with (torch.enable_grad() if keep else torch.no_grad()):
             rand_states.append(RandContext(chunk))
             if gathered is None:  # allocated on the main stream before any side-stream use
                 dev = chunk["input_ids"].device
@@ -306,6 +381,9 @@ def _chunked_embeddings_with_gather(model, chunks, n_local):
             with (torch.cuda.stream(streams[i & 1]) if streams else nullcontext()):
                 with _autocast_for(chunk):
                     emb = model(**chunk)["embedding"]
+                if keep and emb.requires_grad:
+                    _retained[i] = emb
+                emb = emb.detach()
                 e32 = emb.float().contiguous()
                 b, width = e32.shape
                 if gathered is None:
@@ -332,7 +410,7 @@ def _chunked_embeddings_with_gather(model, chunks, n_local):
     return torch.concat(embeddings, dim=0), rand_states, gathered
 
 
-def accumulate_gradients(model, inputs, cache, rand_states, router_aux_coeff, _grad_reducer=None):
+def accumulate_gradients(model, inputs, cache, rand_states, router_aux_coeff, _grad_reducer=None, _retained=None):
     """Pass 2 of GradCache (reference loss.py:149-161): re-forward each chunk with its RNG replayed and back-propagate
     <embedding, cached gradient>; DDP gradient sync only on the last chunk (``_grad_reducer``: our explicit equivalent, armed
     right before the last chunk's backward so the bucketed all-reduce runs under it)."""
@@ -345,6 +423,12 @@ def accumulate_gradients(model, inputs, cache, rand_states, router_aux_coeff, _g
         for s in streams:
             s.wait_stream(main)
     for i, (inp, grad, state, sync_context) in enumerate(zip(inputs, cache, rand_states, sync_contexts)):
+        kept = _retained.pop(i, None) if _retained else None
+        if kept is not None:  # pass 1 kept this chunk's graph: back-propagate <embedding, cached gradient> through it directly
+            if _grad_reducer is not None and i == length - 1:
+                _grad_reducer.arm()
+            torch.autograd.backward(kept, grad.to(kept.dtype))
+            continue
         with (torch.cuda.stream(streams[i & 1]) if streams else nullcontext()):
             with sync_context():
                 with state:
@@ -384,13 +468,18 @@ def grad_cache_loss(tower1, t1_inputs, tower2, t2_inputs, chunk_size, logit_scal
         chunked_documents.append({k: v[start:start + chunk_size] for k, v in t2_inputs.items()})
 
     query_embs, query_rand_states = get_chunked_embeddings(tower1, chunked_queries)
+    # tower 2's pass 1 comes last: as many of ITS final chunks as HBM holds keep their activations for pass 2 (none when tower 2
+    # will not be back-propagated)
+    retained = {}
+    n_retain = _retain_budget(tower2, chunked_documents) if getattr(tower2, "training", False) else 0
     pregathered = None
     if (dist.is_initialized() and dist.get_world_size() > 1 and dist.get_backend() == "nccl"
             and t2_inputs["input_ids"].is_cuda and total_bs % chunk_size == 0):
         # the document gather runs chunk by chunk on a side stream while the next chunk's encoder forward computes
-        document_embs, doc_rand_states, pregathered = _chunked_embeddings_with_gather(tower2, chunked_documents, total_bs)
+        document_embs, doc_rand_states, pregathered = _chunked_embeddings_with_gather(tower2, chunked_documents, total_bs,
+                                                                                      _retain=n_retain, _retained=retained)
     else:
-        document_embs, doc_rand_states = get_chunked_embeddings(tower2, chunked_documents)
+        document_embs, doc_rand_states = get_chunked_embeddings(tower2, chunked_documents, _retain=n_retain, _retained=retained)
 
     query_cache, document_cache, loss = cache_loss(tower1, tower2, query_embs, document_embs, logit_scale,
                                                    bidirectional=bidirectional, _pregathered=pregathered)
@@ -416,5 +505,6 @@ def grad_cache_loss(tower1, t1_inputs, tower2, t2_inputs, chunk_size, logit_scal
                              router_aux_coeff=router_aux_coeff, _grad_reducer=r1)
     if second_pass:
         accumulate_gradients(tower2, chunked_documents, document_cache.split(chunk_size), doc_rand_states,
-                             router_aux_coeff=router_aux_coeff, _grad_reducer=r2)
+                             router_aux_coeff=router_aux_coeff, _grad_reducer=r2, _retained=retained)
+    retained.clear()
     return loss

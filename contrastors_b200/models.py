@@ -353,6 +353,13 @@ class BiEncoder(nn.Module):
     def device(self):
         return self.trunk._flat.device
 
+    def saved_bytes_per_token(self) -> int:
+        """Activations one token leaves behind for the backward (bf16 h, qkv, attn, o, h1, [y|g], a, m per layer + fp32 statistics):
+        GradCache keeps whole chunks of them across its two passes when HBM allows (``loss._retain_budget``)."""
+        c = self.trunk.config
+        per_layer = 2 * (c.n_embd * 8 + 3 * c.n_inner) + 4 * (4 + c.n_head)  # 768*8 + 3*3072 = 15360 bf16 values at nomic-bert-base
+        return c.n_layer * per_layer + 4 * c.n_embd
+
     def no_sync(self):
         """DDP-style context for GradCache (loss.py:151-154): gradient reduction is explicit here
         (``contrastors_b200.parallel.allreduce_gradients``), so this is a no-op context."""

@@ -218,6 +218,58 @@ def infonce_fwd(q, d, k_dim, scale, scale_dev, rq, rd, label_offset, label_strid
     return lse, argmax, label_logit, stats
 
 
+def infonce_mat_fwd(q, d, dims, scale, scale_dev, rq, rd, label_offset, label_stride):
+    """Matryoshka statistics for every prefix in ``dims`` (ascending multiples of 64) from ONE accumulation over K.
+    rq [P, n], rd [P, m] fp32.  Returns (lse [P, n], argmax [P, n] i32, label_logit [P, n], stats [P, 4])."""
+    import ctypes
+    _require_cuda(q, d, rq, rd)
+    n, m, P = q.shape[0], d.shape[0], len(dims)
+    dev = q.device
+    lse = torch.empty(P, n, device=dev, dtype=torch.float32)
+    argmax = torch.empty(P, n, device=dev, dtype=torch.int32)
+    label_logit = torch.empty(P, n, device=dev, dtype=torch.float32)
+    stats = torch.empty(P, 4, device=dev, dtype=torch.float32)
+    lib = _lib.load()
+    ws = torch.empty(lib.cx_infonce_mat_workspace_bytes(n, m, P), device=dev, dtype=torch.uint8)
+    dims_c = (ctypes.c_int32 * P)(*[int(k) for k in dims])
+    ev = TIMER.begin("infonce_fwd") if TIMER is not None else None
+    _lib.check(lib.cx_infonce_mat_fwd(q.data_ptr(), q.stride(0), d.data_ptr(), d.stride(0), n, m, P, ctypes.addressof(dims_c), float(scale),
+                                      _ptr(scale_dev), rq.data_ptr(), rd.data_ptr(), label_offset, label_stride, lse.data_ptr(),
+                                      argmax.data_ptr(), label_logit.data_ptr(), stats.data_ptr(), ws.data_ptr(), _stream()),
+               "cx_infonce_mat_fwd")
+    if ev is not None:
+        TIMER.end("infonce_fwd", 2.0 * n * m * max(dims), ev)
+    return lse, argmax, label_logit, stats
+
+
+def infonce_mat_bwd(q, d, dims, wrel, scale, scale_dev, rq, rd, label_offset, label_stride, lse, coef, coef_gamma_dev, inv_gamma_dev,
+                    width):
+    """Single-accumulation Matryoshka backward (2..4 ascending dims).  Returns (dq_raw [n, width], dd_raw [m, width] fp32 -- the
+    scale * T_t * operand part of the gradients, zero beyond max(dims) --, alpha [P, n], beta [P, m])."""
+    import ctypes
+    n, m, P, K = q.shape[0], d.shape[0], len(dims), max(dims)
+    dev = q.device
+    ldw = (width + 3) // 4 * 4
+    mk = (torch.zeros if width > K else torch.empty)
+    dq = mk(n, ldw, device=dev, dtype=torch.float32)[:, :width]
+    dd = mk(m, ldw, device=dev, dtype=torch.float32)[:, :width]
+    alpha = torch.empty(P, n, device=dev, dtype=torch.float32)
+    beta = torch.empty(P, m, device=dev, dtype=torch.float32)
+    lib = _lib.load()
+    ws = torch.empty(lib.cx_infonce_mat_bwd_workspace_bytes(n, m, K, P), device=dev, dtype=torch.uint8)
+    dims_c = (ctypes.c_int32 * P)(*[int(k) for k in dims])
+    wrel_c = (ctypes.c_float * P)(*[float(w) for w in wrel])
+    ev = TIMER.begin("infonce_bwd") if TIMER is not None else None
+    _lib.check(lib.cx_infonce_mat_bwd(q.data_ptr(), q.stride(0), d.data_ptr(), d.stride(0), n, m, P, ctypes.addressof(dims_c),
+                                      ctypes.addressof(wrel_c), float(scale), _ptr(scale_dev), rq.data_ptr(), rd.data_ptr(), label_offset,
+                                      label_stride, lse.data_ptr(), float(coef), coef_gamma_dev.data_ptr(), inv_gamma_dev.data_ptr(),
+                                      dq.data_ptr(), dq.stride(0), dd.data_ptr(), dd.stride(0), alpha.data_ptr(), beta.data_ptr(),
+                                      ws.data_ptr(), _stream()), "cx_infonce_mat_bwd")
+    if ev is not None:
+        TIMER.end("infonce_bwd", 4.0 * n * m * K, ev)
+    return dq, dd, alpha, beta
+
+
 def infonce_bwd(q, d, k_dim, scale, scale_dev, rq, rd, label_offset, label_stride, lse, coef, coef_dev, dq, dd,
                 accumulate_dd, stats, workspace):
     lib = _lib.load()

@@ -93,6 +93,25 @@ CX_API size_t cx_infonce_workspace_bytes(int n, int m, int k_dim);
 CX_API int cx_infonce_fwd(const void* q, int64_t ldq, const void* d, int64_t ldd, int n, int m, int k_dim, float scale,
                    const float* scale_dev, const float* rq, const float* rd, int label_offset, int label_stride, float* lse, int32_t* argmax,
                    float* label_logit, float* stats, void* workspace, cx_stream_t stream);
+/* Matryoshka forward in ONE accumulation over K = dims[n_dims-1] (replaces the per-dim loop of trainers/text_text.py:352-369):
+ * dims ascending multiples of 64 (<= 8 of them); rq [n_dims][n], rd [n_dims][m] = inverse L2 norms of the row prefixes; outputs per
+ * prefix: lse / argmax / label_logit [n_dims][n], stats [n_dims][4] (stats[s][0] = sum_i (lse - label logit), [s][1] = hits).
+ * 2*n*m*K FLOPs instead of 2*n*m*sum(dims); each prefix's logits are the running sum of segment products kept in tensor memory. */
+CX_API size_t cx_infonce_mat_workspace_bytes(int n, int m, int n_dims);
+CX_API int cx_infonce_mat_fwd(const void* q, int64_t ldq, const void* d, int64_t ldd, int n, int m, int n_dims, const int32_t* dims,
+                       float scale, const float* scale_dev, const float* rq, const float* rd, int label_offset, int label_stride,
+                       float* lse, int32_t* argmax, float* label_logit, float* stats, void* workspace, cx_stream_t stream);
+/* Matryoshka backward from ONE more accumulation (2..4 prefix dims): emits, per SEGMENT t of the columns, the raw gradient
+ * contribution dq_raw[:, seg_t] = a * T_t d[:, seg_t], dd_raw[:, seg_t] = a * T_t^T q[:, seg_t] with a = scale * coef * (*coef_gamma_dev)
+ * and T_t = sum_{s>=t} wrel_s diag(rq_s)(softmax_s - onehot) diag(rd_s) * (*inv_gamma_dev)  (fp16 workspace), plus the per-prefix
+ * scalars alpha[s][i] = sum_j wrel_s (softmax_s - onehot) S_s, beta[s][j] (column sums).  The caller finishes
+ * dq = dq_raw - q * sum_{s>=t} coef' rq_s^2 alpha_s (see loss.py::_matryoshka_backward).  4*n*m*K FLOPs for the contractions. */
+CX_API size_t cx_infonce_mat_bwd_workspace_bytes(int n, int m, int k_max, int n_dims);
+CX_API int cx_infonce_mat_bwd(const void* q, int64_t ldq, const void* d, int64_t ldd, int n, int m, int n_dims, const int32_t* dims,
+                       const float* wrel, float scale, const float* scale_dev, const float* rq, const float* rd, int label_offset,
+                       int label_stride, const float* lse, float coef, const float* coef_gamma_dev, const float* inv_gamma_dev,
+                       float* dq_raw, int64_t lddq, float* dd_raw, int64_t lddd, float* alpha, float* beta, void* workspace,
+                       cx_stream_t stream);
 CX_API int cx_infonce_bwd(const void* q, int64_t ldq, const void* d, int64_t ldd, int n, int m, int k_dim, float scale,
                    const float* scale_dev, const float* rq, const float* rd, int label_offset, int label_stride, const float* lse, float coef,
                    const float* coef_dev,

@@ -207,6 +207,65 @@ def test_config4_matryoshka_dims_768_512_256_128_vs_oracle():
         assert abs(logged[f"accuracy/accuracy_x_matryoshka_{dim_k}"] - per["accuracy"]) < 1e-7, dim_k
 
 
+@pytest.mark.parametrize("n,m,dims,offset,stride", [(200, 330, [64, 128, 192], 0, 1), (256, 256, [128, 256, 512, 768], 0, 1),
+                                                    (1024, 4096, [64, 128, 256, 512, 768], 1024, 1), (300, 1200, [128, 768], 0, 4)])
+def test_matryoshka_single_accumulation_forward_vs_per_prefix_and_oracle(n, m, dims, offset, stride):
+    """cx_infonce_mat_fwd (one accumulation over K, prefix sums in tensor memory) against (a) the per-prefix kernel it replaces
+    (same bf16 operands, same inverse norms: lse to 1e-5, argmax bit-exact) and (b) the float64 oracle of normalize(x[:, :k])
+    logits at 1e-3; ragged n / m, label offsets and strides included."""
+    from contrastors_b200 import ops
+    rs = np.random.RandomState(n + m)
+    K = max(dims)
+    q = O.bf16_round((rs.randn(n, K) * 1.3).astype(np.float32))
+    d = O.bf16_round((rs.randn(m, K) * 0.8).astype(np.float32))
+    qt, dt = torch.tensor(q, device="cuda"), torch.tensor(d, device="cuda")
+    qb, _ = ops.rows_to_bf16(qt)
+    db, _ = ops.rows_to_bf16(dt)
+    rq = torch.stack([ops.row_inv_norms(qt, k) for k in dims])
+    rd = torch.stack([ops.row_inv_norms(dt, k) for k in dims])
+    scale = 20.0
+    lse, argmax, label_logit, stats = ops.infonce_mat_fwd(qb, db, dims, scale, None, rq, rd, offset, stride)
+    torch.cuda.synchronize()
+    labels = (np.arange(n) + offset) * stride
+    for j, k in enumerate(dims):
+        ws = ops.infonce_workspace(n, m, K, "cuda")
+        lse1, arg1, ll1, st1 = ops.infonce_fwd(qb, db, k, scale, None, rq[j], rd[j], offset, stride, ws)
+        assert torch.equal(argmax[j], arg1), k
+        assert (lse[j] - lse1).abs().max().item() <= 1e-5 * max(lse1.abs().max().item(), 1.0), k
+        assert (label_logit[j] - ll1).abs().max().item() <= 1e-5 * max(ll1.abs().max().item(), 1.0), k
+        assert abs(stats[j, 0].item() - st1[0].item()) <= 1e-4 * max(abs(st1[0].item()), 1.0) and stats[j, 1].item() == st1[1].item()
+        s64 = scale * (O.l2_normalize(q[:, :k]) @ O.l2_normalize(d[:, :k]).T)
+        want = O._lse_rows(s64)
+        rel_close(lse[j].cpu().numpy(), want)
+        assert np.array_equal(argmax[j].cpu().numpy().astype(np.int64), s64.argmax(axis=1))
+        rel_close(label_logit[j].cpu().numpy(), s64[np.arange(n), labels], floor=1.0)
+
+
+@pytest.mark.parametrize("n,neg,dims,weights", [(200, 2, [64, 128, 192], [1.0, 0.5, 2.0]), (384, 1, [256, 768], [1.0, 1.0]),
+                                                (130, 3, [768, 512, 256, 128], [0.5, 1.0, 1.0, 0.25])])
+def test_matryoshka_single_accumulation_backward_vs_oracle(n, neg, dims, weights):
+    """matryoshka_clip_loss through the single-accumulation forward AND backward (cumulative dS matrices per column segment, the
+    F.normalize chain folded into per-prefix row / column scalars): loss, dQ, dD, d logit-scale at 1e-3 of the float64 oracle;
+    ragged sizes, hard-negative label stride, unequal weights, dims given in any order."""
+    from contrastors_b200 import LogitScale, matryoshka_clip_loss
+    rs = np.random.RandomState(n + len(dims))
+    K, m = max(dims), n * neg
+    q = rs.randn(n, K)
+    d = rs.randn(m, K)
+    d[::neg] += 0.3 * q
+    q, d = O.bf16_round((q * 1.4).astype(np.float32)), O.bf16_round((d * 0.7).astype(np.float32))
+    o = O.matryoshka_loss_fwd_bwd(q, d, 30.0, dims, weights)
+    qt = torch.tensor(q, device="cuda", requires_grad=True)
+    dt = torch.tensor(d, device="cuda", requires_grad=True)
+    ls = LogitScale(logit_scale=30.0, trainable_logit_scale=True).cuda()
+    loss = matryoshka_clip_loss(qt, dt, ls, dims, weights)
+    (loss * 0.7).backward()   # a non-unit upstream gradient exercises the device-side coefficient
+    rel_close(loss.item(), o["loss"])
+    rel_close(qt.grad.cpu().numpy(), 0.7 * o["dq"])
+    rel_close(dt.grad.cpu().numpy(), 0.7 * o["dd"])
+    rel_close(ls.logit_scale.grad.item(), 0.7 * o["dlogit"], rel=3e-3, floor=0.7 * sum(p["dlogit_abs"] for p in o["per_dim"]) * 1e-1)
+
+
 def test_config3_symmetric_loss_rank_shard_512_by_4096_vs_oracle():
     """BASELINE configs[2] shape class: one rank's half of the symmetric CLIP loss with N = 512 local rows against M = 4096
     gathered rows (world size 8, this rank = 3): normalisation in the kernel, label offset rank*N, mult = ws / 2.  The
