@@ -132,7 +132,7 @@ def _step_logit_scale(logit_scale, lr, betas, eps):
 
 def training_step(model, batch, logit_scale, *, lr: float, chunk_size: Optional[int] = 64, betas=(0.9, 0.999), eps=1e-8,
                   weight_decay=0.01, max_grad_norm: Optional[float] = 1.0, matryoshka_dims=None, matryoshka_loss_weights=None,
-                  overlap_grad_reduce: bool = True):
+                  overlap_grad_reduce: bool = False):
     """base.py:366-393 for a BiEncoder tower on the fused path: forward (+ backward), gradient all-reduce across ranks
     (DDP's job in the reference; in layer-ordered buckets under the last backward when ``overlap_grad_reduce``), global-norm
     clip + AdamW + zero_grad in two launches with DDP's 1 / world_size folded into the step, and the trainable logit

@@ -167,11 +167,11 @@ def test_dual_encoder_loss_two_ranks(tmp_path):
     assert True
 
 
-def _bucket_worker(rank, ws, port, out_dir):
+def _bucket_worker(rank, ws, port, out_dir, backend="nccl"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=ws)
+    torch.cuda.set_device(rank if backend == "nccl" else 0)
+    dist.init_process_group(backend, rank=rank, world_size=ws)
     import contrastors_b200 as cb
     from contrastors_b200.trainer import training_step
     cfg = cb.NomicBertConfig(vocab_size=256, n_embd=128, n_head=2, n_inner=256, n_layer=3)
@@ -190,6 +190,16 @@ def _bucket_worker(rank, ws, port, out_dir):
         out["loss_%d" % overlap] = loss.item()
     np.savez(os.path.join(out_dir, f"bk{rank}.npz"), **out)
     dist.destroy_process_group()
+
+
+def test_bucketed_gradient_reduction_two_processes_one_gpu(tmp_path):
+    """The same check with both ranks on ONE GPU over gloo (CUDA tensors): exercises the trainer / reducer plumbing (arming before
+    the last backward, per-layer buckets from the autograd thread, the folded 1/ws) on the driver's 1-GPU box too."""
+    mp.spawn(_bucket_worker, args=(2, 29661, str(tmp_path), "gloo"), nprocs=2, join=True)
+    z0, z1 = np.load(tmp_path / "bk0.npz"), np.load(tmp_path / "bk1.npz")
+    assert np.array_equal(z0["w_1"], z1["w_1"]) and np.array_equal(z0["w_0"], z1["w_0"])
+    diff = np.abs(z0["w_1"] - z0["w_0"])
+    assert (diff > 0.5e-3).mean() < 1e-3 and abs(z0["loss_1"] - z0["loss_0"]) <= 1e-6 * abs(z0["loss_0"]) + 1e-7
 
 
 def test_bucketed_gradient_reduction_equals_single_allreduce(tmp_path):
