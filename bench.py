@@ -130,11 +130,11 @@ def _ensure_group(backend):
     import torch.distributed as dist
     if dist.is_initialized():
         return False
-    import socket
-    with socket.socket() as sk:  # a private 1-rank group on a free port (never the torchrun rendezvous store)
-        sk.bind(("127.0.0.1", 0))
-        port = sk.getsockname()[1]
-    dist.init_process_group(backend, init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    import tempfile
+    # a private 1-rank group through a FileStore: under torchrun a tcp:// rendezvous is redirected to the elastic agent's store
+    # (TORCHELASTIC_USE_AGENT_STORE) and a worker that asks for its own port waits for a server that never comes
+    store = dist.FileStore(os.path.join(tempfile.mkdtemp(prefix="cxbench_"), "store"), 1)
+    dist.init_process_group(backend, store=store, rank=0, world_size=1)
     return True
 
 

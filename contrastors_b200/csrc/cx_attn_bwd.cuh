@@ -217,15 +217,20 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     const float2 sc2 = make_float2(scale2, scale2), ss2 = make_float2(softmax_scale, softmax_scale);
     const float* lse_h = lse + (size_t)head * T + seq_begin;
     const float* dl_h = delta + (size_t)head * T + seq_begin;
-    // thread wt publishes one column statistic per tile: wt < 128: -lse * log2(e) of query wt; else -delta * scale of query wt - 128
+    // thread wt publishes one column statistic per tile: wt < 128: -lse * log2(e) of query wt; else -delta * scale of query wt - 128.
+    // The raw value of the NEXT tile is loaded a whole iteration ahead and only converted when it is published (round 2: with the
+    // multiply next to the load, every worker stalled ~7 % of the kernel on that global load, profiles/r02e_attn_bwd3_stalls...)
     const int sq = wt & 127;
-    float st_n = (sq < len) ? ((wt < 128) ? -lse_h[sq] * kLog2e : -dl_h[sq] * softmax_scale) : ((wt < 128) ? -INFINITY : 0.f);
+    const float* st_src = (wt < 128) ? lse_h : dl_h;
+    const float st_mul = (wt < 128) ? -kLog2e : -softmax_scale;
+    const float st_pad = (wt < 128) ? -INFINITY : 0.f;
+    float st_raw = (sq < len) ? st_src[sq] : 0.f;
     for (int i = 0; i < nq; ++i) {
       float* sb = stat + (i & 1) * 256;
-      sb[wt] = st_n;  // [0,128): -lse2 per query (-inf past the sequence end => P = 0), [128,256): -delta*scale
+      sb[wt] = (i * 128 + sq < len) ? st_raw * st_mul : st_pad;  // [0,128): -lse2 per query (-inf past the end => P = 0), [128,256): -delta*scale
       {
-        const int nqr = (i + 1) * 128 + sq;  // prefetch the next tile's statistic
-        st_n = (nqr < len) ? ((wt < 128) ? -lse_h[nqr] * kLog2e : -dl_h[nqr] * softmax_scale) : ((wt < 128) ? -INFINITY : 0.f);
+        const int nqr = (i + 1) * 128 + sq;  // prefetch the next tile's statistic (consumed one iteration later)
+        st_raw = (nqr < len) ? st_src[nqr] : 0.f;
       }
       named_bar_sync(4, 256);
       const float* nl = sb + grp * 64;        // -lse2 of this thread's 64 queries

@@ -132,12 +132,15 @@ def _step_logit_scale(logit_scale, lr, betas, eps):
 
 def training_step(model, batch, logit_scale, *, lr: float, chunk_size: Optional[int] = 64, betas=(0.9, 0.999), eps=1e-8,
                   weight_decay=0.01, max_grad_norm: Optional[float] = 1.0, matryoshka_dims=None, matryoshka_loss_weights=None,
-                  overlap_grad_reduce: bool = False):
+                  overlap_grad_reduce: Optional[bool] = None):
     """base.py:366-393 for a BiEncoder tower on the fused path: forward (+ backward), gradient all-reduce across ranks
     (DDP's job in the reference; in layer-ordered buckets under the last backward when ``overlap_grad_reduce``), global-norm
     clip + AdamW + zero_grad in two launches with DDP's 1 / world_size folded into the step, and the trainable logit
     scale's own all-reduce + AdamW.  ``chunk_size=None`` selects the plain (non-GradCache) step."""
     model.train()
+    if overlap_grad_reduce is None:  # default: one all-reduce after the last backward; CX_OVERLAP_GRAD_REDUCE=1 selects the buckets
+        import os
+        overlap_grad_reduce = os.environ.get("CX_OVERLAP_GRAD_REDUCE", "0") == "1"
     reducer = None
     if overlap_grad_reduce and dist.is_initialized() and dist.get_world_size() > 1 and hasattr(model.trunk, "layer_grad_slices"):
         reducer = model.__dict__.get("_cx_reducer")

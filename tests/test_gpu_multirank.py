@@ -186,7 +186,7 @@ def _bucket_worker(rank, ws, port, out_dir, backend="nccl"):
         model.trunk.reset_parameters(seed=3)
         loss = training_step(model, dict(batch), ls, lr=1e-3, chunk_size=4, max_grad_norm=1.0, overlap_grad_reduce=overlap)
         torch.cuda.synchronize()
-        out["w_%d" % overlap] = model.trunk._flat.cpu().numpy()
+        out["w_%d" % overlap] = model.trunk._flat.detach().cpu().numpy()
         out["loss_%d" % overlap] = loss.item()
     np.savez(os.path.join(out_dir, f"bk{rank}.npz"), **out)
     dist.destroy_process_group()
