@@ -1,7 +1,7 @@
 """mbarrier protocols of the attention kernels on the discrete-event model (tools/sim_attn_protocol.py): every kernel
-generation terminates without deadlock, barrier over-arrival, parity aliasing or data hazard over random schedules, and the
-model does catch a removed wait (negative controls).  CPU only; guards the protocol of the two kernels that have not run on
-hardware yet (attn_fwd4_kernel, attn_bwd3_kernel) as well as the default ones."""
+terminates without deadlock, barrier over-arrival, parity aliasing or data hazard over random schedules, and the model does catch
+a removed wait (negative controls).  CPU only; the two kernels modelled are the ones in the library (attn_fwd4_kernel,
+attn_bwd3_kernel: written against this model at the end of round 1, validated on hardware in round 2)."""
 import os
 import sys
 
@@ -16,8 +16,7 @@ def test_protocol_terminates_without_hazards(name):
     sim.sweep(name, sizes=range(1, 9), schedules=40)
 
 
-@pytest.mark.parametrize("name,bug", [("attn_fwd3_kernel", "no_s_free"), ("attn_fwd4_kernel", "no_s_free"),
-                                      ("attn_fwd4_kernel", "no_pv_done"), ("attn_fwd5_kernel", "no_q_full"), ("attn_bwd2_kernel", "no_dq_full_wait"),
+@pytest.mark.parametrize("name,bug", [("attn_fwd4_kernel", "no_s_free"), ("attn_fwd4_kernel", "no_pv_done"),
                                       ("attn_bwd3_kernel", "no_dq_full_wait")])
 def test_model_catches_a_removed_wait(name, bug):
     caught = 0

@@ -141,108 +141,6 @@ def check(cond, msg):
         raise ProtocolError(msg)
 
 
-# ================================================================================================ forward, wide-S (fwd3)
-def run_fwd3(nu, seed, bug=None):
-    """attn_fwd3_kernel: nu = number of 64-key halves; 4 softmax warps (one thread per row)."""
-    sim = Sim(seed)
-    nk = (nu + 1) // 2
-    B = lambda n, c: sim.barrier(n, c)
-    q_full, s_full, s_free, o_full = B("q_full", 1), B("s_full", 1), B("s_free", 128), B("o_full", 1)
-    k_full, k_empty = [B("k_full0", 1), B("k_full1", 1)], [B("k_empty0", 1), B("k_empty1", 1)]
-    v_full, v_empty = [B("v_full0", 1), B("v_full1", 1)], [B("v_empty0", 1), B("v_empty1", 1)]
-    p_ready, pv_done = [B("p_ready0", 128), B("p_ready1", 128)], [B("pv_done0", 1), B("pv_done1", 1)]
-    S = dict(tile=-1, loaded=set())             # score columns: tile held, (warp, half) pairs that loaded it
-    P = [dict(u=-1, written=set(), consumed=-1) for _ in range(2)]   # P columns of half h
-    O = dict(pv_running=False, pv_done_upto=-1)
-    Kst, Vst = [dict(tile=-1, busy=False) for _ in range(2)], [dict(tile=-1, busy=0) for _ in range(2)]
-
-    def tma():
-        sim.tma(q_full)
-        Kst[0]["tile"] = 0; sim.tma(k_full[0])
-        Vst[0]["tile"] = 0; sim.tma(v_full[0])
-        for j in range(1, nk):
-            st = j & 1
-            yield ("wait", k_empty[st], (j >> 1) - 1 if j >= 2 else -1) if j >= 2 else ("now",)
-            check(not Kst[st]["busy"], f"K stage {st} reloaded while S MMA reads it")
-            Kst[st]["tile"] = j; sim.tma(k_full[st])
-            yield ("wait", v_empty[st], (j >> 1) - 1) if j >= 2 else ("now",)
-            check(Vst[st]["busy"] == 0, f"V stage {st} reloaded while PV reads it")
-            Vst[st]["tile"] = j; sim.tma(v_full[st])
-
-    def issue_s(j):
-        st = j & 1
-        def start():
-            check(Kst[st]["tile"] == j, f"S({j}) reads K stage holding tile {Kst[st]['tile']}")
-            need = {(w, h) for w in range(4) for h in range(min(2, nu - 2 * (j - 1)))} if j > 0 else set()
-            check(j == 0 or (S["tile"] == j - 1 and S["loaded"] >= need), f"S({j}) overwrites scores of tile {S['tile']} not fully loaded")
-            Kst[st]["busy"] = True
-        def end():
-            S["tile"], S["loaded"] = j, set()
-            Kst[st]["busy"] = False
-        sim.mma(256, start, end)
-        sim.commit(s_full)
-        sim.commit(k_empty[st])
-
-    def mma():
-        yield ("wait", q_full, 0)
-        yield ("wait", k_full[0], 0)
-        issue_s(0)
-        for j in range(nk):
-            st = j & 1
-            halves = min(2, nu - 2 * j)
-            yield ("wait", v_full[st], j >> 1)
-            for h in range(halves):
-                u = 2 * j + h
-                yield ("wait", p_ready[h], j)
-                def start(u=u, h=h, st=st, j=j):
-                    check(P[h]["u"] == u and len(P[h]["written"]) == 4, f"PV({u}) reads P[{h}] holding {P[h]['u']} / {P[h]['written']}")
-                    check(Vst[st]["tile"] == j, f"PV({u}) reads V stage holding tile {Vst[st]['tile']}")
-                    check(not O["pv_running"], "two PV chains overlap")
-                    O["pv_running"] = True; Vst[st]["busy"] += 1
-                def end(u=u, h=h, st=st):
-                    O["pv_running"] = False; O["pv_done_upto"] = u; P[h]["consumed"] = u; Vst[st]["busy"] -= 1
-                sim.mma(256, start, end)
-                if h == halves - 1:
-                    sim.commit(v_empty[st])
-                sim.commit(pv_done[h])
-                if h == 0 and j + 1 < nk:
-                    if bug != "no_s_free":
-                        yield ("wait", s_free, j)
-                    yield ("wait", k_full[st ^ 1], (j + 1) >> 1)
-                    issue_s(j + 1)
-        sim.commit(o_full)
-
-    def softmax(w):
-        for u in range(nu):
-            h, j = u & 1, u >> 1
-            if h == 0:
-                yield ("wait", s_full, j)
-            check(S["tile"] == j, f"softmax {w} loads scores of tile {S['tile']} expecting {j}")
-            yield ("sleep", sim.rng.uniform(20, 500))     # tcgen05.ld (long tail: a descheduled warp)
-            check(S["tile"] == j, f"scores of tile {j} overwritten under softmax {w}'s load")
-            S["loaded"].add((w, h))
-            if h == 1 or u == nu - 1:
-                s_free.arrive(32)
-            yield ("sleep", sim.rng.uniform(300, 1500))   # max, exponentials
-            if j > 0:
-                yield ("wait", pv_done[h], j - 1)
-            check(P[h]["consumed"] >= u - 2 or u < 2, f"P[{h}] overwritten before PV({u - 2}) finished")
-            if P[h]["u"] != u:
-                P[h]["u"], P[h]["written"] = u, set()
-            P[h]["written"].add(w)
-            if u > 0 and sim.rng.random() < 0.5:          # O rescale (rare in reality)
-                yield ("wait", pv_done[h ^ 1], (u - 1) >> 1)
-                check(O["pv_done_upto"] >= u - 1 and not O["pv_running"], f"O rescaled while PV({u - 1}) may run")
-                yield ("sleep", sim.rng.uniform(50, 200))
-            p_ready[h].arrive(32)
-        yield ("wait", o_full, 0)
-
-    sim.spawn("tma", tma()); sim.spawn("mma", mma())
-    for w in range(4):
-        sim.spawn(f"softmax{w}", softmax(w))
-    sim.run()
-
-
 # ================================================================================================ forward, two threads per row (fwd4)
 def run_fwd4(nk, seed, bug=None):
     """attn_fwd4_kernel: nk = number of 128-key tiles; 8 softmax warps (two threads per row)."""
@@ -335,136 +233,6 @@ def run_fwd4(nk, seed, bug=None):
 
 
 # ================================================================================================ forward, persistent (fwd5)
-def run_fwd5(n_items, seed, bug=None):
-    """attn_fwd5_kernel: one persistent CTA running n_items work items of 1..4 key tiles each; 8 softmax warps."""
-    sim = Sim(seed)
-    nks = [sim.rng.randint(1, 4) for _ in range(n_items)]
-    B = lambda n, c: sim.barrier(n, c)
-    s_full, s_free, p_ready, pv_done, o_full, o_free = B("s_full", 1), B("s_free", 256), B("p_ready", 256), B("pv_done", 1), B("o_full", 1), B("o_free", 256)
-    q_full, q_empty = [B("q_full0", 1), B("q_full1", 1)], [B("q_empty0", 257), B("q_empty1", 257)]
-    k_full, k_empty = [B("k_full0", 1), B("k_full1", 1)], [B("k_empty0", 1), B("k_empty1", 1)]
-    v_full, v_empty = [B("v_full0", 1), B("v_full1", 1)], [B("v_empty0", 1), B("v_empty1", 1)]
-    S = dict(tile=-1, loaded=set())
-    P = dict(tile=-1, written=set(), consumed=-1)
-    O = dict(item=-1, running=False, done_tile=-1, read_out=-1)   # read_out: last item whose O every warp has loaded
-    Oread = {}
-    Qb = [dict(item=-1, s_busy=0, staged=set(), copied=set(), landed=False) for _ in range(2)]
-    Kst, Vst = [dict(tile=-1, busy=False) for _ in range(2)], [dict(tile=-1, busy=False) for _ in range(2)]
-    tiles = [(n, j) for n, nk in enumerate(nks) for j in range(nk)]   # global tile g -> (item, j)
-
-    def tma():
-        g = 0
-        for n, nk in enumerate(nks):
-            qb = n & 1
-            if n >= 2:
-                yield ("wait", q_empty[qb], (n >> 1) - 1)
-            check(Qb[qb]["s_busy"] == 0, f"Q buffer {qb} reloaded while an S MMA reads it")
-            check(n < 2 or len(Qb[qb]["copied"]) == 8, f"Q buffer {qb} reloaded before item {n - 2}'s epilogue copied its staging tile out")
-            Qb[qb].update(item=n, staged=set(), copied=set(), landed=False)
-            sim.tma(q_full[qb], on_land=lambda qb=qb: Qb[qb].update(landed=True))
-            for j in range(nk):
-                st = g & 1
-                if g >= 2:
-                    yield ("wait", k_empty[st], (g >> 1) - 1)
-                check(not Kst[st]["busy"], "K stage reloaded while in use")
-                Kst[st]["tile"] = g; sim.tma(k_full[st])
-                if g >= 2:
-                    yield ("wait", v_empty[st], (g >> 1) - 1)
-                check(not Vst[st]["busy"], "V stage reloaded while in use")
-                Vst[st]["tile"] = g; sim.tma(v_full[st])
-                g += 1
-
-    def issue_s(g):
-        n, _ = tiles[g]
-        qb, st = n & 1, g & 1
-        def start():
-            check(Qb[qb]["item"] == n and Qb[qb]["landed"], f"S({g}) reads Q buffer holding item {Qb[qb]['item']} (wants {n}, landed {Qb[qb]['landed']})")
-            check(not Qb[qb]["staged"], f"S({g}) reads a Q buffer already used as staging")
-            check(Kst[st]["tile"] == g, f"S({g}) reads K stage holding {Kst[st]['tile']}")
-            check(g == 0 or (S["tile"] == g - 1 and len(S["loaded"]) == 8), f"S({g}) overwrites scores {S['tile']} loaded by {len(S['loaded'])}/8")
-            Kst[st]["busy"] = True; Qb[qb]["s_busy"] += 1
-        def end():
-            S["tile"], S["loaded"] = g, set(); Kst[st]["busy"] = False; Qb[qb]["s_busy"] -= 1
-        sim.mma(256, start, end)
-        sim.commit(s_full)
-        sim.commit(k_empty[st])
-
-    def mma():
-        yield ("wait", q_full[0], 0)
-        yield ("wait", k_full[0], 0)
-        issue_s(0)
-        for g, (n, j) in enumerate(tiles):
-            last = j == nks[n] - 1
-            has_next = g + 1 < len(tiles)
-            if has_next:
-                yield ("wait", s_free, g)
-                if last and bug != "no_q_full":
-                    yield ("wait", q_full[(n + 1) & 1], (n + 1) >> 1)
-                yield ("wait", k_full[(g + 1) & 1], (g + 1) >> 1)
-                issue_s(g + 1)
-            if last:
-                sim.commit(q_empty[n & 1])
-            yield ("wait", v_full[g & 1], g >> 1)
-            yield ("wait", p_ready, g)
-            if j == 0 and n > 0 and bug != "no_o_free":
-                yield ("wait", o_free, n - 1)
-            def start(g=g, n=n, j=j):
-                check(P["tile"] == g and len(P["written"]) == 8, f"PV({g}) reads P holding {P['tile']}")
-                check(Vst[g & 1]["tile"] == g, "PV reads the wrong V stage")
-                if j == 0:
-                    check(n == 0 or O["read_out"] >= n - 1, f"PV of item {n} overwrites item {n - 1}'s O before the epilogue read it")
-                O["item"] = n; O["running"] = True; Vst[g & 1]["busy"] = True
-            def end(g=g):
-                O["running"] = False; O["done_tile"] = g; P["consumed"] = g; Vst[g & 1]["busy"] = False
-            sim.mma(256, start, end)
-            sim.commit(v_empty[g & 1])
-            sim.commit(pv_done)
-            if last:
-                sim.commit(o_full)
-
-    def softmax(w):
-        g = 0
-        for n, nk in enumerate(nks):
-            for j in range(nk):
-                yield ("wait", s_full, g)
-                check(S["tile"] == g, f"softmax {w} loads scores of tile {S['tile']} expecting {g}")
-                yield ("sleep", sim.rng.uniform(20, 500))
-                check(S["tile"] == g, f"scores of tile {g} overwritten under softmax {w}'s load")
-                S["loaded"].add(w)
-                s_free.arrive(32)
-                yield ("sleep", sim.rng.uniform(300, 1200))
-                if g > 0:
-                    yield ("wait", pv_done, g - 1)
-                check(P["consumed"] >= g - 1, f"P overwritten before PV({g - 1}) finished")
-                if P["tile"] != g:
-                    P["tile"], P["written"] = g, set()
-                yield ("sleep", sim.rng.uniform(300, 1200))
-                if j > 0:
-                    check(O["done_tile"] >= g - 1 and not O["running"] and O["item"] == n, "O rescaled at the wrong time")
-                P["written"].add(w)
-                p_ready.arrive(32)
-                g += 1
-            yield ("wait", o_full, n)
-            check(O["item"] == n and not O["running"], f"epilogue of item {n} reads O of item {O['item']}")
-            yield ("sleep", sim.rng.uniform(20, 200))
-            Oread.setdefault(n, set()).add(w)
-            if len(Oread[n]) == 8:
-                O["read_out"] = n
-            o_free.arrive(32)
-            yield ("sleep", sim.rng.uniform(50, 300))     # row-sum exchange, named barriers
-            qb = n & 1
-            check(Qb[qb]["item"] == n and Qb[qb]["s_busy"] == 0, f"staging into Q buffer {qb} (item {Qb[qb]['item']}) while in use")
-            Qb[qb]["staged"].add(w)
-            yield ("sleep", sim.rng.uniform(100, 600))    # copy-out
-            Qb[qb]["copied"].add(w)
-            q_empty[qb].arrive(32)
-
-    sim.spawn("tma", tma()); sim.spawn("mma", mma())
-    for w in range(8):
-        sim.spawn(f"softmax{w}", softmax(w))
-    sim.run()
-
-
 # ================================================================================================ backward (bwd2 / bwd3)
 def run_bwd(nq, seed, transposed, bug=None):
     """attn_bwd2_kernel (transposed=False) / attn_bwd3_kernel (transposed=True): nq query tiles; 8 worker warps, 4 drain warps."""
@@ -615,10 +383,7 @@ def run_bwd(nq, seed, transposed, bug=None):
 
 
 KERNELS = {
-    "attn_fwd3_kernel": lambda n, seed, bug=None: run_fwd3(n, seed, bug),
     "attn_fwd4_kernel": lambda n, seed, bug=None: run_fwd4(n, seed, bug),
-    "attn_fwd5_kernel": lambda n, seed, bug=None: run_fwd5(n, seed, bug),
-    "attn_bwd2_kernel": lambda n, seed, bug=None: run_bwd(n, seed, False, bug),
     "attn_bwd3_kernel": lambda n, seed, bug=None: run_bwd(n, seed, True, bug),
 }
 
