@@ -150,10 +150,27 @@ int launch_gemm(const GemmArgs& g_in) {
     int splits = g.splits;
     if (splits <= 0) {
       splits = 1;
-      if (g.mode == EPI_STORE && g.out_f32 && tiles * 2 <= sm_count()) {
-        splits = sm_count() / tiles;
-        if (splits > num_kb / 4) splits = num_kb / 4;
-        if (splits < 1) splits = 1;
+      if (g.mode == EPI_STORE && g.out_f32) {
+        if (bn == 256 && gemm_use_pair(g)) {
+          // CTA pairs work on 256 x 256 tiles: pick the split count whose work items fill whole waves of SM pairs (round 1 counted
+          // 128-row tiles here: the Wqkv weight gradient, 9 x 3 pair tiles, got 2 splits = 54 items for 74 pairs)
+          const int ptiles = ((g.M + 255) / 256) * ((g.N + 255) / 256), pairs = sm_count() / 2;
+          int max_s = num_kb / 8;
+          if (max_s > 16) max_s = 16;
+          double best = 0.0;
+          for (int sp = 1; sp <= (max_s < 1 ? 1 : max_s); ++sp) {
+            const int items = ptiles * sp, waves = (items + pairs - 1) / pairs;
+            const double eff = (double)items / ((double)waves * pairs) - 0.004 * sp;  // prefer fewer reduce-add passes on a tie
+            if (eff > best + 1e-9) {
+              best = eff;
+              splits = sp;
+            }
+          }
+        } else if (tiles * 2 <= sm_count()) {
+          splits = sm_count() / tiles;
+          if (splits > num_kb / 4) splits = num_kb / 4;
+          if (splits < 1) splits = 1;
+        }
       }
     }
     if (splits > 1 && !(g.mode == EPI_STORE && g.out_f32)) return fail(CX_ERR_INVALID, "gemm: split-K needs an fp32 output");
