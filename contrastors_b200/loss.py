@@ -346,6 +346,7 @@ def get_chunked_embeddings(model, chunks, _retain: int = 0, _retained=None):
 
 
 _COMM_STREAMS = {}
+_GATHER_EVERY = 8  # chunks per document all-gather on the side stream
 
 
 def _comm_stream(device):
@@ -364,7 +365,7 @@ def _chunked_embeddings_with_gather(model, chunks, n_local, _retain: int = 0, _r
     embeddings, rand_states = [], []
     gathered = None
     comm = None
-    row = 0
+    row = row0 = 0
     streams = _chunk_streams(model, chunks)
     main = torch.cuda.current_stream()
     if streams:
@@ -398,11 +399,18 @@ def _chunked_embeddings_with_gather(model, chunks, n_local, _retain: int = 0, _r
                 if streams:
                     emb.record_stream(main)
             embeddings.append(emb)
-            outs = [gathered[r * n_local + row: r * n_local + row + b] for r in range(ws)]
-            with torch.cuda.stream(comm):
-                comm.wait_event(ready)
-                _timed("allgather_chunk", lambda: dist.all_gather(outs, mine))
             row += b
+            # one collective per _GATHER_EVERY chunks (and one for the tail): every call costs a launch, ws output views and a
+            # staging copy inside the process group, and the loss only needs the rows once the LAST chunk is in
+            if (i + 1) % _GATHER_EVERY == 0 or i == len(chunks) - 1:
+                outs = [gathered[r * n_local + row0: r * n_local + row] for r in range(ws)]
+                mine_all = gathered[rank * n_local + row0: rank * n_local + row]
+                with torch.cuda.stream(comm):
+                    comm.wait_event(ready)
+                    for s_ in (streams or ()):  # chunks alternate between two streams: the group spans both
+                        comm.wait_stream(s_)
+                    _timed("allgather_chunk", lambda: dist.all_gather(outs, mine_all))
+                row0 = row
     if streams:
         for s in streams:
             main.wait_stream(s)
