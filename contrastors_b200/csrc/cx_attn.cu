@@ -78,7 +78,7 @@ extern "C" int cx_attn_bwd(const void* qkv, const void* out, const void* dout, c
   const int T = total_tokens;
   {
     const int64_t threads = (int64_t)T * H * 8;
-    attn_delta_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta, T, H);
+    attn_delta_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta, dq_acc, T, H);
     CX_LAUNCH_CHECK();
   }
   CUtensorMap tmQKV, tmDO, tmDQ;

@@ -4,9 +4,10 @@
 constexpr int kBwd2Threads = 512;
 
 // ============================================================================================== backward
-// delta[h, t] = sum_d dO[t,h,d] * O[t,h,d]; 8 threads per (t, h) row of 64, 16-byte loads
+// delta[h, t] = sum_d dO[t,h,d] * O[t,h,d]; 8 threads per (t, h) row of 64, 16-byte loads.  The same threads zero the fp32 dQ
+// accumulator row the backward kernel reduce-adds into (32 bytes each): no separate 100 MB fill launch per layer.
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
-                                  float* __restrict__ delta, int T, int H) {
+                                  float* __restrict__ delta, float* __restrict__ dq_acc, int T, int H) {
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t row = gid >> 3;  // (t, h) flattened: element offset row * 64
   const int sub = (int)(gid & 7);
@@ -18,6 +19,9 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __n
     const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
 #pragma unroll
     for (int i = 0; i < 4; ++i) s += __low2float(pa[i]) * __low2float(pb[i]) + __high2float(pa[i]) * __high2float(pb[i]);
+    float4* z = reinterpret_cast<float4*>(dq_acc + row * kDh + sub * 8);
+    z[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    z[1] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   s += __shfl_xor_sync(0xffffffffu, s, 4);
   s += __shfl_xor_sync(0xffffffffu, s, 2);

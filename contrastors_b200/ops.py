@@ -435,7 +435,7 @@ def attn_bwd(qkv, out, dout, lse, cu_seqlens, max_seqlen, H, Dh, softmax_scale, 
     T = qkv.shape[0]
     nseq = cu_seqlens.numel() - 1
     dqkv = torch.empty_like(qkv)
-    dq_acc = torch.zeros(T, H * Dh, device=qkv.device, dtype=torch.float32)
+    dq_acc = torch.empty(T, H * Dh, device=qkv.device, dtype=torch.float32)  # zeroed by the delta kernel inside cx_attn_bwd
     delta = torch.empty(H, T, device=qkv.device, dtype=torch.float32)
     lib = _lib.load()
     ev = TIMER.begin("attn_bwd") if TIMER is not None else None

@@ -215,7 +215,7 @@ CX_API int cx_attn_pool_bwd(const float* q, const void* kv, const int32_t* cu_se
 /* ---- varlen non-causal attention on tcgen05 (replaces flash_attn_varlen_qkvpacked_func: layers/attention.py:158-181)
  * qkv [T,3,H,Dh] bf16 (RoPE already applied), cu_seqlens int32[nseq+1]; out [T,H,Dh] bf16; lse [H,T] fp32 (natural log).
  * Dh == 64.  Backward: dqkv [T,3,H,Dh] bf16 (dk, dv written directly; dq through the fp32 accumulator dq_acc [T,H*Dh],
- * which the caller zeroes and then finalises with cx_dq_finalize_rope or cx_dq_finalize). delta [H,T] fp32 scratch.
+ * which cx_attn_bwd zeroes itself and the caller finalises with cx_dq_finalize_rope or cx_dq_finalize). delta [H,T] fp32 scratch.
  * dk_rope_inv_freq (32 fp32 values, or NULL): when given, dk leaves the kernel already rotated back (the transpose of the
  * rotary embedding applied to k before the forward; position = the key's index inside its sequence), so the caller runs no
  * rotary pass over dqkv. */
