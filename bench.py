@@ -45,9 +45,9 @@ WORKLOAD = "configs[1]: nomic-bert-base text-text InfoNCE bf16 seq=512 global_bs
 
 def ncu_gemm_traffic():
     """Mean DRAM bytes (read + write) per launch of the GEMM kernel, from the committed `ncu --set full` capture of the
-    four forward GEMMs of one layer (profiles/r01_gemm_final_ncu_full_raw.csv); None if the capture is not there."""
+    four forward GEMMs of one layer (profiles/r02g_gemm_ncu_full_raw.csv); None if the capture is not there."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r01_gemm_final_ncu_full_raw.csv")
+    path = os.path.join(ROOT, "profiles", "r02g_gemm_ncu_full_raw.csv")
     try:
         rows = list(csv.reader(open(path)))
         hdr = rows[0]
@@ -416,7 +416,7 @@ def run_ours(args):
         achieved = gm["work_avg"] / (gm["ms_avg"] * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "cx::gemm_kernel (tcgen05, all encoder linears fwd/dgrad/wgrad)", "achieved": achieved,
                 "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": ncu_gemm_traffic(),
-                "traffic_note": "mean DRAM read+write bytes per launch over the 4 forward GEMMs of a layer (ncu --set full, profiles/r01_gemm_final_ncu_full_raw.csv); algorithmic operand+result bytes of the same 4 launches average 289 MB",
+                "traffic_note": "mean DRAM read+write bytes per launch over the 4 forward GEMMs of a layer (ncu --set full, profiles/r02g_gemm_ncu_full_raw.csv); algorithmic operand+result bytes of the same 4 launches average 289 MB (the fc1 launch also stores the 403 MB of pre-activations in training form)",
                 "peak_source": pk["source"] + " bf16_tflops_sustained", "launches_per_step": gm["launches"] / args.steps,
                 "avg_launch_ms": gm["ms_avg"], "sampled_launches": gm["sampled"],
                 "share_of_step": gm["ms_avg"] * gm["launches"] / ms_dev}
@@ -495,7 +495,9 @@ def run_image_text(args):
     global_batch = args.global_batch or (65536 if lit else 32768)
     n_local, seq = global_batch // world, 77
     torch.manual_seed(0)
-    vision = cb.VisionBiEncoder(cb.VisionBiEncoderConfig(encoder=cb.vit_l14() if lit else cb.vit_b16(), freeze=lit)).to(dev)
+    # LiT: the 1024-wide frozen ViT-L/14 meets the 768-wide text tower through a (trainable) projection, as BiEncoder.proj does
+    vision = cb.VisionBiEncoder(cb.VisionBiEncoderConfig(encoder=cb.vit_l14() if lit else cb.vit_b16(), freeze=lit,
+                                                         projection_dim=768 if lit else None)).to(dev)
     text = cb.BiEncoder(cb.BiEncoderConfig(encoder=cb.nomic_bert_base())).to(dev)
     vision.trunk.reset_parameters(seed=1)
     text.trunk.reset_parameters(seed=0)

@@ -66,6 +66,8 @@ class _FusedInfoNCE(torch.autograd.Function):
             raise RuntimeError("contrastors_b200.clip_loss needs CUDA tensors on a B200 (there is no CPU fallback); "
                                "the CPU restatement lives in oracle/ and is test infrastructure only")
         n, width = query.shape
+        if document.dim() != 2 or document.shape[1] != width:  # torch.matmul's complaint in the reference (loss.py:109)
+            raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({n}x{width} and {document.shape[1]}x{document.shape[0]})")
         q_bf = _as_bf16_rows(query.detach())
         if spec.pregathered is not None:
             d_bf = spec.pregathered  # gathered chunk by chunk on the side stream while the encoder was still running

@@ -130,6 +130,33 @@ def _step_logit_scale(logit_scale, lr, betas, eps):
         opts.setdefault(id(p), _ScalarAdamW(p)).update(lr, betas, eps)
 
 
+def _step_tower(model, grad_scale, lr, betas, eps, weight_decay, max_grad_norm):
+    """Fused clip + AdamW on the tower's flat buffers, and the same step (same global clip coefficient) for the pooler / projection
+    parameters that live outside them.  A frozen trunk (LiT) is skipped; its trainable head is still stepped."""
+    head = [p for p in head_parameters(model) if p.grad is not None]
+    trunk_trainable = any(p.requires_grad for p in model.trunk.parameters())
+    extra = None
+    if head:
+        for p in head:
+            if dist.is_initialized() and dist.get_world_size() > 1:
+                dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)
+                p.grad.mul_(1.0 / dist.get_world_size())
+        extra = torch.stack([p.grad.float().pow(2).sum() for p in head]).sum()
+    coef = None
+    if trunk_trainable:
+        coef = model.trunk.fused_adamw_step(lr, betas=betas, eps=eps, weight_decay=weight_decay, max_grad_norm=max_grad_norm,
+                                            grad_scale=grad_scale, extra_sq_norm=extra)
+    elif head and max_grad_norm:
+        coef = torch.clamp(max_grad_norm / (extra.sqrt() + 1e-6), max=1.0).reshape(1)
+    if head:
+        opts = model.__dict__.setdefault("_cx_head_adamw", {})
+        with torch.no_grad():
+            for p in head:
+                if coef is not None:
+                    p.grad.mul_(coef.to(p.grad.dtype))
+                opts.setdefault(id(p), _ScalarAdamW(p)).update(lr, betas, eps, weight_decay if p.squeeze().ndim >= 2 else 0.0)
+
+
 def training_step(model, batch, logit_scale, *, lr: float, chunk_size: Optional[int] = 64, betas=(0.9, 0.999), eps=1e-8,
                   weight_decay=0.01, max_grad_norm: Optional[float] = 1.0, matryoshka_dims=None, matryoshka_loss_weights=None,
                   overlap_grad_reduce: Optional[bool] = None):
@@ -156,23 +183,7 @@ def training_step(model, batch, logit_scale, *, lr: float, chunk_size: Optional[
             reducer.arm()
         out["loss"].backward()
     grad_scale = reducer.wait() if reducer is not None else allreduce_gradients(model, average=False)
-    head = [p for p in head_parameters(model) if p.grad is not None]  # pooler / projection parameters outside the flat buffers
-    extra = None
-    if head:
-        for p in head:
-            if dist.is_initialized() and dist.get_world_size() > 1:
-                dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)
-                p.grad.mul_(1.0 / dist.get_world_size())
-        extra = torch.stack([p.grad.float().pow(2).sum() for p in head]).sum()
-    coef = model.trunk.fused_adamw_step(lr, betas=betas, eps=eps, weight_decay=weight_decay, max_grad_norm=max_grad_norm,
-                                        grad_scale=grad_scale, extra_sq_norm=extra)
-    if head:
-        opts = model.__dict__.setdefault("_cx_head_adamw", {})
-        with torch.no_grad():
-            for p in head:
-                if coef is not None:
-                    p.grad.mul_(coef.to(p.grad.dtype))
-                opts.setdefault(id(p), _ScalarAdamW(p)).update(lr, betas, eps, weight_decay if p.squeeze().ndim >= 2 else 0.0)
+    _step_tower(model, grad_scale, lr, betas, eps, weight_decay, max_grad_norm)
     _step_logit_scale(logit_scale, lr, betas, eps)
     return out["loss"].detach()
 
@@ -192,9 +203,7 @@ def dual_training_step(vision, text, vision_inputs, text_inputs, logit_scale, *,
     loss = grad_cache_loss(tower1=vision, t1_inputs=vision_inputs, tower2=text, t2_inputs=text_inputs, chunk_size=chunk_size,
                            logit_scale=logit_scale, bidirectional=bidirectional)
     for tower in (vision, text):
-        if not any(p.requires_grad for p in tower.trunk.parameters()):
-            continue
-        scale = allreduce_gradients(tower, average=False)
-        tower.trunk.fused_adamw_step(lr, betas=betas, eps=eps, weight_decay=weight_decay, max_grad_norm=max_grad_norm, grad_scale=scale)
+        scale = allreduce_gradients(tower, average=False)  # (skips a frozen trunk)
+        _step_tower(tower, scale, lr, betas, eps, weight_decay, max_grad_norm)
     _step_logit_scale(logit_scale, lr, betas, eps)
     return loss.detach()
