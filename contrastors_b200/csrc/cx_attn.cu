@@ -108,3 +108,10 @@ extern "C" int cx_dq_finalize(const float* dq_acc, void* dqkv, int T, int H, int
   CX_LAUNCH_CHECK();
   return 0;
 }
+
+#ifdef CX_ATTN_TRACE
+// trace build only (tools/trace_attn_bwd.py): point the backward kernel's phase trace at a device buffer (nullptr: off)
+extern "C" __attribute__((visibility("default"))) int cx_attn_trace_set(long long* buf) {
+  return cudaMemcpyToSymbol(cx::g_bwd_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : 1;
+}
+#endif

@@ -46,6 +46,19 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __n
 // TMEM: S^T [0,128)  dP^T [128,256)  dV [256,320)  dK [320,384)  dQ [384,448);  P^T over S^T columns [0,32) + [64,96),
 // dS^T over dP^T columns [128,160) + [192,224) (each thread overwrites only columns it has already loaded itself).
 // 16 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 workers (two threads per key row, 64 query columns each), 12-15 dQ drain.
+// Optional phase trace (tools/trace_attn_bwd.py builds a separate library with -DCX_ATTN_TRACE; the product build compiles none
+// of it): one lane of one warp per role stamps clock64() at its phase boundaries, [block][role 5][tile 8][point 8].
+#ifdef CX_ATTN_TRACE
+__device__ long long* g_bwd_trace = nullptr;
+#define CX_TR(role, tile, pt)                                                                                          \
+  do {                                                                                                                 \
+    if (g_bwd_trace != nullptr && lane == 0 && (tile) < 8)                                                             \
+      g_bwd_trace[((((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 5 + (role)) * 8 + (tile)) * 8 + (pt)] = clock64(); \
+  } while (0)
+#else
+#define CX_TR(role, tile, pt) do { } while (0)
+#endif
+
 struct Bwd3Smem {
   static constexpr int kTile = 128 * kDh * 2;   // 16 KB
   static constexpr int kK = 0;                  // K_j  (A of S^T, B of dQ as MN-major)
@@ -87,6 +100,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   if (k0 >= len) return;
   const int nq = (len + 127) / 128;
   const float scale2 = softmax_scale * kLog2e;
+  if (warp == 0) CX_TR(4, 0, 0);
 
   const int col_q = (0 * H + head) * kDh, col_k = (1 * H + head) * kDh, col_v = (2 * H + head) * kDh;
   const int col_o = head * kDh;
@@ -117,6 +131,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (warp == 0) CX_TR(4, 0, 1);
 
   if (warp == 0) {
     for (int i = 1; i < nq; ++i) {  // K, V and the first query tile were issued during set-up
@@ -161,9 +176,11 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
           constexpr int kT = Bwd3Smem::kTile;
           const int ns = st ^ 1;
           const bool more = i + 1 < nq;
+          CX_TR(2, i, 0);
           mbar_wait(p_ready, i & 1);
           if (more) mbar_wait(&q_full[ns], ((i + 1) >> 1) & 1);
           tc_fence_after();
+          CX_TR(2, i, 1);
           if (elect_one()) {
             // dV += P^T dO_i: A = P^T from TMEM (16 queries = 8 columns per k-step; queries 64.. live at column 64),
             // B = dO_i MN-major (16 query rows = +2048 B per k-step)
@@ -179,9 +196,12 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
             }
           }
           __syncwarp();
+          CX_TR(2, i, 2);
           mbar_wait(ds_ready, i & 1);
+          CX_TR(2, i, 3);
           if (i > 0) mbar_wait(dq_free, (i - 1) & 1);
           tc_fence_after();
+          CX_TR(2, i, 4);
           if (elect_one()) {
             // dK += dS^T Q_i: A = dS^T from TMEM (over the dP^T columns), B = Q_i MN-major
 #pragma unroll
@@ -203,6 +223,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
             umma_commit(&q_empty[st]);
           }
           __syncwarp();
+          CX_TR(2, i, 5);
         }
       }
     }
@@ -229,7 +250,15 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     const float st_mul = (wt < 128) ? -kLog2e : -softmax_scale;
     const float st_pad = (wt < 128) ? -INFINITY : 0.f;
     float st_raw = (sq < len) ? st_src[sq] : 0.f;
+    const int tr_role = (warp == 4) ? 0 : (warp == 8 ? 1 : 5);  // trace: the first warp of each query half
+    (void)tr_role;
+#ifdef CX_ATTN_TRACE
+#define CX_TRW(i, pt) do { if (tr_role < 5) CX_TR(tr_role, i, pt); } while (0)
+#else
+#define CX_TRW(i, pt) do { } while (0)
+#endif
     for (int i = 0; i < nq; ++i) {
+      CX_TRW(i, 0);
       float* sb = stat + (i & 1) * 256;
       sb[wt] = (i * 128 + sq < len) ? st_raw * st_mul : st_pad;  // [0,128): -lse2 per query (-inf past the end => P = 0), [128,256): -delta*scale
       {
@@ -237,17 +266,20 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         st_raw = (nqr < len) ? st_src[nqr] : 0.f;
       }
       named_bar_sync(4, 256);
+      CX_TRW(i, 1);
       const float* nl = sb + grp * 64;        // -lse2 of this thread's 64 queries
       const float* nd = sb + 128 + grp * 64;  // -delta*scale
       // ---- X: P^T = exp2(S^T * scale2 - lse2[q]) -> bf16 pairs -> this thread's first 32 score columns
       uint32_t pp[32];
       mbar_wait(s_full, i & 1);
       tc_fence_after();
+      CX_TRW(i, 2);
       {
         uint32_t va[32], vb[32];
         tmem_ld_32x32(tmem_base + lane_base + grp * 64, va);
         tmem_ld_32x32(tmem_base + lane_base + grp * 64 + 32, vb);
         tmem_ld_wait();
+        CX_TRW(i, 3);
 #pragma unroll
         for (int t = 0; t < 16; t += 2) {
           const float4 c = *reinterpret_cast<const float4*>(nl + 2 * t);  // broadcast: every lane reads the same address
@@ -273,10 +305,12 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_ready);
+      CX_TRW(i, 4);
       // ---- Y: dS^T = P^T * (dP^T * scale - delta[q] * scale) -> TMEM (A of dK) and smem (A of dQ)
       mbar_wait(dp_full, i & 1);
       tc_fence_after();
       if (i > 0) mbar_wait_quiet(dq_full, (i - 1) & 1);  // dQ(i-1) has finished reading the dS buffer
+      CX_TRW(i, 5);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t vd[32];
@@ -299,15 +333,18 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         // over this thread's own dP^T columns [0,16) / [16,32): both lie inside chunk 0, which is in registers by now
         tmem_st_32x16(tmem_base + lane_base + 128 + grp * 64 + c * 16, w);
       }
+      CX_TRW(i, 6);
       fence_proxy_async_smem();
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(ds_ready);
+      CX_TRW(i, 7);
     }
     // dV (group 0) / dK (group 1) -> bf16 -> the (dead) dS buffer, one swizzled 128-byte row per thread; then each group
     // copies its tile out with row-contiguous 16-byte stores
     mbar_wait(acc_full, 0);
     tc_fence_after();
+    if (warp == 4) CX_TR(4, 0, 2);
     uint8_t* stg = smem + Bwd3Smem::kDS + grp * 16384;
     if (grp == 1 && rope_inv_freq != nullptr) {
       // dK with the transposed rotary embedding (the keys were rotated before the scores were formed): a thread owns one key
@@ -374,6 +411,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
               *reinterpret_cast<const uint4*>(stg + row * 128 + ((ch ^ (row & 7)) << 4));
       }
     }
+    if (warp == 4) CX_TR(4, 0, 3);
   } else if (warp >= 12) {
     // ---------------------------------------------------------------- dQ drain: one thread per query row, 64 columns
     const int ew = warp & 3;
@@ -383,16 +421,20 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     uint8_t* stage = smem + Bwd3Smem::kDQ;  // two [128 x 32] fp32 boxes (128-byte rows, 128B swizzle)
     for (int i = 0; i < nq; ++i) {
       const bool row_ok = i * 128 + r < len;
+      if (warp == 12) CX_TR(3, i, 0);
       mbar_wait(dq_full, i & 1);
       tc_fence_after();
+      if (warp == 12) CX_TR(3, i, 1);
       uint32_t va[32], vb[32];
       tmem_ld_32x32(tmem_base + lane_base + 384, va);
       tmem_ld_32x32(tmem_base + lane_base + 384 + 32, vb);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(dq_free);  // the next tile's dQ MMA may overwrite the columns
+      if (warp == 12) CX_TR(3, i, 2);
       if (etid == 0) tma_store_wait_read<0>();  // the previous reduce-add has finished reading the stage
       named_bar_sync(1, 128);
+      if (warp == 12) CX_TR(3, i, 3);
       uint8_t* d0 = stage + r * 128;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -408,12 +450,15 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         tma_reduce_add_2d(&tmDQ, stage + 16384, col_o + 32, seq_begin + i * 128);
         tma_store_commit();
       }
+      if (warp == 12) CX_TR(3, i, 4);
     }
     if (etid == 0) tma_store_wait_read<0>();
+    if (warp == 12) CX_TR(4, 0, 5);
   }
 
   tc_fence_before();
   __syncthreads();
+  if (warp == 0) CX_TR(4, 0, 4);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);

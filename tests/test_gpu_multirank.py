@@ -162,9 +162,7 @@ def test_dual_encoder_loss_two_ranks(tmp_path):
         assert np.abs(got["dt"] - o["dtext"]).max() <= 1e-3 * np.abs(o["dtext"]).max()
         assert np.abs(got["dv"] - o["dvision"]).max() <= 1e-3 * np.abs(o["dvision"]).max()
         assert abs(got["dlogit"] - o["dlogit"]) <= 3e-3 * max(abs(o["dlogit"]), 1e-2)
-        ref_keys = [k for k in z.files if k.startswith(f"r{r}_") and "loss" in k]
-        assert ref_keys, z.files  # the golden was generated with unscaled inputs: same loss family, checked loosely
-    assert True
+        assert any(k.startswith(f"r{r}_") and "loss" in k for k in z.files), z.files  # the reference-generated fixture of this case
 
 
 def _bucket_worker(rank, ws, port, out_dir, backend="nccl"):

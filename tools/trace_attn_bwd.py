@@ -1,0 +1,111 @@
+"""Phase trace of the attention backward kernel (clock64 stamps per role and query tile).
+
+    python tools/trace_attn_bwd.py --build     # here, no GPU: nvcc -DCX_ATTN_TRACE -> tools/_trace/libcx_trace.so (travels with gpurun)
+    python tools/trace_attn_bwd.py             # on the B200: run once with the trace on, print the per-phase medians
+
+The trace library is a separate build of csrc/cx_attn.cu; the product library contains none of the trace code.
+Roles: 0 / 1 = first worker warp of query half 0 / 1, 2 = MMA warp, 3 = first dQ-drain warp, 4 = block-level stamps.
+"""
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "tools", "_trace")
+LIB = os.path.join(OUT, "libcx_trace.so")
+
+
+def build():
+    from contrastors_b200 import build as b
+    b.build()
+    os.makedirs(OUT, exist_ok=True)
+    obj = os.path.join(OUT, "cx_attn_trace.o")
+    subprocess.run([b.NVCC, *b.FLAGS, "-DCX_ATTN_TRACE", "-c", os.path.join(b.CSRC, "cx_attn.cu"), "-o", obj], check=True)
+    others = [os.path.join(b.OBJ, f[:-3] + ".o") for f in b._sources() if f != "cx_attn.cu"]
+    subprocess.run([b.NVCC, "-shared", "-o", LIB, obj, *others, "-gencode", "arch=compute_100a,code=sm_100a"], check=True)
+    print(LIB)
+
+
+def main():
+    import numpy as np
+    import torch
+    from contrastors_b200 import ops
+    lib = C.CDLL(LIB)
+    lib.cx_attn_trace_set.argtypes = [C.c_void_p]
+    lib.cx_attn_bwd.argtypes = [C.c_void_p] * 8 + [C.c_int] * 5 + [C.c_float, C.c_void_p, C.c_void_p]
+    lib.cx_last_error.restype = C.c_char_p
+    nseq, S, H, Dh = 64, 512, 12, 64
+    T = nseq * S
+    torch.manual_seed(0)
+    qkv = torch.randn(T, 3 * H * Dh, device="cuda").to(torch.bfloat16)
+    dout = torch.randn(T, H * Dh, device="cuda").to(torch.bfloat16)
+    cu = torch.arange(0, T + 1, S, dtype=torch.int32, device="cuda")
+    scale = 1.0 / math.sqrt(Dh)
+    out, lse = ops.attn_fwd(qkv, cu, S, H, Dh, scale)
+    ref = ops.attn_bwd(qkv, out, dout, lse, cu, S, H, Dh, scale)
+    nblk = (S // 128) * H * nseq
+    trace = torch.zeros(nblk * 5 * 8 * 8, dtype=torch.int64, device="cuda")
+    dqkv = torch.empty_like(qkv)
+    dq_acc = torch.empty(T, H * Dh, device="cuda", dtype=torch.float32)
+    delta = torch.empty(H, T, device="cuda", dtype=torch.float32)
+
+    def run():
+        rc = lib.cx_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), cu.data_ptr(), dqkv.data_ptr(),
+                             dq_acc.data_ptr(), delta.data_ptr(), T, nseq, S, H, Dh, scale, None,
+                             torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, lib.cx_last_error()
+    run()  # warm, trace off
+    torch.cuda.synchronize()
+    assert lib.cx_attn_trace_set(trace.data_ptr()) == 0
+    run()
+    torch.cuda.synchronize()
+    lib.cx_attn_trace_set(None)
+    # the drained dk/dv slots match the product library's (dq is finalized by a separate kernel, not compared here)
+    HD = H * Dh
+    assert torch.equal(dqkv[:, HD:], ref[:, HD:]), "trace build disagrees with the product build"
+    t = trace.cpu().numpy().reshape(nblk, 5, 8, 8)
+    nq = S // 128
+    res = {}
+
+    def med(x):
+        return float(np.median(x))
+    t0 = t[:, 4, 0, 0]
+    res["block_total"] = med(t[:, 4, 0, 4] - t0)
+    res["setup_to_sync"] = med(t[:, 4, 0, 1] - t0)
+    res["acc_full_at"] = med(t[:, 4, 0, 2] - t0)
+    res["worker_epilogue"] = med(t[:, 4, 0, 3] - t[:, 4, 0, 2])
+    res["drain_done_at"] = med(t[:, 4, 0, 5] - t0)
+    names_w = ["top", "stat_bar", "s_full", "x_loaded", "x_done", "dp_dq_full", "y_done", "ds_arrived"]
+    for role in (0, 1):
+        for i in range(nq):
+            prev = t[:, role, i, 0]
+            row = {"start_at": med(prev - t0)}
+            for p in range(1, 8):
+                row[names_w[p]] = med(t[:, role, i, p] - t[:, role, i, p - 1])
+            row["tile_total"] = med(t[:, role, i, 7] - t[:, role, i, 0])
+            res[f"worker{role}_tile{i}"] = row
+    names_m = ["top", "p_ready", "issue1", "ds_ready", "dq_free", "issue2"]
+    for i in range(nq):
+        row = {"start_at": med(t[:, 2, i, 0] - t0)}
+        for p in range(1, 6):
+            row[names_m[p]] = med(t[:, 2, i, p] - t[:, 2, i, p - 1])
+        res[f"mma_tile{i}"] = row
+    names_d = ["top", "dq_full", "loaded", "stage_free_bar", "stored"]
+    for i in range(nq):
+        row = {"start_at": med(t[:, 3, i, 0] - t0)}
+        for p in range(1, 5):
+            row[names_d[p]] = med(t[:, 3, i, p] - t[:, 3, i, p - 1])
+        res[f"drain_tile{i}"] = row
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "attn_bwd_trace.json"), "w"), indent=1)
+    np.save(os.path.join(ROOT, "gpurun_out", "attn_bwd_trace_first296.npy"), t[:296])
+    for k, v in res.items():
+        print(k, v)
+
+
+if __name__ == "__main__":
+    build() if "--build" in sys.argv else main()
