@@ -91,10 +91,17 @@ extern "C" int cx_attn_bwd(const void* qkv, const void* out, const void* dout, c
   rc = make_tmap_2d(&tmDQ, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dq_acc, (uint64_t)H * Dh, (uint64_t)T, (uint64_t)H * Dh * 4, 32,
                     128, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  CX_SET_SMEM_ONCE(attn_bwd3_kernel, Bwd3Smem::kTotal);
   dim3 grid((max_seqlen + 127) / 128, H, nseq);
-  attn_bwd3_kernel<<<grid, kBwd2Threads, Bwd3Smem::kTotal, stream>>>(tmQKV, tmDO, tmDQ, cu_seqlens, lse, delta,
-                                                                    (__nv_bfloat16*)dqkv, T, H, softmax_scale, dk_rope_inv_freq);
+  static const bool use_bwd3 = [] { const char* e = getenv("CX_ATTN_BWD3"); return e && *e == '1'; }();  // A/B during bring-up
+  if (use_bwd3) {
+    CX_SET_SMEM_ONCE(attn_bwd3_kernel, Bwd3Smem::kTotal);
+    attn_bwd3_kernel<<<grid, kBwd2Threads, Bwd3Smem::kTotal, stream>>>(tmQKV, tmDO, tmDQ, cu_seqlens, lse, delta,
+                                                                      (__nv_bfloat16*)dqkv, T, H, softmax_scale, dk_rope_inv_freq);
+  } else {
+    CX_SET_SMEM_ONCE(attn_bwd4_kernel, Bwd4Smem::kTotal);
+    attn_bwd4_kernel<<<grid, kBwd4Threads, Bwd4Smem::kTotal, stream>>>(tmQKV, tmDO, tmDQ, cu_seqlens, lse, delta,
+                                                                      (__nv_bfloat16*)dqkv, T, H, softmax_scale, dk_rope_inv_freq);
+  }
   CX_LAUNCH_CHECK();
   return 0;
 }

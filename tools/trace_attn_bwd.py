@@ -4,7 +4,7 @@
     python tools/trace_attn_bwd.py             # on the B200: run once with the trace on, print the per-phase medians
 
 The trace library is a separate build of csrc/cx_attn.cu; the product library contains none of the trace code.
-Roles: 0 / 1 = first worker warp of query half 0 / 1, 2 = MMA warp, 3 = first dQ-drain warp, 4 = block-level stamps.
+CX_ATTN_BWD3=1 traces the previous generation.  Roles: 0 / 1 = first worker warp of query half 0 / 1 (bwd4: quarters 0 / 2), 2 = MMA warp, 3 = first dQ-drain warp, 4 = block-level stamps.
 """
 import ctypes as C
 import json
@@ -19,22 +19,32 @@ OUT = os.path.join(ROOT, "tools", "_trace")
 LIB = os.path.join(OUT, "libcx_trace.so")
 
 
+VARIANTS = {"": [], "nostat": ["-DCX_EXP_NOSTAT"], "nodsstore": ["-DCX_EXP_NODSSTORE"], "noexp": ["-DCX_EXP_NOEXP"],
+            "nodrain": ["-DCX_EXP_NODRAIN"], "nodqmma": ["-DCX_EXP_NODQMMA", "-DCX_EXP_NODRAIN"],
+            "nostat_noexp": ["-DCX_EXP_NOSTAT", "-DCX_EXP_NOEXP"],
+            "all_off": ["-DCX_EXP_NOSTAT", "-DCX_EXP_NOEXP", "-DCX_EXP_NODSSTORE", "-DCX_EXP_NODRAIN"]}
+
+
 def build():
+    """The plain trace library plus ablation variants (wrong results on purpose: each removes one consumer of a shared resource)."""
     from contrastors_b200 import build as b
     b.build()
     os.makedirs(OUT, exist_ok=True)
-    obj = os.path.join(OUT, "cx_attn_trace.o")
-    subprocess.run([b.NVCC, *b.FLAGS, "-DCX_ATTN_TRACE", "-c", os.path.join(b.CSRC, "cx_attn.cu"), "-o", obj], check=True)
     others = [os.path.join(b.OBJ, f[:-3] + ".o") for f in b._sources() if f != "cx_attn.cu"]
-    subprocess.run([b.NVCC, "-shared", "-o", LIB, obj, *others, "-gencode", "arch=compute_100a,code=sm_100a"], check=True)
-    print(LIB)
+    for name, flags in VARIANTS.items():
+        obj = os.path.join(OUT, f"cx_attn_trace_{name}.o")
+        lib = LIB if not name else LIB.replace(".so", f"_{name}.so")
+        subprocess.run([b.NVCC, *b.FLAGS, "-DCX_ATTN_TRACE", *flags, "-c", os.path.join(b.CSRC, "cx_attn.cu"), "-o", obj], check=True)
+        subprocess.run([b.NVCC, "-shared", "-o", lib, obj, *others, "-gencode", "arch=compute_100a,code=sm_100a"], check=True)
+        print(lib)
 
 
 def main():
     import numpy as np
     import torch
     from contrastors_b200 import ops
-    lib = C.CDLL(LIB)
+    variant = os.environ.get("CX_TRACE_VARIANT", "")
+    lib = C.CDLL(LIB if not variant else LIB.replace(".so", f"_{variant}.so"))
     lib.cx_attn_trace_set.argtypes = [C.c_void_p]
     lib.cx_attn_bwd.argtypes = [C.c_void_p] * 8 + [C.c_int] * 5 + [C.c_float, C.c_void_p, C.c_void_p]
     lib.cx_last_error.restype = C.c_char_p
@@ -64,9 +74,18 @@ def main():
     run()
     torch.cuda.synchronize()
     lib.cx_attn_trace_set(None)
+    for _ in range(30):  # let the clocks ramp before timing
+        run()
+    evs = []
+    for _ in range(11):
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); run(); b_.record(); torch.cuda.synchronize()
+        evs.append(a.elapsed_time(b_) * 1e3)
+    print("variant", variant or "plain", "cx_attn_bwd (delta + kernel) us, trace off:", sorted(evs)[5])
     # the drained dk/dv slots match the product library's (dq is finalized by a separate kernel, not compared here)
     HD = H * Dh
-    assert torch.equal(dqkv[:, HD:], ref[:, HD:]), "trace build disagrees with the product build"
+    err = (dqkv[:, HD:].float() - ref[:, HD:].float()).abs().max().item() / ref[:, HD:].float().abs().max().item()
+    assert variant or err < 2e-2, f"trace build disagrees with the product build: {err}"
     t = trace.cpu().numpy().reshape(nblk, 5, 8, 8)
     nq = S // 128
     res = {}
@@ -79,7 +98,10 @@ def main():
     res["acc_full_at"] = med(t[:, 4, 0, 2] - t0)
     res["worker_epilogue"] = med(t[:, 4, 0, 3] - t[:, 4, 0, 2])
     res["drain_done_at"] = med(t[:, 4, 0, 5] - t0)
-    names_w = ["top", "stat_bar", "s_full", "x_loaded", "x_done", "dp_dq_full", "y_done", "ds_arrived"]
+    if os.environ.get("CX_ATTN_BWD3") == "1":
+        names_w = ["top", "stat_bar", "s_full", "x_loaded", "x_done", "dp_dq_full", "y_done", "ds_arrived"]
+    else:  # attn_bwd4_kernel
+        names_w = ["top", "s_full", "x_loaded", "x_done", "dp_dq_full", "y_loaded", "y_done", "ds_arrived"]
     for role in (0, 1):
         for i in range(nq):
             prev = t[:, role, i, 0]
@@ -91,7 +113,12 @@ def main():
     names_m = ["top", "p_ready", "issue1", "ds_ready", "dq_free", "issue2"]
     for i in range(nq):
         row = {"start_at": med(t[:, 2, i, 0] - t0)}
-        for p in range(1, 6):
+        if t[:, 2, i, 6].any():  # bwd4 stamps the Q/dO stage wait separately (point 6, between top and p_ready)
+            row["q_full"] = med(np.where(t[:, 2, i, 6] > 0, t[:, 2, i, 6] - t[:, 2, i, 0], 0))
+            row["p_ready"] = med(np.where(t[:, 2, i, 6] > 0, t[:, 2, i, 1] - t[:, 2, i, 6], t[:, 2, i, 1] - t[:, 2, i, 0]))
+        else:
+            row["p_ready"] = med(t[:, 2, i, 1] - t[:, 2, i, 0])
+        for p in range(2, 6):
             row[names_m[p]] = med(t[:, 2, i, p] - t[:, 2, i, p - 1])
         res[f"mma_tile{i}"] = row
     names_d = ["top", "dq_full", "loaded", "stage_free_bar", "stored"]
