@@ -491,8 +491,10 @@ struct Bwd4Smem {
   static constexpr int kDO = kQ + kStages * kTile;   // kStages x dO_i (B of dP^T, B of dV as MN-major)
   static constexpr int kDS = kDO + kStages * kTile;  // dS^T [128 keys x 128 q] bf16: 2 blocks (q halves) x 128 rows x 128 B
   static constexpr int kDQ = kDS + 32768;       // fp32 staging for the dQ reduce-add: 2 x [128 x 32] (128 B rows)
-  static constexpr int kStat = kDQ + 2 * 16384; // 3 buffers x { -lse*log2e [128], -delta*scale [128] } fp32
-  static constexpr int kBars = kStat + 3072;
+  // auxiliary K-major operand tile [128 rows x 64 bf16]: k-step 0 (columns 0..15) = ones (A), k-step 1 = -lse/scale of the query
+  // tile split into three bf16 terms (B of S^T), k-step 2 = -delta split the same way (B of dP^T); k-step 3 unused
+  static constexpr int kAux = kDQ + 2 * 16384;
+  static constexpr int kBars = kAux + kTile;
   static constexpr int kTotal = kBars + 256 + 1024;
 };
 
@@ -514,7 +516,8 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   uint64_t* dq_full = bars + 11;   // dQ(i) partial in TMEM; also: dQ(i) has finished reading dS(i) from smem
   uint64_t* dq_free = bars + 12;   // dQ TMEM columns drained (128 arrivals)
   uint64_t* acc_full = bars + 13;  // dK / dV complete
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* aux_init = bars + 14;  // the auxiliary operand tile holds ones and tile 0's statistics (512 arrivals)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   CX_TR_INIT();
@@ -542,6 +545,7 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     mbar_init(dq_full, 1);
     mbar_init(dq_free, 128);
     mbar_init(acc_full, 1);
+    mbar_init(aux_init, 512);
     fence_barrier_init();
     mbar_arrive_expect_tx(kv_full, 2 * Bwd4Smem::kTile);
     tma_load_2d(smem + Bwd4Smem::kK, &tmQKV, kv_full, col_k, seq_begin + k0);
@@ -581,15 +585,22 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     const uint64_t qm = make_smem_desc_sw128(smem_u32(smem + Bwd4Smem::kQ), 8192, 1024);     // Q_i  MN-major (B of dK)
     const uint64_t dom = make_smem_desc_sw128(smem_u32(smem + Bwd4Smem::kDO), 8192, 1024);   // dO_i MN-major (B of dV)
     const uint64_t dsm = make_smem_desc_sw128(smem_u32(smem + Bwd4Smem::kDS), 16384, 1024);  // dS^T MN-major (A of dQ)
+    // fifth k-step of S^T and dP^T: ones [128 keys x 16] times the statistics [128 queries x 16] adds -lse/scale resp. -delta
+    // of each query column to the whole column, inside the accumulation (the workers then only scale)
+    const uint64_t xd = make_smem_desc_sw128(smem_u32(smem + Bwd4Smem::kAux), 0, 1024);
+    const uint64_t x_ones = xd, x_lse = xd + (32 >> 4), x_delta = xd + (64 >> 4);
     mbar_wait(kv_full, 0);
     mbar_wait(&q_full[0], 0);
+    mbar_wait(aux_init, 0);
     tc_fence_after();
     if (elect_one()) {
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) umma_f16_ss(tmem_base + 0, kd + ((kk * 32) >> 4), qd + ((kk * 32) >> 4), id_kk, kk > 0 ? 1u : 0u);
+      umma_f16_ss(tmem_base + 0, x_ones, x_lse, id_kk, 1u);
       umma_commit(s_full);
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) umma_f16_ss(tmem_base + 128, vd + ((kk * 32) >> 4), dod + ((kk * 32) >> 4), id_kk, kk > 0 ? 1u : 0u);
+      umma_f16_ss(tmem_base + 128, x_ones, x_delta, id_kk, 1u);
       umma_commit(dp_full);
     }
     __syncwarp();
@@ -614,6 +625,7 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             umma_f16_ss(tmem_base + 0, kd + ((kk * 32) >> 4), qd + ((ns * kT + kk * 32) >> 4), id_kk, kk > 0 ? 1u : 0u);
+          umma_f16_ss(tmem_base + 0, x_ones, x_lse, id_kk, 1u);
           umma_commit(s_full);
         }
       }
@@ -634,15 +646,14 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             umma_f16_ss(tmem_base + 128, vd + ((kk * 32) >> 4), dod + ((ns * kT + kk * 32) >> 4), id_kk, kk > 0 ? 1u : 0u);
+          umma_f16_ss(tmem_base + 128, x_ones, x_delta, id_kk, 1u);
           umma_commit(dp_full);
         }
         // dQ_i(partial) = dS K_j: A = dS^T in smem read MN-major (16 keys = +2048 B per k-step, the two 64-query atoms
         // 16 KB apart), B = K_j MN-major
-#ifndef CX_EXP_NODQMMA
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
           umma_f16_ss(tmem_base + 384, dsm + ((kk * 2048) >> 4), km + ((kk * 2048) >> 4), id_mm, kk > 0 ? 1u : 0u);
-#endif
         umma_commit(dq_full);
         umma_commit(&q_empty[st]);
       }
@@ -662,41 +673,52 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     // this thread's 64 bytes of its dS^T row: block = query half, chunks (qq & 1) * 4 .. + 3 of the 128-byte row
     uint8_t* dd = smem + Bwd4Smem::kDS + (qq >> 1) * 16384 + r * 128;
     const int ch0 = (qq & 1) * 4;
-    float* stat = reinterpret_cast<float*>(smem + Bwd4Smem::kStat);
     const float2 sc2 = make_float2(scale2, scale2), ss2 = make_float2(softmax_scale, softmax_scale);
-    // threads 0..255 publish one column statistic per tile: wt < 128: -lse * log2(e) of query wt; else -delta * scale of query
-    // wt - 128.  The raw value is loaded a whole tile before it is converted and published, and published a tile before it is read.
-    const bool pub = wt < 256;
+    // The per-query statistics enter through the MMA (see the auxiliary operand tile): row `sq` of the tile holds, as three bf16
+    // terms each, -lse/scale (k-step 1) and -delta (k-step 2) of query sq of the CURRENT tile.  Quarter 1's threads rewrite the lse
+    // terms for tile i+1 once S^T(i) has completed (behind the s_full(i) wait, before their p_ready(i) arrival, which S^T(i+1)
+    // waits for); quarter 2's threads rewrite the delta terms once dP^T(i) has completed (behind dp_full(i), before ds_ready(i),
+    // which dP^T(i+1) waits for).  The raw values are loaded from global memory a tile earlier still.
     const int sq = wt & 127;
-    const float* st_src = (wt < 128) ? lse + (size_t)head * T + seq_begin : delta + (size_t)head * T + seq_begin;
-    const float st_mul = (wt < 128) ? -kLog2e : -softmax_scale;
-    const float st_pad = (wt < 128) ? -INFINITY : 0.f;  // -inf => P = 0 for queries past the end
+    uint8_t* aux_row = smem + Bwd4Smem::kAux + sq * 128;
+    const float inv_scale = 1.f / softmax_scale;
+    const float* st_src = (qq == 1 ? lse : delta) + (size_t)head * T + seq_begin;
+    auto stat_terms = [&](float raw, bool ok) -> uint4 {  // value = hi + mid + lo exactly to 2^-24 relative
+      const float v = (qq == 1) ? (ok ? -raw * inv_scale : -1e30f) : (ok ? -raw : 0.f);  // -1e30 => P = 0 for queries past the end
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      const float r1 = v - __bfloat162float(h);
+      const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+      const __nv_bfloat16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+      return make_uint4((uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(m) << 16), (uint32_t)__bfloat16_as_ushort(l), 0u, 0u);
+    };
     float st_raw = 0.f;
-    if (pub) {
-      stat[wt] = (sq < len) ? st_src[sq] * st_mul : st_pad;
-      st_raw = (128 + sq < len) ? st_src[128 + sq] : 0.f;
+    {
+      // quarter qq initialises logical 16-byte chunks 2*qq and 2*qq+1 of row sq: k-step qq's 16 columns
+      uint4 first = make_uint4(0u, 0u, 0u, 0u);
+      if (qq == 0) first = make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u);  // ones in columns 0..2
+      if (qq == 1 || qq == 2) {
+        first = stat_terms((sq < len) ? st_src[sq] : 0.f, sq < len);
+        st_raw = (128 + sq < len) ? st_src[128 + sq] : 0.f;
+      }
+      *reinterpret_cast<uint4*>(aux_row + (((2 * qq) ^ (sq & 7)) << 4)) = first;
+      *reinterpret_cast<uint4*>(aux_row + (((2 * qq + 1) ^ (sq & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+      fence_proxy_async_smem();
+      mbar_arrive(aux_init);
     }
-    named_bar_sync(4, 512);
     const int tr_role = (warp == 4) ? 0 : (warp == 12 ? 1 : 5);  // trace: the first warp of query quarters 0 and 2
     (void)tr_role;
-    int sb_cur = 0;  // statistics buffer of tile i (i mod 3)
     for (int i = 0; i < nq; ++i) {
       CX_TRW(i, 0);
-      const float* sb = stat + sb_cur * 256;
-      const int sb_next = (sb_cur == 2) ? 0 : sb_cur + 1;
-      const float* nl = sb + qq * 32;        // -lse2 of this thread's 32 queries
-      const float* nd = sb + 128 + qq * 32;  // -delta*scale
-      // ---- X: P^T = exp2(S^T * scale2 - lse2[q]) -> bf16 pairs -> this thread's first 16 score columns
+      // ---- X: P^T = exp2((S^T - lse/scale) * scale2) -> bf16 pairs -> this thread's first 16 score columns
       uint32_t pp[16];
       mbar_wait(s_full, i & 1);
       tc_fence_after();
       CX_TRW(i, 1);
-      // s_full(i) completed => every worker finished tile i-1's X, so nobody reads buffer (i+1) mod 3 = (i-2) mod 3 any more;
-      // the readers of tile i+1 wait on s_full(i+1), which the MMA warp commits after all p_ready(i) arrivals below.
-      if (pub && i + 1 < nq) {
-        stat[sb_next * 256 + wt] = ((i + 1) * 128 + sq < len) ? st_raw * st_mul : st_pad;
+      if (qq == 1 && i + 1 < nq) {
+        *reinterpret_cast<uint4*>(aux_row + ((2 ^ (sq & 7)) << 4)) = stat_terms(st_raw, (i + 1) * 128 + sq < len);
         const int nqr = (i + 2) * 128 + sq;
         st_raw = (nqr < len) ? st_src[nqr] : 0.f;
+        fence_proxy_async_smem();
       }
       {
         uint32_t va[32];
@@ -705,18 +727,11 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         CX_TRW(i, 2);
 #pragma unroll
         for (int t = 0; t < 16; t += 2) {
-#ifdef CX_EXP_NOSTAT
-          const float4 c = make_float4(-8.f, -8.f, -8.f, -8.f);
-#else
-          const float4 c = *reinterpret_cast<const float4*>(nl + 2 * t);  // broadcast: every lane reads the same address
-#endif
-          float2 xa = ffma2(make_float2(__uint_as_float(va[2 * t]), __uint_as_float(va[2 * t + 1])), sc2, make_float2(c.x, c.y));
-          float2 xb = ffma2(make_float2(__uint_as_float(va[2 * t + 2]), __uint_as_float(va[2 * t + 3])), sc2, make_float2(c.z, c.w));
-#ifndef CX_EXP_NOEXP
+          float2 xa = fmul2(make_float2(__uint_as_float(va[2 * t]), __uint_as_float(va[2 * t + 1])), sc2);
+          float2 xb = fmul2(make_float2(__uint_as_float(va[2 * t + 2]), __uint_as_float(va[2 * t + 3])), sc2);
           xa = make_float2(fast_exp2(xa.x), fast_exp2(xa.y));
           if (kBwd4Poly == 8 || (kBwd4Poly == 4 && ((t >> 1) & 1))) xb = exp2_poly2(xb);
           else xb = make_float2(fast_exp2(xb.x), fast_exp2(xb.y));
-#endif
           pp[t] = pack_bf16x2(xa.x, xa.y);
           pp[t + 1] = pack_bf16x2(xb.x, xb.y);
         }
@@ -730,9 +745,14 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       tc_fence_before();
       mbar_arrive(p_ready);
       CX_TRW(i, 3);
-      // ---- Y: dS^T = P^T * (dP^T * scale - delta[q] * scale) -> TMEM (A of dK) and smem (A of dQ)
+      // ---- Y: dS^T = P^T * (dP^T - delta[q]) * scale -> TMEM (A of dK) and smem (A of dQ)
       mbar_wait(dp_full, i & 1);
       tc_fence_after();
+      if (qq == 2 && i + 1 < nq) {  // made visible to the MMA by the proxy fence ahead of the ds_ready arrival below
+        *reinterpret_cast<uint4*>(aux_row + ((4 ^ (sq & 7)) << 4)) = stat_terms(st_raw, (i + 1) * 128 + sq < len);
+        const int nqr = (i + 2) * 128 + sq;
+        st_raw = (nqr < len) ? st_src[nqr] : 0.f;
+      }
       if (i > 0) mbar_wait_quiet(dq_full, (i - 1) & 1);  // dQ(i-1) has finished reading the dS buffer
       CX_TRW(i, 4);
       {
@@ -743,23 +763,16 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         uint32_t w[16];
 #pragma unroll
         for (int t = 0; t < 16; t += 2) {
-#ifdef CX_EXP_NOSTAT
-          const float4 dc = make_float4(0.1f, 0.1f, 0.1f, 0.1f);
-#else
-          const float4 dc = *reinterpret_cast<const float4*>(nd + 2 * t);
-#endif
-          const float2 ga = ffma2(make_float2(__uint_as_float(vd[2 * t]), __uint_as_float(vd[2 * t + 1])), ss2, make_float2(dc.x, dc.y));
-          const float2 gb = ffma2(make_float2(__uint_as_float(vd[2 * t + 2]), __uint_as_float(vd[2 * t + 3])), ss2, make_float2(dc.z, dc.w));
+          const float2 ga = fmul2(make_float2(__uint_as_float(vd[2 * t]), __uint_as_float(vd[2 * t + 1])), ss2);
+          const float2 gb = fmul2(make_float2(__uint_as_float(vd[2 * t + 2]), __uint_as_float(vd[2 * t + 3])), ss2);
           const float2 da = fmul2(unpack_bf16x2(pp[t]), ga);
           const float2 db = fmul2(unpack_bf16x2(pp[t + 1]), gb);
           w[t] = pack_bf16x2(da.x, da.y);
           w[t + 1] = pack_bf16x2(db.x, db.y);
         }
-#ifndef CX_EXP_NODSSTORE
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           *reinterpret_cast<uint4*>(dd + (((ch0 + q) ^ (r & 7)) << 4)) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-#endif
         tmem_st_32x16(tmem_base + lane_base + 128 + qq * 32, w);  // over this thread's own (already loaded) dP^T columns
       }
       CX_TRW(i, 6);
@@ -768,7 +781,6 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       tc_fence_before();
       mbar_arrive(ds_ready);
       CX_TRW(i, 7);
-      sb_cur = sb_next;
     }
     // dV (quarters 0, 1) / dK (quarters 2, 3) -> bf16 -> the (dead) dS buffer, half a swizzled 128-byte row per thread; then each
     // group of 256 threads copies its tile out with row-contiguous 16-byte stores
@@ -864,7 +876,6 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       named_bar_sync(1, 128);
       if (warp == 20) CX_TR(3, i, 3);
       uint8_t* d0 = stage + r * 128;
-#ifndef CX_EXP_NODRAIN
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         *reinterpret_cast<uint4*>(d0 + ((q ^ (r & 7)) << 4)) =
@@ -879,7 +890,6 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         tma_reduce_add_2d(&tmDQ, stage + 16384, col_o + 32, seq_begin + i * 128);
         tma_store_commit();
       }
-#endif
       if (warp == 20) CX_TR(3, i, 4);
     }
     if (etid == 0) tma_store_wait_read<0>();

@@ -4,7 +4,7 @@
     python tools/trace_attn_bwd.py             # on the B200: run once with the trace on, print the per-phase medians
 
 The trace library is a separate build of csrc/cx_attn.cu; the product library contains none of the trace code.
-CX_ATTN_BWD3=1 traces the previous generation.  Roles: 0 / 1 = first worker warp of query half 0 / 1 (bwd4: quarters 0 / 2), 2 = MMA warp, 3 = first dQ-drain warp, 4 = block-level stamps.
+CX_ATTN_BWD3=1 traces the previous generation.  Roles: 0 / 1 = first worker warp of query quarters 0 / 2 (bwd3: of query halves 0 / 1), 2 = MMA warp, 3 = first dQ-drain warp, 4 = block-level stamps.
 """
 import ctypes as C
 import json
@@ -19,10 +19,7 @@ OUT = os.path.join(ROOT, "tools", "_trace")
 LIB = os.path.join(OUT, "libcx_trace.so")
 
 
-VARIANTS = {"": [], "nostat": ["-DCX_EXP_NOSTAT"], "nodsstore": ["-DCX_EXP_NODSSTORE"], "noexp": ["-DCX_EXP_NOEXP"],
-            "nodrain": ["-DCX_EXP_NODRAIN"], "nodqmma": ["-DCX_EXP_NODQMMA", "-DCX_EXP_NODRAIN"],
-            "nostat_noexp": ["-DCX_EXP_NOSTAT", "-DCX_EXP_NOEXP"],
-            "all_off": ["-DCX_EXP_NOSTAT", "-DCX_EXP_NOEXP", "-DCX_EXP_NODSSTORE", "-DCX_EXP_NODRAIN"]}
+VARIANTS = {"": []}   # name -> extra -D flags (ablation builds go here)
 
 
 def build():
@@ -98,35 +95,24 @@ def main():
     res["acc_full_at"] = med(t[:, 4, 0, 2] - t0)
     res["worker_epilogue"] = med(t[:, 4, 0, 3] - t[:, 4, 0, 2])
     res["drain_done_at"] = med(t[:, 4, 0, 5] - t0)
-    if os.environ.get("CX_ATTN_BWD3") == "1":
-        names_w = ["top", "stat_bar", "s_full", "x_loaded", "x_done", "dp_dq_full", "y_done", "ds_arrived"]
-    else:  # attn_bwd4_kernel
-        names_w = ["top", "s_full", "x_loaded", "x_done", "dp_dq_full", "y_loaded", "y_done", "ds_arrived"]
-    for role in (0, 1):
+    bwd3 = os.environ.get("CX_ATTN_BWD3") == "1"
+    if bwd3:   # role 0 / 1: first worker warp of each query half (X then Y in the same warp)
+        names = {0: ["top", "stat_bar", "s_full", "x_loaded", "x_done", "dp_dq_full", "y_done", "ds_arrived"],
+                 2: ["top", "p_ready", "issue1", "ds_ready", "dq_free", "issue2"]}
+        names[1] = names[0]
+    else:      # attn_bwd4_kernel: role 0 / 1 = first worker warp of query quarters 0 / 2
+        names = {0: ["top", "s_full", "x_loaded", "x_done", "dp_dq_full", "y_loaded", "y_done", "ds_arrived"],
+                 2: ["top", "p_ready", "issue1", "ds_ready", "dq_free", "issue2"]}
+        names[1] = names[0]
+    names[3] = ["top", "dq_full", "loaded", "stage_free_bar", "stored"]
+    for role, label in ((0, "worker0"), (1, "worker1"), (2, "mma"), (3, "drain")):
+        nm = names[role]
         for i in range(nq):
-            prev = t[:, role, i, 0]
-            row = {"start_at": med(prev - t0)}
-            for p in range(1, 8):
-                row[names_w[p]] = med(t[:, role, i, p] - t[:, role, i, p - 1])
-            row["tile_total"] = med(t[:, role, i, 7] - t[:, role, i, 0])
-            res[f"worker{role}_tile{i}"] = row
-    names_m = ["top", "p_ready", "issue1", "ds_ready", "dq_free", "issue2"]
-    for i in range(nq):
-        row = {"start_at": med(t[:, 2, i, 0] - t0)}
-        if t[:, 2, i, 6].any():  # bwd4 stamps the Q/dO stage wait separately (point 6, between top and p_ready)
-            row["q_full"] = med(np.where(t[:, 2, i, 6] > 0, t[:, 2, i, 6] - t[:, 2, i, 0], 0))
-            row["p_ready"] = med(np.where(t[:, 2, i, 6] > 0, t[:, 2, i, 1] - t[:, 2, i, 6], t[:, 2, i, 1] - t[:, 2, i, 0]))
-        else:
-            row["p_ready"] = med(t[:, 2, i, 1] - t[:, 2, i, 0])
-        for p in range(2, 6):
-            row[names_m[p]] = med(t[:, 2, i, p] - t[:, 2, i, p - 1])
-        res[f"mma_tile{i}"] = row
-    names_d = ["top", "dq_full", "loaded", "stage_free_bar", "stored"]
-    for i in range(nq):
-        row = {"start_at": med(t[:, 3, i, 0] - t0)}
-        for p in range(1, 5):
-            row[names_d[p]] = med(t[:, 3, i, p] - t[:, 3, i, p - 1])
-        res[f"drain_tile{i}"] = row
+            row = {"start_at": med(t[:, role, i, 0] - t0)}
+            for p in range(1, len(nm)):
+                row[nm[p]] = med(t[:, role, i, p] - t[:, role, i, p - 1])
+            row["tile_total"] = med(t[:, role, i, len(nm) - 1] - t[:, role, i, 0])
+            res[f"{label}_tile{i}"] = row
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "attn_bwd_trace.json"), "w"), indent=1)
     np.save(os.path.join(ROOT, "gpurun_out", "attn_bwd_trace_first296.npy"), t[:296])
