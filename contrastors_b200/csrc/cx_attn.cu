@@ -6,12 +6,14 @@
 //
 // Forward (attn_fwd4_kernel, cx_attn_fwd.cuh): one CTA = (sequence, head, 128 query rows), two CTAs per SM, two softmax threads
 //   per query row; S in TMEM, P (bf16) in its own TMEM columns feeding O += P V straight from tensor memory.
-// Backward (attn_bwd3_kernel, cx_attn_bwd.cuh): one CTA = (sequence, head, 128 keys), loops over query tiles with TRANSPOSED
-//   scores so that P^T / dS^T feed dV / dK from tensor memory; dQ partials leave through TMA reduce-add into an fp32 accumulator.
+// Backward (attn_bwd4_kernel, cx_attn_bwd.cuh): one CTA = (sequence, head, 128 keys), loops over query tiles with TRANSPOSED
+//   scores so that P^T / dS^T feed dV / dK from tensor memory; the per-query statistics enter through a fifth MMA k-step; dQ
+//   partials leave through TMA reduce-add into an fp32 accumulator.
 //   With rope_inv_freq the transposed rotary embedding is applied to dK in the epilogue (the key's position is its row index
 //   inside the sequence), so no rotary pass over dqkv remains in the backward.
 // Round 1 kept five forward and three backward generations selectable by environment variable; they were timed on hardware in
-// round 2 (profiles/r02a_bench_attn_fwd4_bwd3_vs_flash_attn2.json) and the losers deleted.
+// round 2 (profiles/r02a_bench_attn_fwd4_bwd3_vs_flash_attn2.json) and the losers deleted; the backward was then re-scheduled
+// from a phase trace (profiles/r02l_*, r02n_*: 325 -> 312 us), its predecessor deleted as well.
 // What binds (tools/ubench, profiles/r01_ubench_tmem_mma.txt): forward, nearest hard bound the SFU (16384 exponentials per
 // 128 x 128 tile at 16 / clk / SM = 1024 clk against 512 clk of tensor time); backward, the shared-memory port.
 // The thread that ISSUES the MMAs must stay tight: the TMA / MMA warps run converged with elect.sync around the
@@ -92,16 +94,9 @@ extern "C" int cx_attn_bwd(const void* qkv, const void* out, const void* dout, c
                     128, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   dim3 grid((max_seqlen + 127) / 128, H, nseq);
-  static const bool use_bwd3 = [] { const char* e = getenv("CX_ATTN_BWD3"); return e && *e == '1'; }();  // A/B during bring-up
-  if (use_bwd3) {
-    CX_SET_SMEM_ONCE(attn_bwd3_kernel, Bwd3Smem::kTotal);
-    attn_bwd3_kernel<<<grid, kBwd2Threads, Bwd3Smem::kTotal, stream>>>(tmQKV, tmDO, tmDQ, cu_seqlens, lse, delta,
-                                                                      (__nv_bfloat16*)dqkv, T, H, softmax_scale, dk_rope_inv_freq);
-  } else {
-    CX_SET_SMEM_ONCE(attn_bwd4_kernel, Bwd4Smem::kTotal);
-    attn_bwd4_kernel<<<grid, kBwd4Threads, Bwd4Smem::kTotal, stream>>>(tmQKV, tmDO, tmDQ, cu_seqlens, lse, delta,
-                                                                      (__nv_bfloat16*)dqkv, T, H, softmax_scale, dk_rope_inv_freq);
-  }
+  CX_SET_SMEM_ONCE(attn_bwd4_kernel, Bwd4Smem::kTotal);
+  attn_bwd4_kernel<<<grid, kBwd4Threads, Bwd4Smem::kTotal, stream>>>(tmQKV, tmDO, tmDQ, cu_seqlens, lse, delta,
+                                                                    (__nv_bfloat16*)dqkv, T, H, softmax_scale, dk_rope_inv_freq);
   CX_LAUNCH_CHECK();
   return 0;
 }

@@ -1,8 +1,6 @@
 // Attention backward kernels (included by cx_attn.cu inside namespace cx; see the overview there).
 #pragma once
 
-constexpr int kBwd2Threads = 512;
-
 // ============================================================================================== backward
 // delta[h, t] = sum_d dO[t,h,d] * O[t,h,d]; 8 threads per (t, h) row of 64, 16-byte loads.  The same threads zero the fp32 dQ
 // accumulator row the backward kernel reduce-adds into (32 bytes each): no separate 100 MB fill launch per layer.
@@ -32,20 +30,6 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __n
   }
 }
 
-// ---------------------------------------------------------------------------------------------- backward, transposed scores
-// One CTA = (sequence, head, 128 keys); loops over query tiles.  The straightforward formulation (S = Q K^T, P and dS through
-// shared memory as the A operands of dV += P^T dO and dK += dS^T Q) is bound by the shared-memory port: 368 KB per 128 x 128
-// tile (MMA operands + P / dS stores + dQ staging), 2900 clk against 1664 clk of tensor time (round 1: 376 us at 64 x 512 x
-// 12 incl. delta and finalize; this kernel 351 us; FlashAttention-2 on the same box 547 us).
-// Here the scores are computed TRANSPOSED, S^T = K_j Q_i^T and dP^T = V_j dO_i^T (lane = key, column = query), so that P^T and
-// dS^T -- the A operands of dV += P^T dO and dK += dS^T Q -- are written back into tensor memory (bf16 pairs, over the
-// thread's own first 32 score columns) and those two contractions read only their B operand from shared memory (a TS MMA
-// with N = 64 runs at 32 clk instead of 48, profiles/r01_ubench_tmem_mma.txt).  dS still goes to shared memory once, as the
-// (MN-major) A operand of dQ = dS K.  Shared-memory traffic per tile: 240 KB.  The row statistics are per COLUMN now: the
-// workers publish -lse*log2(e) and -delta*scale of the query tile in shared memory and read them with broadcast loads.
-// TMEM: S^T [0,128)  dP^T [128,256)  dV [256,320)  dK [320,384)  dQ [384,448);  P^T over S^T columns [0,32) + [64,96),
-// dS^T over dP^T columns [128,160) + [192,224) (each thread overwrites only columns it has already loaded itself).
-// 16 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 workers (two threads per key row, 64 query columns each), 12-15 dQ drain.
 // Optional phase trace (tools/trace_attn_bwd.py builds a separate library with -DCX_ATTN_TRACE; the product build compiles none
 // of it): one lane of one warp per role stamps clock64() at its phase boundaries, [block][role 5][tile 8][point 8].
 #ifdef CX_ATTN_TRACE
@@ -64,420 +48,32 @@ __device__ long long* g_bwd_trace = nullptr;
 #define CX_TRW(i, pt) do { } while (0)
 #endif
 
-struct Bwd3Smem {
-  static constexpr int kTile = 128 * kDh * 2;   // 16 KB
-  static constexpr int kK = 0;                  // K_j  (A of S^T, B of dQ as MN-major)
-  static constexpr int kV = kK + kTile;         // V_j  (A of dP^T)
-  static constexpr int kQ = kV + kTile;         // 2 stages: Q_i (B of S^T, B of dK as MN-major)
-  static constexpr int kDO = kQ + 2 * kTile;    // 2 stages: dO_i (B of dP^T, B of dV as MN-major)
-  static constexpr int kDS = kDO + 2 * kTile;   // dS^T [128 keys x 128 q] bf16: 2 blocks (q halves) x 128 rows x 128 B
-  static constexpr int kDQ = kDS + 32768;       // fp32 staging for the dQ reduce-add: 2 x [128 x 32] (128 B rows)
-  static constexpr int kStat = kDQ + 2 * 16384; // 2 buffers x { -lse*log2e [128], -delta*scale [128] } fp32
-  static constexpr int kBars = kStat + 2048;
-  static constexpr int kTotal = kBars + 256 + 1024;
-};
-
-__global__ void __launch_bounds__(kBwd2Threads, 1)
-attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                 const __grid_constant__ CUtensorMap tmDQ, const int* __restrict__ cu_seqlens,
-                 const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T,
-                 int H, float softmax_scale, const float* __restrict__ rope_inv_freq) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Bwd3Smem::kBars);
-  uint64_t* kv_full = bars;        // [1]
-  uint64_t* q_full = bars + 1;     // [2]  Q_i and dO_i of a stage landed
-  uint64_t* q_empty = bars + 3;    // [2]  every MMA reading the stage has completed
-  uint64_t* s_full = bars + 5;     // S^T(i) in TMEM
-  uint64_t* dp_full = bars + 6;    // dP^T(i) in TMEM
-  uint64_t* p_ready = bars + 7;    // P^T(i) in TMEM, every worker has loaded its S^T(i) columns (256 arrivals)
-  uint64_t* ds_ready = bars + 8;   // dS^T(i) in TMEM and in smem, every worker has loaded its dP^T(i) columns (256 arrivals)
-  uint64_t* dq_full = bars + 9;    // dQ(i) partial in TMEM; also: dQ(i) has finished reading dS(i) from smem
-  uint64_t* dq_free = bars + 10;   // dQ TMEM columns drained (128 arrivals)
-  uint64_t* acc_full = bars + 11;  // dK / dV complete
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  CX_TR_INIT();
-  const int seq = blockIdx.z, head = blockIdx.y;
-  const int seq_begin = cu_seqlens[seq];
-  const int len = cu_seqlens[seq + 1] - seq_begin;
-  const int k0 = blockIdx.x * 128;
-  if (k0 >= len) return;
-  const int nq = (len + 127) / 128;
-  const float scale2 = softmax_scale * kLog2e;
-  if (warp == 0) CX_TR(4, 0, 0);
-
-  const int col_q = (0 * H + head) * kDh, col_k = (1 * H + head) * kDh, col_v = (2 * H + head) * kDh;
-  const int col_o = head * kDh;
-  if (warp == 0 && lane == 0) {
-    mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&q_full[i], 1);
-      mbar_init(&q_empty[i], 1);
-    }
-    mbar_init(s_full, 1);
-    mbar_init(dp_full, 1);
-    mbar_init(p_ready, 256);
-    mbar_init(ds_ready, 256);
-    mbar_init(dq_full, 1);
-    mbar_init(dq_free, 128);
-    mbar_init(acc_full, 1);
-    fence_barrier_init();
-    mbar_arrive_expect_tx(kv_full, 2 * Bwd3Smem::kTile);
-    tma_load_2d(smem + Bwd3Smem::kK, &tmQKV, kv_full, col_k, seq_begin + k0);
-    tma_load_2d(smem + Bwd3Smem::kV, &tmQKV, kv_full, col_v, seq_begin + k0);
-    mbar_arrive_expect_tx(&q_full[0], 2 * Bwd3Smem::kTile);
-    tma_load_2d(smem + Bwd3Smem::kQ, &tmQKV, &q_full[0], col_q, seq_begin);
-    tma_load_2d(smem + Bwd3Smem::kDO, &tmDO, &q_full[0], col_o, seq_begin);
-    tma_prefetch_desc(&tmDQ);
-  }
-  if (warp == 2) tmem_alloc<512>(tmem_ptr);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-  if (warp == 0) CX_TR(4, 0, 1);
-
-  if (warp == 0) {
-    for (int i = 1; i < nq; ++i) {  // K, V and the first query tile were issued during set-up
-      const int st = i & 1;
-      mbar_wait(&q_empty[st], ((i >> 1) & 1) ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&q_full[st], 2 * Bwd3Smem::kTile);
-        tma_load_2d(smem + Bwd3Smem::kQ + st * Bwd3Smem::kTile, &tmQKV, &q_full[st], col_q, seq_begin + i * 128);
-        tma_load_2d(smem + Bwd3Smem::kDO + st * Bwd3Smem::kTile, &tmDO, &q_full[st], col_o, seq_begin + i * 128);
-      }
-      __syncwarp();
-    }
-  } else if (warp == 1) {
-    constexpr uint32_t id_kk = make_idesc_bf16(128, 128, 0, 0);  // S^T, dP^T: A (K_j / V_j) K-major, B (Q_i / dO_i) K-major
-    constexpr uint32_t id_tm = make_idesc_bf16(128, 64, 0, 1);   // dV, dK: A from TMEM, B (dO_i / Q_i) MN-major, N = 64
-    constexpr uint32_t id_mm = make_idesc_bf16(128, 64, 1, 1);   // dQ: A (dS^T in smem) MN-major, B (K_j) MN-major, N = 64
-    const uint64_t kd = make_smem_desc_sw128(smem_u32(smem + Bwd3Smem::kK), 0, 1024);        // K_j  K-major (A of S^T)
-    const uint64_t vd = make_smem_desc_sw128(smem_u32(smem + Bwd3Smem::kV), 0, 1024);        // V_j  K-major (A of dP^T)
-    const uint64_t qd = make_smem_desc_sw128(smem_u32(smem + Bwd3Smem::kQ), 0, 1024);        // Q_i  K-major (B of S^T)
-    const uint64_t dod = make_smem_desc_sw128(smem_u32(smem + Bwd3Smem::kDO), 0, 1024);      // dO_i K-major (B of dP^T)
-    const uint64_t km = make_smem_desc_sw128(smem_u32(smem + Bwd3Smem::kK), 8192, 1024);     // K_j  MN-major (B of dQ)
-    const uint64_t qm = make_smem_desc_sw128(smem_u32(smem + Bwd3Smem::kQ), 8192, 1024);     // Q_i  MN-major (B of dK)
-    const uint64_t dom = make_smem_desc_sw128(smem_u32(smem + Bwd3Smem::kDO), 8192, 1024);   // dO_i MN-major (B of dV)
-    const uint64_t dsm = make_smem_desc_sw128(smem_u32(smem + Bwd3Smem::kDS), 16384, 1024);  // dS^T MN-major (A of dQ)
-    mbar_wait(kv_full, 0);
-    mbar_wait(&q_full[0], 0);
-    tc_fence_after();
-    if (elect_one()) {
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) umma_f16_ss(tmem_base + 0, kd + ((kk * 32) >> 4), qd + ((kk * 32) >> 4), id_kk, kk > 0 ? 1u : 0u);
-      umma_commit(s_full);
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) umma_f16_ss(tmem_base + 128, vd + ((kk * 32) >> 4), dod + ((kk * 32) >> 4), id_kk, kk > 0 ? 1u : 0u);
-      umma_commit(dp_full);
-    }
-    __syncwarp();
-    for (int i0 = 0; i0 < nq; i0 += 2) {
-#pragma unroll
-      for (int st = 0; st < 2; ++st) {  // st = i & 1 is a compile-time constant after unrolling
-        const int i = i0 + st;
-        if (i < nq) {                   // warp-uniform
-          constexpr int kT = Bwd3Smem::kTile;
-          const int ns = st ^ 1;
-          const bool more = i + 1 < nq;
-          CX_TR(2, i, 0);
-          mbar_wait(p_ready, i & 1);
-          if (more) mbar_wait(&q_full[ns], ((i + 1) >> 1) & 1);
-          tc_fence_after();
-          CX_TR(2, i, 1);
-          if (elect_one()) {
-            // dV += P^T dO_i: A = P^T from TMEM (16 queries = 8 columns per k-step; queries 64.. live at column 64),
-            // B = dO_i MN-major (16 query rows = +2048 B per k-step)
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk)
-              umma_f16_ts(tmem_base + 256, tmem_base + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8), dom + ((st * kT + kk * 2048) >> 4),
-                          id_tm, (i > 0 || kk > 0) ? 1u : 0u);
-            if (more) {  // S^T(i+1) = K_j Q_{i+1}^T overwrites the score columns (and P^T) behind dV(i), in issue order
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                umma_f16_ss(tmem_base + 0, kd + ((kk * 32) >> 4), qd + ((ns * kT + kk * 32) >> 4), id_kk, kk > 0 ? 1u : 0u);
-              umma_commit(s_full);
-            }
-          }
-          __syncwarp();
-          CX_TR(2, i, 2);
-          mbar_wait(ds_ready, i & 1);
-          CX_TR(2, i, 3);
-          if (i > 0) mbar_wait(dq_free, (i - 1) & 1);
-          tc_fence_after();
-          CX_TR(2, i, 4);
-          if (elect_one()) {
-            // dK += dS^T Q_i: A = dS^T from TMEM (over the dP^T columns), B = Q_i MN-major
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk)
-              umma_f16_ts(tmem_base + 320, tmem_base + 128 + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8),
-                          qm + ((st * kT + kk * 2048) >> 4), id_tm, (i > 0 || kk > 0) ? 1u : 0u);
-            if (more) {  // dP^T(i+1) = V_j dO_{i+1}^T overwrites dS^T behind dK(i)
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                umma_f16_ss(tmem_base + 128, vd + ((kk * 32) >> 4), dod + ((ns * kT + kk * 32) >> 4), id_kk, kk > 0 ? 1u : 0u);
-              umma_commit(dp_full);
-            }
-            // dQ_i(partial) = dS K_j: A = dS^T in smem read MN-major (16 keys = +2048 B per k-step, the two 64-query atoms
-            // 16 KB apart), B = K_j MN-major
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk)
-              umma_f16_ss(tmem_base + 384, dsm + ((kk * 2048) >> 4), km + ((kk * 2048) >> 4), id_mm, kk > 0 ? 1u : 0u);
-            umma_commit(dq_full);
-            umma_commit(&q_empty[st]);
-          }
-          __syncwarp();
-          CX_TR(2, i, 5);
-        }
-      }
-    }
-    if (elect_one()) umma_commit(acc_full);
-    __syncwarp();
-  } else if (warp >= 4 && warp < 12) {
-    // ---------------------------------------------------------------- workers: two threads per KEY row, 64 queries each
-    const int ew = warp & 3;
-    const int grp = (warp - 4) >> 2;  // queries [grp*64, grp*64+64) of the tile
-    const int r = ew * 32 + lane;     // key row within the tile
-    const int wt = grp * 128 + r;     // worker thread index 0..255
-    const uint32_t lane_base = static_cast<uint32_t>(ew * 32) << 16;
-    const bool key_ok = k0 + r < len;
-    uint8_t* dd = smem + Bwd3Smem::kDS + grp * 16384 + r * 128;   // this thread's 128-byte row of dS^T (its query half)
-    float* stat = reinterpret_cast<float*>(smem + Bwd3Smem::kStat);
-    const float2 sc2 = make_float2(scale2, scale2), ss2 = make_float2(softmax_scale, softmax_scale);
-    const float* lse_h = lse + (size_t)head * T + seq_begin;
-    const float* dl_h = delta + (size_t)head * T + seq_begin;
-    // thread wt publishes one column statistic per tile: wt < 128: -lse * log2(e) of query wt; else -delta * scale of query wt - 128.
-    // The raw value of the NEXT tile is loaded a whole iteration ahead and only converted when it is published (round 2: with the
-    // multiply next to the load, every worker stalled ~7 % of the kernel on that global load, profiles/r02e_attn_bwd3_stalls...)
-    const int sq = wt & 127;
-    const float* st_src = (wt < 128) ? lse_h : dl_h;
-    const float st_mul = (wt < 128) ? -kLog2e : -softmax_scale;
-    const float st_pad = (wt < 128) ? -INFINITY : 0.f;
-    float st_raw = (sq < len) ? st_src[sq] : 0.f;
-    const int tr_role = (warp == 4) ? 0 : (warp == 8 ? 1 : 5);  // trace: the first warp of each query half
-    (void)tr_role;
-    for (int i = 0; i < nq; ++i) {
-      CX_TRW(i, 0);
-      float* sb = stat + (i & 1) * 256;
-      sb[wt] = (i * 128 + sq < len) ? st_raw * st_mul : st_pad;  // [0,128): -lse2 per query (-inf past the end => P = 0), [128,256): -delta*scale
-      {
-        const int nqr = (i + 1) * 128 + sq;  // prefetch the next tile's statistic (consumed one iteration later)
-        st_raw = (nqr < len) ? st_src[nqr] : 0.f;
-      }
-      named_bar_sync(4, 256);
-      CX_TRW(i, 1);
-      const float* nl = sb + grp * 64;        // -lse2 of this thread's 64 queries
-      const float* nd = sb + 128 + grp * 64;  // -delta*scale
-      // ---- X: P^T = exp2(S^T * scale2 - lse2[q]) -> bf16 pairs -> this thread's first 32 score columns
-      uint32_t pp[32];
-      mbar_wait(s_full, i & 1);
-      tc_fence_after();
-      CX_TRW(i, 2);
-      {
-        uint32_t va[32], vb[32];
-        tmem_ld_32x32(tmem_base + lane_base + grp * 64, va);
-        tmem_ld_32x32(tmem_base + lane_base + grp * 64 + 32, vb);
-        tmem_ld_wait();
-        CX_TRW(i, 3);
-#pragma unroll
-        for (int t = 0; t < 16; t += 2) {
-          const float4 c = *reinterpret_cast<const float4*>(nl + 2 * t);  // broadcast: every lane reads the same address
-          const float2 xa = ffma2(make_float2(__uint_as_float(va[2 * t]), __uint_as_float(va[2 * t + 1])), sc2, make_float2(c.x, c.y));
-          const float2 xb = ffma2(make_float2(__uint_as_float(va[2 * t + 2]), __uint_as_float(va[2 * t + 3])), sc2, make_float2(c.z, c.w));
-          pp[t] = pack_bf16x2(fast_exp2(xa.x), fast_exp2(xa.y));
-          pp[t + 1] = pack_bf16x2(fast_exp2(xb.x), fast_exp2(xb.y));
-        }
-#pragma unroll
-        for (int t = 0; t < 16; t += 2) {
-          const float4 c = *reinterpret_cast<const float4*>(nl + 32 + 2 * t);
-          const float2 xa = ffma2(make_float2(__uint_as_float(vb[2 * t]), __uint_as_float(vb[2 * t + 1])), sc2, make_float2(c.x, c.y));
-          const float2 xb = ffma2(make_float2(__uint_as_float(vb[2 * t + 2]), __uint_as_float(vb[2 * t + 3])), sc2, make_float2(c.z, c.w));
-          pp[16 + t] = pack_bf16x2(fast_exp2(xa.x), fast_exp2(xa.y));
-          pp[16 + t + 1] = pack_bf16x2(fast_exp2(xb.x), fast_exp2(xb.y));
-        }
-      }
-      if (!key_ok) {  // keys past the sequence end contribute nothing
-#pragma unroll
-        for (int t = 0; t < 32; ++t) pp[t] = 0u;
-      }
-      tmem_st_32x32(tmem_base + lane_base + grp * 64, pp);  // over this thread's own (already loaded) score columns
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(p_ready);
-      CX_TRW(i, 4);
-      // ---- Y: dS^T = P^T * (dP^T * scale - delta[q] * scale) -> TMEM (A of dK) and smem (A of dQ)
-      mbar_wait(dp_full, i & 1);
-      tc_fence_after();
-      if (i > 0) mbar_wait_quiet(dq_full, (i - 1) & 1);  // dQ(i-1) has finished reading the dS buffer
-      CX_TRW(i, 5);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t vd[32];
-        tmem_ld_32x32(tmem_base + lane_base + 128 + grp * 64 + c * 32, vd);
-        tmem_ld_wait();
-        uint32_t w[16];
-#pragma unroll
-        for (int t = 0; t < 16; t += 2) {
-          const float4 dc = *reinterpret_cast<const float4*>(nd + c * 32 + 2 * t);
-          const float2 ga = ffma2(make_float2(__uint_as_float(vd[2 * t]), __uint_as_float(vd[2 * t + 1])), ss2, make_float2(dc.x, dc.y));
-          const float2 gb = ffma2(make_float2(__uint_as_float(vd[2 * t + 2]), __uint_as_float(vd[2 * t + 3])), ss2, make_float2(dc.z, dc.w));
-          const float2 da = fmul2(unpack_bf16x2(pp[c * 16 + t]), ga);
-          const float2 db = fmul2(unpack_bf16x2(pp[c * 16 + t + 1]), gb);
-          w[t] = pack_bf16x2(da.x, da.y);
-          w[t + 1] = pack_bf16x2(db.x, db.y);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(dd + (((c * 4 + q) ^ (r & 7)) << 4)) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-        // over this thread's own dP^T columns [0,16) / [16,32): both lie inside chunk 0, which is in registers by now
-        tmem_st_32x16(tmem_base + lane_base + 128 + grp * 64 + c * 16, w);
-      }
-      CX_TRW(i, 6);
-      fence_proxy_async_smem();
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(ds_ready);
-      CX_TRW(i, 7);
-    }
-    // dV (group 0) / dK (group 1) -> bf16 -> the (dead) dS buffer, one swizzled 128-byte row per thread; then each group
-    // copies its tile out with row-contiguous 16-byte stores
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    if (warp == 4) CX_TR(4, 0, 2);
-    uint8_t* stg = smem + Bwd3Smem::kDS + grp * 16384;
-    if (grp == 1 && rope_inv_freq != nullptr) {
-      // dK with the transposed rotary embedding (the keys were rotated before the scores were formed): a thread owns one key
-      // row, i.e. both halves (x1 = columns [0,32), x2 = [32,64)) of the head; the key's position is its row index in the sequence
-      //   d x1 = g1 cos + g2 sin,  d x2 = g2 cos - g1 sin      (forward: o1 = x1 cos - x2 sin, o2 = x2 cos + x1 sin)
-      uint32_t v1[32], v2[32];
-      tmem_ld_32x32(tmem_base + lane_base + 256 + 64, v1);
-      tmem_ld_32x32(tmem_base + lane_base + 256 + 64 + 32, v2);
-      tmem_ld_wait();
-      const float posf = (float)(k0 + r);
-#pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        const float2 f2 = __ldg(reinterpret_cast<const float2*>(rope_inv_freq + j));
-        const float a0 = posf * f2.x, a1 = posf * f2.y;
-        const float c0 = __cosf(a0), s0 = __sinf(a0), c1 = __cosf(a1), s1 = __sinf(a1);
-        const float g10 = __uint_as_float(v1[j]), g11 = __uint_as_float(v1[j + 1]);
-        const float g20 = __uint_as_float(v2[j]), g21 = __uint_as_float(v2[j + 1]);
-        v1[j] = __float_as_uint(g10 * c0 + g20 * s0);
-        v1[j + 1] = __float_as_uint(g11 * c1 + g21 * s1);
-        v2[j] = __float_as_uint(g20 * c0 - g10 * s0);
-        v2[j + 1] = __float_as_uint(g21 * c1 - g11 * s1);
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint4 w1, w2;
-        w1.x = pack_bf16x2(__uint_as_float(v1[8 * q + 0]), __uint_as_float(v1[8 * q + 1]));
-        w1.y = pack_bf16x2(__uint_as_float(v1[8 * q + 2]), __uint_as_float(v1[8 * q + 3]));
-        w1.z = pack_bf16x2(__uint_as_float(v1[8 * q + 4]), __uint_as_float(v1[8 * q + 5]));
-        w1.w = pack_bf16x2(__uint_as_float(v1[8 * q + 6]), __uint_as_float(v1[8 * q + 7]));
-        w2.x = pack_bf16x2(__uint_as_float(v2[8 * q + 0]), __uint_as_float(v2[8 * q + 1]));
-        w2.y = pack_bf16x2(__uint_as_float(v2[8 * q + 2]), __uint_as_float(v2[8 * q + 3]));
-        w2.z = pack_bf16x2(__uint_as_float(v2[8 * q + 4]), __uint_as_float(v2[8 * q + 5]));
-        w2.w = pack_bf16x2(__uint_as_float(v2[8 * q + 6]), __uint_as_float(v2[8 * q + 7]));
-        *reinterpret_cast<uint4*>(stg + r * 128 + ((q ^ (r & 7)) << 4)) = w1;
-        *reinterpret_cast<uint4*>(stg + r * 128 + (((4 + q) ^ (r & 7)) << 4)) = w2;
-      }
-    } else {
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + lane_base + 256 + grp * 64 + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
-          w.y = pack_bf16x2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
-          w.z = pack_bf16x2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
-          w.w = pack_bf16x2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
-          *reinterpret_cast<uint4*>(stg + r * 128 + (((c * 4 + q) ^ (r & 7)) << 4)) = w;
-        }
-      }
-    }
-    named_bar_sync(2 + grp, 128);
-    {
-      const int tid = (threadIdx.x - 128) & 127;
-      const int rows_ok = min(128, len - k0);
-      uint8_t* obase = reinterpret_cast<uint8_t*>(dqkv + ((size_t)(seq_begin + k0) * 3 + (grp == 0 ? 2 : 1)) * H * kDh + (size_t)head * kDh);
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int idx = it * 128 + tid, row = idx >> 3, ch = idx & 7;
-        if (row < rows_ok)
-          *reinterpret_cast<uint4*>(obase + (size_t)row * 3 * H * kDh * 2 + ch * 16) =
-              *reinterpret_cast<const uint4*>(stg + row * 128 + ((ch ^ (row & 7)) << 4));
-      }
-    }
-    if (warp == 4) CX_TR(4, 0, 3);
-  } else if (warp >= 12) {
-    // ---------------------------------------------------------------- dQ drain: one thread per query row, 64 columns
-    const int ew = warp & 3;
-    const int r = ew * 32 + lane;
-    const int etid = threadIdx.x - 384;
-    const uint32_t lane_base = static_cast<uint32_t>(ew * 32) << 16;
-    uint8_t* stage = smem + Bwd3Smem::kDQ;  // two [128 x 32] fp32 boxes (128-byte rows, 128B swizzle)
-    for (int i = 0; i < nq; ++i) {
-      const bool row_ok = i * 128 + r < len;
-      if (warp == 12) CX_TR(3, i, 0);
-      mbar_wait(dq_full, i & 1);
-      tc_fence_after();
-      if (warp == 12) CX_TR(3, i, 1);
-      uint32_t va[32], vb[32];
-      tmem_ld_32x32(tmem_base + lane_base + 384, va);
-      tmem_ld_32x32(tmem_base + lane_base + 384 + 32, vb);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(dq_free);  // the next tile's dQ MMA may overwrite the columns
-      if (warp == 12) CX_TR(3, i, 2);
-      if (etid == 0) tma_store_wait_read<0>();  // the previous reduce-add has finished reading the stage
-      named_bar_sync(1, 128);
-      if (warp == 12) CX_TR(3, i, 3);
-      uint8_t* d0 = stage + r * 128;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        *reinterpret_cast<uint4*>(d0 + ((q ^ (r & 7)) << 4)) =
-            make_uint4(row_ok ? va[4 * q] : 0u, row_ok ? va[4 * q + 1] : 0u, row_ok ? va[4 * q + 2] : 0u, row_ok ? va[4 * q + 3] : 0u);
-        *reinterpret_cast<uint4*>(d0 + 16384 + ((q ^ (r & 7)) << 4)) =
-            make_uint4(row_ok ? vb[4 * q] : 0u, row_ok ? vb[4 * q + 1] : 0u, row_ok ? vb[4 * q + 2] : 0u, row_ok ? vb[4 * q + 3] : 0u);
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(1, 128);
-      if (etid == 0) {
-        tma_reduce_add_2d(&tmDQ, stage, col_o, seq_begin + i * 128);
-        tma_reduce_add_2d(&tmDQ, stage + 16384, col_o + 32, seq_begin + i * 128);
-        tma_store_commit();
-      }
-      if (warp == 12) CX_TR(3, i, 4);
-    }
-    if (etid == 0) tma_store_wait_read<0>();
-    if (warp == 12) CX_TR(4, 0, 5);
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) CX_TR(4, 0, 4);
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------- backward, four threads per key row
-// Same data flow and TMEM / shared-memory layout as attn_bwd3_kernel; what changes is who does the element-wise work.  The phase
-// trace of bwd3 (tools/trace_attn_bwd.py, profiles/r02h_attn_bwd3_phase_trace.txt) shows a query tile costing ~3800 clk of which the
-// tensor pipe is busy 1640: the 8 worker warps (2 per scheduler) need 1650 clk for P^T = exp2(...) and 970 clk for dS^T, each
-// thread walking 64 elements through dependent FFMA -> MUFU -> F2F chains with too few warps to hide the latencies, plus ~200 clk
-// at the per-tile named barrier that publishes the column statistics.  Here:
-//  * 16 worker warps (4 per scheduler), FOUR threads per key row with 32 query columns each;
-//  * a quarter of the exponentials goes to the FMA pipe (exp2_poly2), as in the forward kernel;
-//  * the column statistics of tile i+1 are published (triple-buffered) behind the s_full(i) wait, so the existing
-//    p_ready(i) -> S^T(i+1) commit -> s_full(i+1) chain orders them and the per-tile barrier is gone;
+// ---------------------------------------------------------------------------------------------- backward, transposed scores
+// One CTA = (sequence, head, 128 keys); loops over the query tiles of the sequence.  The straightforward formulation (S = Q K^T,
+// P and dS through shared memory as the A operands of dV += P^T dO and dK += dS^T Q) is bound by the shared-memory port.  Here
+// the scores are computed TRANSPOSED, S^T = K_j Q_i^T and dP^T = V_j dO_i^T (lane = key, column = query), so that P^T and dS^T --
+// the A operands of dV += P^T dO and dK += dS^T Q -- are written back into tensor memory (bf16 pairs, over the thread's own
+// score columns) and those two contractions read only their B operand from shared memory.  dS still goes to shared memory once,
+// as the (MN-major) A operand of dQ = dS K; dQ partials leave through a TMA reduce-add into an fp32 accumulator.
+//
+// What the phase trace (tools/trace_attn_bwd.py, profiles/r02l_*, r02n_*) showed about the first version of this kernel (8 worker
+// warps, two threads per key row, statistics read from shared memory; 325 us incl. delta + finalize at 64 x 512 x 12) and what
+// this version does about it:
+//  * the query-tile period (~3400 clk) is the SUM of the two element-wise phases of the worker warps (X: P^T = exp2(..), Y: dS^T),
+//    the tensor pipe (~1550 clk of MMAs per tile) being hidden underneath; every consumer of the shared-memory port that is
+//    removed shortens the period by about its wavefront count.  The per-COLUMN statistics were the largest avoidable one: a
+//    broadcast LDS.128 still delivers 16 bytes to each lane = 4 wavefronts, 1024 per tile.  They now enter through the MMA: a
+//    fifth k-step multiplies a ones operand with -lse/scale (resp. -delta) of the query tile, split into three bf16 terms (exact
+//    to 2^-24), so S^T and dP^T arrive with the statistic already subtracted and the workers only scale;
+//  * 16 worker warps, FOUR threads per key row with 32 query columns each (the dependent FFMA -> MUFU -> F2F chains of 64
+//    elements per thread were latency-bound with two warps per scheduler), a quarter of the exponentials on the FMA pipe;
+//  * a three-stage Q_i / dO_i ring (with two, the request for tile i+1 went out only when tile i-1's last MMA had completed);
 //  * the epilogue (dV / dK conversion, rotary transpose, copy-out) is shared by twice as many threads.
-// P^T of query quarter qq lives over S^T columns [qq*32, qq*32+16), dS^T over dP^T columns [128+qq*32, +16).
+// Measured and NOT adopted (each slower, the traces are in profiles/): X and Y on separate warp groups with P^T in its own
+// columns (r02m: 343 us -- the two groups contend for the same port), dQ issued one slot late (r02o: 325 us), K_j / V_j as
+// tensor-memory A operands of S^T / dP^T (320 us -- TS MMAs with N = 128 collide with the workers' tcgen05.ld / st).
+// TMEM: S^T [0,128)  dP^T [128,256)  dV [256,320)  dK [320,384)  dQ [384,448);  P^T of query quarter qq over S^T columns
+// [qq*32, qq*32+16), dS^T over dP^T columns [128+qq*32, +16) (each thread overwrites only columns it has already loaded itself).
 // 24 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-19 workers, 20-23 dQ drain.
 constexpr int kBwd4Threads = 768;
 constexpr int kBwd4Poly = 4;  // every other quad of the second half-pair: 25 % of the exponentials on the FMA pipe

@@ -1,7 +1,7 @@
 """mbarrier protocols of the attention kernels on the discrete-event model (tools/sim_attn_protocol.py): every kernel
 terminates without deadlock, barrier over-arrival, parity aliasing or data hazard over random schedules, and the model does catch
 a removed wait (negative controls).  CPU only; the two kernels modelled are the ones in the library (attn_fwd4_kernel,
-attn_bwd3_kernel: written against this model at the end of round 1, validated on hardware in round 2)."""
+attn_bwd4_kernel; the backward model was updated with the kernel when its schedule changed in round 2)."""
 import os
 import sys
 
@@ -17,7 +17,7 @@ def test_protocol_terminates_without_hazards(name):
 
 
 @pytest.mark.parametrize("name,bug", [("attn_fwd4_kernel", "no_s_free"), ("attn_fwd4_kernel", "no_pv_done"),
-                                      ("attn_bwd3_kernel", "no_dq_full_wait")])
+                                      ("attn_bwd4_kernel", "no_dq_full_wait"), ("attn_bwd4_kernel", "early_lse_write")])
 def test_model_catches_a_removed_wait(name, bug):
     caught = 0
     for n in range(2, 7):

@@ -26,8 +26,8 @@ def timeit(fn, iters=8, warm=2):
     return ts[len(ts) // 2]
 
 
-MODES = [(8, 3)]  # the one generation left: two-threads-per-row forward, transposed-score backward
-TAG = "fwd4_bwd3"
+MODES = [(4, 4)]  # the one generation left: two-threads-per-row forward, transposed-score backward with four threads per key row
+TAG = "fwd4_bwd4"
 res = {}
 for name, nseq, S, H in [("bert_64x512", 64, 512, 12), ("vit_256x197", 256, 197, 12)]:
     Dh = 64

@@ -233,182 +233,32 @@ def run_fwd4(nk, seed, bug=None):
 
 
 # ================================================================================================ forward, persistent (fwd5)
-# ================================================================================================ backward (bwd2 / bwd3)
-def run_bwd(nq, seed, transposed, bug=None):
-    """attn_bwd2_kernel (transposed=False) / attn_bwd3_kernel (transposed=True): nq query tiles; 8 worker warps, 4 drain warps."""
+# ================================================================================================ backward (bwd4)
+def run_bwd4(nq, seed, bug=None):
+    """attn_bwd4_kernel: nq query tiles; 16 worker warps (X then Y per tile), 4 dQ drain warps, 3-stage Q/dO ring, P^T / dS^T in
+    tensor memory over the score columns, the per-query statistics in an auxiliary MMA operand tile rewritten one tile ahead."""
     sim = Sim(seed)
     B = lambda n, c: sim.barrier(n, c)
-    kv_full, s_full, dp_full = B("kv_full", 1), B("s_full", 1), B("dp_full", 1)
-    p_ready, ds_ready, dq_full, dq_free, acc_full = B("p_ready", 256), B("ds_ready", 256), B("dq_full", 1), B("dq_free", 128), B("acc_full", 1)
-    p_free = B("p_free", 1)
-    q_full, q_empty = [B("q_full0", 1), B("q_full1", 1)], [B("q_empty0", 1), B("q_empty1", 1)]
+    NS, NW = 3, 16
+    kv_full, s_full, dp_full, aux_init = B("kv_full", 1), B("s_full", 1), B("dp_full", 1), B("aux_init", 32 * NW)
+    p_ready, ds_ready = B("p_ready", 32 * NW), B("ds_ready", 32 * NW)
+    dq_full, dq_free, acc_full = B("dq_full", 1), B("dq_free", 128), B("acc_full", 1)
+    q_full, q_empty = [B(f"q_full{k}", 1) for k in range(NS)], [B(f"q_empty{k}", 1) for k in range(NS)]
     Sreg, DPreg = dict(tile=-1, loaded=set()), dict(tile=-1, loaded=set())
-    Pbuf = dict(tile=-1, written=set(), consumed=-1)    # bwd2: smem P; bwd3: P^T in TMEM over the score columns
+    Pbuf = dict(tile=-1, written=set(), consumed=-1)        # P^T in TMEM over the score columns
     DSbuf = dict(tile=-1, written=set(), dk_done=-1, dq_done=-1)
     DQ = dict(tile=-1, drained=-1)
-    Qst = [dict(tile=-1, busy=0) for _ in range(2)]
-
-    def tma():
-        sim.tma(kv_full)
-        Qst[0]["tile"] = 0; sim.tma(q_full[0])
-        for i in range(1, nq):
-            st = i & 1
-            yield ("wait", q_empty[st], (i >> 1) - 1) if i >= 2 else ("now",)
-            check(Qst[st]["busy"] == 0, f"Q/dO stage {st} reloaded while {Qst[st]['busy']} MMAs read it")
-            Qst[st]["tile"] = i; sim.tma(q_full[st])
-
-    def s_mma(i):
-        st = i & 1
-        def start():
-            check(Qst[st]["tile"] == i, f"S({i}) reads stage holding {Qst[st]['tile']}")
-            check(i == 0 or (Sreg["tile"] == i - 1 and len(Sreg["loaded"]) == 8), f"S({i}) overwrites unread scores")
-            if transposed:
-                check(i == 0 or Pbuf["consumed"] >= i - 1, f"S^T({i}) overwrites P^T({i - 1}) before dV read it")
-            Qst[st]["busy"] += 1
-        def end():
-            Sreg["tile"], Sreg["loaded"] = i, set(); Qst[st]["busy"] -= 1
-        sim.mma(256, start, end)
-        sim.commit(s_full)
-
-    def dp_mma(i):
-        st = i & 1
-        def start():
-            check(Qst[st]["tile"] == i, f"dP({i}) reads stage holding {Qst[st]['tile']}")
-            check(i == 0 or (DPreg["tile"] == i - 1 and len(DPreg["loaded"]) == 8), f"dP({i}) overwrites unread dP")
-            if transposed:
-                check(i == 0 or DSbuf["dk_done"] >= i - 1, f"dP^T({i}) overwrites dS^T({i - 1}) before dK read it")
-            Qst[st]["busy"] += 1
-        def end():
-            DPreg["tile"], DPreg["loaded"] = i, set(); Qst[st]["busy"] -= 1
-        sim.mma(256, start, end)
-        sim.commit(dp_full)
-
-    def mma():
-        yield ("wait", kv_full, 0)
-        yield ("wait", q_full[0], 0)
-        s_mma(0)
-        dp_mma(0)
-        for i in range(nq):
-            st, more = i & 1, i + 1 < nq
-            yield ("wait", p_ready, i)
-            if more:
-                yield ("wait", q_full[st ^ 1], (i + 1) >> 1)
-            def dv_start(i=i, st=st):
-                check(Pbuf["tile"] == i and len(Pbuf["written"]) == 8, f"dV({i}) reads P holding {Pbuf['tile']}")
-                Qst[st]["busy"] += 1
-            def dv_end(i=i, st=st):
-                Pbuf["consumed"] = i; Qst[st]["busy"] -= 1
-            if transposed:
-                sim.mma(256, dv_start, dv_end)
-                if more:
-                    s_mma(i + 1)
-            else:
-                if more:
-                    s_mma(i + 1)
-                sim.mma(384, dv_start, dv_end)
-                sim.commit(p_free)
-            yield ("wait", ds_ready, i)
-            if i > 0:
-                yield ("wait", dq_free, i - 1)
-            def dk_start(i=i, st=st):
-                check(DSbuf["tile"] == i and len(DSbuf["written"]) == 8, f"dK({i}) reads dS holding {DSbuf['tile']}")
-                Qst[st]["busy"] += 1
-            def dk_end(i=i, st=st):
-                DSbuf["dk_done"] = i; Qst[st]["busy"] -= 1
-            def dq_start(i=i):
-                check(DSbuf["tile"] == i, f"dQ({i}) reads dS holding {DSbuf['tile']}")
-                check(DQ["drained"] >= i - 1, f"dQ({i}) overwrites the undrained partial {DQ['tile']}")
-            def dq_end(i=i):
-                DSbuf["dq_done"] = i; DQ["tile"] = i
-            if transposed:
-                sim.mma(256, dk_start, dk_end)
-                if more:
-                    dp_mma(i + 1)
-                sim.mma(384, dq_start, dq_end)
-            else:
-                if more:
-                    dp_mma(i + 1)
-                sim.mma(384, dk_start, dk_end)
-                sim.mma(384, dq_start, dq_end)
-            sim.commit(dq_full)
-            sim.commit(q_empty[st])
-        sim.commit(acc_full)
-
-    def worker(w):
-        for i in range(nq):
-            if transposed:
-                yield ("sleep", sim.rng.uniform(10, 80))  # publish the column statistics, named barrier
-            yield ("wait", s_full, i)
-            check(Sreg["tile"] == i, f"worker {w} loads scores of tile {Sreg['tile']} expecting {i}")
-            yield ("sleep", sim.rng.uniform(300, 1500))
-            Sreg["loaded"].add(w)
-            if not transposed:
-                if i > 0:
-                    yield ("wait", p_free, i - 1)
-                check(Pbuf["consumed"] >= i - 1, f"P smem overwritten before dV({i - 1}) finished")
-            if Pbuf["tile"] != i:
-                Pbuf["tile"], Pbuf["written"] = i, set()
-            Pbuf["written"].add(w)
-            p_ready.arrive(32)
-            yield ("wait", dp_full, i)
-            if i > 0 and bug != "no_dq_full_wait":
-                yield ("wait", dq_full, i - 1)
-            check(DPreg["tile"] == i, f"worker {w} loads dP of tile {DPreg['tile']} expecting {i}")
-            yield ("sleep", sim.rng.uniform(150, 800))
-            DPreg["loaded"].add(w)
-            check(DSbuf["dq_done"] >= i - 1, f"dS smem overwritten before dQ({i - 1}) finished")
-            if not transposed:
-                check(DSbuf["dk_done"] >= i - 1, f"dS smem overwritten before dK({i - 1}) finished")
-            if DSbuf["tile"] != i:
-                DSbuf["tile"], DSbuf["written"] = i, set()
-            DSbuf["written"].add(w)
-            ds_ready.arrive(32)
-        yield ("wait", acc_full, 0)
-
-    def drain(w):
-        for i in range(nq):
-            yield ("wait", dq_full, i)
-            check(DQ["tile"] == i, f"drain loads dQ partial {DQ['tile']} expecting {i}")
-            yield ("sleep", sim.rng.uniform(30, 150))
-            DQ["drained"] = max(DQ["drained"], i) if w == 3 else DQ["drained"]  # last drain warp marks the tile (approximation)
-            dq_free.arrive(32)
-            yield ("sleep", sim.rng.uniform(100, 600))    # staging + TMA reduce-add
-
-    sim.spawn("tma", tma()); sim.spawn("mma", mma())
-    for w in range(8):
-        sim.spawn(f"worker{w}", worker(w))
-    for w in range(4):
-        sim.spawn(f"drain{w}", drain(w))
-    sim.run()
-
-
-# ================================================================================================ backward, split X / Y roles (bwd5)
-def run_bwd5(nq, seed, bug=None):
-    """attn_bwd5_kernel: nq query tiles; 8 X warps (scores -> P^T), 8 Y warps (P^T, dP^T -> dS^T), 4 dQ drain warps, 3-stage
-    Q/dO ring, P^T in its own tensor-memory columns, column statistics triple-buffered per role."""
-    sim = Sim(seed)
-    B = lambda n, c: sim.barrier(n, c)
-    kv_full, s_full, s_free, dp_full = B("kv_full", 1), B("s_full", 1), B("s_free", 256), B("dp_full", 1)
-    p_ready, p_free, ds_ready = B("p_ready", 256), B("p_free", 257), B("ds_ready", 256)
-    dq_full, dq_free, acc_full = B("dq_full", 1), B("dq_free", 128), B("acc_full", 1)
-    NS = 3
-    q_full, q_empty = [B(f"q_full{k}", 1) for k in range(NS)], [B(f"q_empty{k}", 1) for k in range(NS)]
-    Sreg = dict(tile=-1, loaded=set())                      # S^T columns: which tile, which X warps hold it in registers
-    Pbuf = dict(tile=-1, written=set(), y_loaded=set(), dv_done=-1)
-    DPreg = dict(tile=-1, loaded=set())                     # dP^T columns (dS^T is packed over them by the Y warps)
-    DS = dict(tile=-1, written=set(), dk_done=-1, dq_done=-1)
-    DQ = dict(tile=-1, drained=-1)
     Qst = [dict(tile=-1, busy=0) for _ in range(NS)]
-    stat = {role: [dict(tile=-1, written=set()) for _ in range(3)] for role in "xy"}
-    reading = {role: {} for role in "xy"}                   # warp -> tile whose statistics buffer it is reading
+    # auxiliary operand tile: which tile's statistics each k-step holds, who has written them, whether an MMA is reading them
+    aux = {k: dict(tile=-1, written=set(), reading=False) for k in ("lse", "delta")}
+    PUB = {"lse": range(4, 8), "delta": range(8, 12)}      # warps of query quarter 1 / 2 rewrite the lse / delta terms
 
-    def publish(role, w, tile):
-        b = stat[role][tile % 3]
-        for ow, ot in reading[role].items():
-            check(ot % 3 != tile % 3 or ot == tile, f"{role}{w} overwrites the statistics buffer {role}{ow} reads for tile {ot}")
-        if b["tile"] != tile:
-            b["tile"], b["written"] = tile, set()
-        b["written"].add(w)
+    def aux_write(kind, w, tile):
+        a = aux[kind]
+        check(not a["reading"], f"worker {w} rewrites the {kind} terms while an MMA reads them")
+        if a["tile"] != tile:
+            a["tile"], a["written"] = tile, set()
+        a["written"].add(w)
 
     def tma():
         sim.tma(kv_full)
@@ -423,58 +273,62 @@ def run_bwd5(nq, seed, bug=None):
         st = i % NS
         def start():
             check(Qst[st]["tile"] == i, f"S^T({i}) reads stage holding {Qst[st]['tile']}")
-            check(i == 0 or (Sreg["tile"] == i - 1 and len(Sreg["loaded"]) == 8), f"S^T({i}) overwrites scores not yet in registers")
+            check(i == 0 or (Sreg["tile"] == i - 1 and len(Sreg["loaded"]) == NW), f"S^T({i}) overwrites unread scores")
+            check(i == 0 or Pbuf["consumed"] >= i - 1, f"S^T({i}) overwrites P^T({i - 1}) before dV read it")
+            check(aux["lse"]["tile"] == i and len(aux["lse"]["written"]) == 4, f"S^T({i}) reads lse terms of tile {aux['lse']['tile']}")
+            aux["lse"]["reading"] = True
             Qst[st]["busy"] += 1
         def end():
-            Sreg["tile"], Sreg["loaded"] = i, set(); Qst[st]["busy"] -= 1
-        sim.mma(256, start, end)
+            Sreg["tile"], Sreg["loaded"] = i, set(); Qst[st]["busy"] -= 1; aux["lse"]["reading"] = False
+        sim.mma(320, start, end)
         sim.commit(s_full)
 
     def dp_mma(i):
         st = i % NS
         def start():
             check(Qst[st]["tile"] == i, f"dP^T({i}) reads stage holding {Qst[st]['tile']}")
-            check(i == 0 or (DPreg["tile"] == i - 1 and len(DPreg["loaded"]) == 8), f"dP^T({i}) overwrites unread dP^T")
-            check(i == 0 or DS["dk_done"] >= i - 1, f"dP^T({i}) overwrites dS^T({i - 1}) before dK read it")
+            check(i == 0 or (DPreg["tile"] == i - 1 and len(DPreg["loaded"]) == NW), f"dP^T({i}) overwrites unread dP^T")
+            check(i == 0 or DSbuf["dk_done"] >= i - 1, f"dP^T({i}) overwrites dS^T({i - 1}) before dK read it")
+            check(aux["delta"]["tile"] == i and len(aux["delta"]["written"]) == 4, f"dP^T({i}) reads delta terms of tile {aux['delta']['tile']}")
+            aux["delta"]["reading"] = True
             Qst[st]["busy"] += 1
         def end():
-            DPreg["tile"], DPreg["loaded"] = i, set(); Qst[st]["busy"] -= 1
-        sim.mma(256, start, end)
+            DPreg["tile"], DPreg["loaded"] = i, set(); Qst[st]["busy"] -= 1; aux["delta"]["reading"] = False
+        sim.mma(320, start, end)
         sim.commit(dp_full)
 
     def mma():
         yield ("wait", kv_full, 0)
         yield ("wait", q_full[0], 0)
+        yield ("wait", aux_init, 0)
         s_mma(0)
         dp_mma(0)
         for i in range(nq):
             st, more = i % NS, i + 1 < nq
             if more:
                 yield ("wait", q_full[(i + 1) % NS], (i + 1) // NS)
-                if bug != "no_s_free_wait":
-                    yield ("wait", s_free, i)
-                s_mma(i + 1)
             yield ("wait", p_ready, i)
             def dv_start(i=i, st=st):
-                check(Pbuf["tile"] == i and len(Pbuf["written"]) == 8, f"dV({i}) reads P^T holding {Pbuf['tile']}")
+                check(Pbuf["tile"] == i and len(Pbuf["written"]) == NW, f"dV({i}) reads P^T holding {Pbuf['tile']}")
                 Qst[st]["busy"] += 1
             def dv_end(i=i, st=st):
-                Pbuf["dv_done"] = i; Qst[st]["busy"] -= 1
+                Pbuf["consumed"] = i; Qst[st]["busy"] -= 1
             sim.mma(256, dv_start, dv_end)
-            sim.commit(p_free)
+            if more:
+                s_mma(i + 1)
             yield ("wait", ds_ready, i)
             if i > 0:
                 yield ("wait", dq_free, i - 1)
             def dk_start(i=i, st=st):
-                check(DS["tile"] == i and len(DS["written"]) == 8, f"dK({i}) reads dS^T holding {DS['tile']}")
+                check(DSbuf["tile"] == i and len(DSbuf["written"]) == NW, f"dK({i}) reads dS^T holding {DSbuf['tile']}")
                 Qst[st]["busy"] += 1
             def dk_end(i=i, st=st):
-                DS["dk_done"] = i; Qst[st]["busy"] -= 1
+                DSbuf["dk_done"] = i; Qst[st]["busy"] -= 1
             def dq_start(i=i):
-                check(DS["tile"] == i, f"dQ({i}) reads dS holding {DS['tile']}")
+                check(DSbuf["tile"] == i, f"dQ({i}) reads dS holding {DSbuf['tile']}")
                 check(DQ["drained"] >= i - 1, f"dQ({i}) overwrites the undrained partial {DQ['tile']}")
             def dq_end(i=i):
-                DS["dq_done"] = i; DQ["tile"] = i
+                DSbuf["dq_done"] = i; DQ["tile"] = i
             sim.mma(256, dk_start, dk_end)
             if more:
                 dp_mma(i + 1)
@@ -483,59 +337,37 @@ def run_bwd5(nq, seed, bug=None):
             sim.commit(q_empty[st])
         sim.commit(acc_full)
 
-    def xwarp(w):
-        if w < 4:
-            publish("x", w, 0)
-        yield ("sleep", sim.rng.uniform(5, 60))          # named barrier of the role (modelled as a delay: all publish before any reads)
+    def worker(w):
+        for kind in ("lse", "delta"):
+            if w in PUB[kind]:
+                aux_write(kind, w, 0)
+        yield ("sleep", sim.rng.uniform(5, 80))
+        aux_init.arrive(32)
         for i in range(nq):
+            if bug == "early_lse_write" and w in PUB["lse"] and i + 1 < nq:
+                aux_write("lse", w, i + 1)
             yield ("wait", s_full, i)
-            if w < 4 and i + 1 < nq:
-                publish("x", w, i + 1)
-            reading["x"][w] = i
-            check(Sreg["tile"] == i, f"x{w} loads scores of tile {Sreg['tile']} expecting {i}")
-            yield ("sleep", sim.rng.uniform(80, 300))
+            if bug != "early_lse_write" and w in PUB["lse"] and i + 1 < nq:
+                aux_write("lse", w, i + 1)      # S^T(i) has completed; S^T(i+1) waits for this warp's p_ready(i) arrival
+            check(Sreg["tile"] == i, f"worker {w} loads scores of tile {Sreg['tile']} expecting {i}")
+            yield ("sleep", sim.rng.uniform(200, 1200))
             Sreg["loaded"].add(w)
-            s_free.arrive(32)
-            yield ("sleep", sim.rng.uniform(400, 1800))  # exponentials
-            b = stat["x"][i % 3]
-            check(b["tile"] == i and len(b["written"]) == 4, f"x{w} read statistics of tile {b['tile']} expecting {i}")
-            reading["x"].pop(w)
-            if i > 0 and bug != "no_p_free_wait":
-                yield ("wait", p_free, i - 1)
-            check(i == 0 or (Pbuf["dv_done"] >= i - 1 and (Pbuf["tile"] == i or len(Pbuf["y_loaded"]) == 8)),
-                  f"x{w} overwrites P^T({i - 1}) still in use")
             if Pbuf["tile"] != i:
-                Pbuf["tile"], Pbuf["written"], Pbuf["y_loaded"] = i, set(), set()
+                Pbuf["tile"], Pbuf["written"] = i, set()
             Pbuf["written"].add(w)
             p_ready.arrive(32)
-        yield ("wait", acc_full, 0)
-
-    def ywarp(w):
-        if w < 4:
-            publish("y", w, 0)
-        yield ("sleep", sim.rng.uniform(5, 60))
-        for i in range(nq):
             yield ("wait", dp_full, i)
-            if w < 4 and i + 1 < nq:
-                publish("y", w, i + 1)
-            yield ("wait", p_ready, i)
-            reading["y"][w] = i
-            check(Pbuf["tile"] == i and len(Pbuf["written"]) == 8, f"y{w} loads P^T of tile {Pbuf['tile']} expecting {i}")
-            yield ("sleep", sim.rng.uniform(60, 250))
-            Pbuf["y_loaded"].add(w)
-            p_free.arrive(32)
+            if w in PUB["delta"] and i + 1 < nq:
+                aux_write("delta", w, i + 1)    # dP^T(i) has completed; dP^T(i+1) waits for this warp's ds_ready(i) arrival
             if i > 0 and bug != "no_dq_full_wait":
                 yield ("wait", dq_full, i - 1)
-            check(DPreg["tile"] == i, f"y{w} loads dP^T of tile {DPreg['tile']} expecting {i}")
-            yield ("sleep", sim.rng.uniform(300, 1400))
+            check(DPreg["tile"] == i, f"worker {w} loads dP^T of tile {DPreg['tile']} expecting {i}")
+            yield ("sleep", sim.rng.uniform(100, 900))
             DPreg["loaded"].add(w)
-            b = stat["y"][i % 3]
-            check(b["tile"] == i and len(b["written"]) == 4, f"y{w} read statistics of tile {b['tile']} expecting {i}")
-            reading["y"].pop(w)
-            check(DS["dq_done"] >= i - 1, f"dS smem overwritten before dQ({i - 1}) finished")
-            if DS["tile"] != i:
-                DS["tile"], DS["written"] = i, set()
-            DS["written"].add(w)
+            check(DSbuf["dq_done"] >= i - 1, f"dS smem overwritten before dQ({i - 1}) finished")
+            if DSbuf["tile"] != i:
+                DSbuf["tile"], DSbuf["written"] = i, set()
+            DSbuf["written"].add(w)
             ds_ready.arrive(32)
         yield ("wait", acc_full, 0)
 
@@ -546,11 +378,11 @@ def run_bwd5(nq, seed, bug=None):
             yield ("sleep", sim.rng.uniform(30, 150))
             DQ["drained"] = max(DQ["drained"], i) if w == 3 else DQ["drained"]  # last drain warp marks the tile (approximation)
             dq_free.arrive(32)
-            yield ("sleep", sim.rng.uniform(100, 2500))   # staging + TMA reduce-add
+            yield ("sleep", sim.rng.uniform(100, 2000))   # staging + TMA reduce-add
 
     sim.spawn("tma", tma()); sim.spawn("mma", mma())
-    for w in range(8):
-        sim.spawn(f"x{w}", xwarp(w)); sim.spawn(f"y{w}", ywarp(w))
+    for w in range(NW):
+        sim.spawn(f"worker{w}", worker(w))
     for w in range(4):
         sim.spawn(f"drain{w}", drain(w))
     sim.run()
@@ -558,8 +390,7 @@ def run_bwd5(nq, seed, bug=None):
 
 KERNELS = {
     "attn_fwd4_kernel": lambda n, seed, bug=None: run_fwd4(n, seed, bug),
-    "attn_bwd3_kernel": lambda n, seed, bug=None: run_bwd(n, seed, True, bug),
-    "attn_bwd5_kernel": lambda n, seed, bug=None: run_bwd5(n, seed, bug),
+    "attn_bwd4_kernel": lambda n, seed, bug=None: run_bwd4(n, seed, bug),
 }
 
 

@@ -4,7 +4,9 @@
     python tools/trace_attn_bwd.py             # on the B200: run once with the trace on, print the per-phase medians
 
 The trace library is a separate build of csrc/cx_attn.cu; the product library contains none of the trace code.
-CX_ATTN_BWD3=1 traces the previous generation.  Roles: 0 / 1 = first worker warp of query quarters 0 / 2 (bwd3: of query halves 0 / 1), 2 = MMA warp, 3 = first dQ-drain warp, 4 = block-level stamps.
+Roles: 0 / 1 = first worker warp of query quarters 0 / 2, 2 = MMA warp (its stamp 6 sits between "top" and "p_ready": Q/dO stage
+landed), 3 = first dQ-drain warp, 4 = block-level stamps.  VARIANTS takes ablation builds (extra -D flags): round 2 used them to
+remove one consumer of the shared-memory port at a time (profiles/r02l_attn_bwd4_ablations.txt).
 """
 import ctypes as C
 import json
@@ -95,15 +97,10 @@ def main():
     res["acc_full_at"] = med(t[:, 4, 0, 2] - t0)
     res["worker_epilogue"] = med(t[:, 4, 0, 3] - t[:, 4, 0, 2])
     res["drain_done_at"] = med(t[:, 4, 0, 5] - t0)
-    bwd3 = os.environ.get("CX_ATTN_BWD3") == "1"
-    if bwd3:   # role 0 / 1: first worker warp of each query half (X then Y in the same warp)
-        names = {0: ["top", "stat_bar", "s_full", "x_loaded", "x_done", "dp_dq_full", "y_done", "ds_arrived"],
-                 2: ["top", "p_ready", "issue1", "ds_ready", "dq_free", "issue2"]}
-        names[1] = names[0]
-    else:      # attn_bwd4_kernel: role 0 / 1 = first worker warp of query quarters 0 / 2
-        names = {0: ["top", "s_full", "x_loaded", "x_done", "dp_dq_full", "y_loaded", "y_done", "ds_arrived"],
-                 2: ["top", "p_ready", "issue1", "ds_ready", "dq_free", "issue2"]}
-        names[1] = names[0]
+    # role 0 / 1 = first worker warp of query quarters 0 / 2 (X then Y in the same warp)
+    names = {0: ["top", "s_full", "x_loaded", "x_done", "dp_dq_full", "y_loaded", "y_done", "ds_arrived"],
+             2: ["top", "p_ready", "issue1", "ds_ready", "dq_free", "issue2"]}
+    names[1] = names[0]
     names[3] = ["top", "dq_full", "loaded", "stage_free_bar", "stored"]
     for role, label in ((0, "worker0"), (1, "worker1"), (2, "mma"), (3, "drain")):
         nm = names[role]
