@@ -163,9 +163,10 @@ def _attn_ref(qkv, lens, H, Dh, scale):
 
 
 @pytest.mark.parametrize("lens,H", [([128], 1), ([512, 512], 2), ([300, 17, 512, 129, 1], 3), ([197] * 4, 12), ([640, 1000], 2),
-                                    ([64], 1), ([65, 191, 192, 193], 2)])
+                                    ([64], 1), ([65, 191, 192, 193], 2), ([2048, 77, 1500], 1)])
 def test_attention_fwd_bwd(lens, H):
-    """Two-threads-per-row forward + transposed-score backward vs fp32 torch (ragged, ViT-like and > 512 lengths)."""
+    """Two-threads-per-row forward + transposed-score backward vs fp32 torch (ragged, ViT-like, > 512 and 2048-token lengths:
+    the last case walks the backward's three-stage query ring and every barrier phase through 16 query tiles)."""
     from contrastors_b200 import ops
     torch.manual_seed(5)
     Dh = 64
