@@ -444,12 +444,14 @@ def accumulate_gradients(model, inputs, cache, rand_states, router_aux_coeff, _g
                 with state:
                     with _autocast_for(inp):
                         embedding = model(**inp)
-                surrogate = torch.dot(embedding["embedding"].flatten().float(), grad.flatten().float())
-                if "router_loss" in embedding and embedding["router_loss"] is not None:
-                    surrogate = surrogate + embedding["router_loss"] * router_aux_coeff
                 if _grad_reducer is not None and i == length - 1:
                     _grad_reducer.arm()
-                surrogate.backward()
+                emb = embedding["embedding"]
+                if "router_loss" in embedding and embedding["router_loss"] is not None:
+                    surrogate = torch.dot(emb.flatten().float(), grad.flatten().float())
+                    (surrogate + embedding["router_loss"] * router_aux_coeff).backward()
+                else:  # d<embedding, grad>/d embedding = grad: seed the backward with it instead of forming the dot product
+                    torch.autograd.backward(emb, grad.to(emb.dtype))
     if streams:
         for s in streams:
             main.wait_stream(s)
