@@ -21,7 +21,7 @@ OUT = os.path.join(ROOT, "tools", "_trace")
 LIB = os.path.join(OUT, "libcx_trace.so")
 
 
-VARIANTS = {"": []}   # name -> extra -D flags (ablation builds go here)
+VARIANTS = {"": []}   # name -> extra -D flags: A/B builds of schedule variants or ablations go here (CX_TRACE_VARIANT=name selects one)
 
 
 def build():
@@ -56,6 +56,14 @@ def main():
     scale = 1.0 / math.sqrt(Dh)
     out, lse = ops.attn_fwd(qkv, cu, S, H, Dh, scale)
     ref = ops.attn_bwd(qkv, out, dout, lse, cu, S, H, Dh, scale)
+    from contrastors_b200 import _lib
+    plib = _lib.load()
+    ref_acc = torch.empty(T, H * Dh, device="cuda", dtype=torch.float32)
+    ref_dqkv = torch.empty_like(qkv)
+    ref_delta = torch.empty(H, T, device="cuda", dtype=torch.float32)
+    _lib.check(plib.cx_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), cu.data_ptr(), ref_dqkv.data_ptr(),
+                                ref_acc.data_ptr(), ref_delta.data_ptr(), T, nseq, S, H, Dh, scale, 0,
+                                torch.cuda.current_stream().cuda_stream), "cx_attn_bwd")
     nblk = (S // 128) * H * nseq
     trace = torch.zeros(nblk * 5 * 8 * 8, dtype=torch.int64, device="cuda")
     dqkv = torch.empty_like(qkv)
@@ -84,7 +92,9 @@ def main():
     # the drained dk/dv slots match the product library's (dq is finalized by a separate kernel, not compared here)
     HD = H * Dh
     err = (dqkv[:, HD:].float() - ref[:, HD:].float()).abs().max().item() / ref[:, HD:].float().abs().max().item()
-    assert variant or err < 2e-2, f"trace build disagrees with the product build: {err}"
+    err_q = (dq_acc - ref_acc).abs().max().item() / ref_acc.abs().max().item()
+    print("variant", variant or "plain", "max rel err vs product: dk/dv", err, "dq_acc", err_q)
+    assert err < 2e-2 and err_q < 2e-2, f"trace build disagrees with the product build: {err} {err_q}"
     t = trace.cpu().numpy().reshape(nblk, 5, 8, 8)
     nq = S // 128
     res = {}
