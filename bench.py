@@ -16,7 +16,8 @@ kernel (tcgen05 GEMM) timed live with CUDA events on the launching stream (1 lau
 a layer), against MEASURED_PEAKS.json; comm_ms = device time of every collective of a step; selfcheck = the loss of the
 first 64 pairs at step 0 against the CPU oracle; gpu_baseline = the UNMODIFIED reference (its pure-PyTorch NomicBertModel
 + its grad_cache_loss, from baseline/_ref) on the same B200 under bf16 autocast over a bounded sample; cpu_baseline = the
-same reference code on this box's host cores (median of 3 after a warm-up).
+same reference code on this box's host cores (median of 3 after a warm-up).  The three checker legs (selfcheck, gpu_baseline,
+cpu_baseline) run on rank 0 at N = 1 only; at N > 1 their keys are null.
 """
 from __future__ import annotations
 
@@ -362,7 +363,7 @@ def run_ours(args):
         return ms.item()
 
     selfcheck = None
-    if rank == 0 and not args.no_selfcheck:
+    if rank == 0 and world == 1 and not args.no_selfcheck:  # the checker legs (oracle self-check, both baselines) run at N = 1 only
         selfcheck = oracle_selfcheck(model, logit_scale, resident["query_input_ids"][:SELFCHECK_PAIRS],
                                      resident["document_input_ids"][:SELFCHECK_PAIRS])
     for _ in range(args.warmup):
@@ -438,7 +439,7 @@ def run_ours(args):
     torch.cuda.empty_cache()
     dist.destroy_process_group()
     gpu_base = None
-    if not args.no_gpu_baseline:
+    if world == 1 and not args.no_gpu_baseline:
         created = _ensure_group("gloo")  # the reference's clip_loss asks for a process group; 1 rank: its gather is the identity
         try:
             gpu_base = gpu_baseline(dev)
@@ -448,7 +449,11 @@ def run_ours(args):
             dist.destroy_process_group()
     # CPU baseline: the reference's own step on the host cores, bounded sample, median of 3 after a warm-up
     threads = cpu_threads()
-    cpu_value, cpu_times, cpu_kind, cpu_sample, _ = cpu_baseline(threads)
+    cpu_base = None
+    if world == 1:
+        cpu_value, cpu_times, cpu_kind, cpu_sample, _ = cpu_baseline(threads)
+        cpu_base = {"value": cpu_value, "unit": "pairs/s", "cores": threads, "kind": cpu_kind, "sample": cpu_sample,
+                    "step_seconds": cpu_times, "stat": "median of 3 after 1 warm-up"}
     comm_ms = {k: {"calls_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps} for k, v in comm.items()}
     comm_total = sum(v["ms_per_step"] for v in comm_ms.values())
     out = {
@@ -467,8 +472,7 @@ def run_ours(args):
                             "the gradient buckets run on side streams under compute, so this is occupancy, not exposed time)"},
         "selfcheck": selfcheck,
         "gpu_baseline": gpu_base,
-        "cpu_baseline": {"value": cpu_value, "unit": "pairs/s", "cores": threads, "kind": cpu_kind, "sample": cpu_sample,
-                         "step_seconds": cpu_times, "stat": "median of 3 after 1 warm-up"},
+        "cpu_baseline": cpu_base,
         "loss": losses[-1] if losses else None,
     }
     print(json.dumps(out))
