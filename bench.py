@@ -309,7 +309,7 @@ def run_ours(args):
     import torch.distributed as dist
     import contrastors_b200 as cb
     from contrastors_b200 import _lib, ops
-    from contrastors_b200.parallel import allreduce_gradients, broadcast_parameters
+    from contrastors_b200.parallel import broadcast_parameters
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

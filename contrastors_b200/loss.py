@@ -22,7 +22,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops
-from .distributed import _rank, _timed, all_gather_rows, gather_with_grad, reduce_scatter_rows  # noqa: F401
+from .distributed import _timed, all_gather_rows, gather_with_grad, reduce_scatter_rows
 from .rand_state import RandContext
 
 

@@ -26,9 +26,9 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .ops import MAJOR_K, MAJOR_MN  # noqa: F401
+from .ops import MAJOR_MN
 
-from .flat_params import FlatParamModule, _OPT_STEPS, _attach  # noqa: F401  (re-exported for vit.py / older imports)
+from .flat_params import FlatParamModule
 
 
 @dataclass
