@@ -11,6 +11,7 @@ What is executed from the reference, untouched:
   trainers/text_text.py:352-369    (Matryoshka loop, exec'd from the file text)
   modeling_biencoder.py:79-90      (MeanPooling, exec'd from the file text)
   models/huggingface/modeling_hf_nomic_bert.py  NomicBertModel (pure torch)
+  modeling_biencoder.py  MultiHeadAttentionPooling, ClsSelector (imported; flash_attn_kvpacked_func given its published definition)
 """
 from __future__ import annotations
 
@@ -329,8 +330,64 @@ def gen_gradcache_soft():
         print("gradcache_soft", ws, {k: v.item() for k, v in out.items() if "loss" in k})
 
 
+POOLER_CASES = {  # name -> (batch, tokens, width, heads, inner, activation)
+    "map_gelu": (3, 10, 64, 4, 96, "gelu"),
+    "map_swiglu": (2, 7, 64, 2, 128, "swiglu"),
+}
+
+
+def gen_poolers():
+    """round 2: the reference's OWN MultiHeadAttentionPooling / ClsSelector / projection tail on CPU (modeling_biencoder.py:44-49,
+    93-152, 264-267, 300-317; layers/attention.py:312-440).  One third-party kernel is substituted by its published definition:
+    flash_attn_kvpacked_func(q [B,Sq,H,D], kv [B,Sk,2,H,D], softmax_scale) = softmax(q k^T * scale) v per head (flash-attn
+    2.x README / flash_attn_interface.py docstring) -- everything else (latent, Wq, Wkv, out_proj, norm1, MLP, residual, the
+    [:, 0] selection) is the reference's code executing."""
+    mb, att = ref_loader.load_biencoder_tail()
+
+    def kvpacked(q, kv, dropout_p=0.0, softmax_scale=None, causal=False, **_):
+        assert dropout_p == 0.0 and not causal
+        k, v = kv[:, :, 0], kv[:, :, 1]
+        scale = softmax_scale if softmax_scale is not None else q.shape[-1] ** -0.5
+        s = torch.einsum("bqhd,bkhd->bhqk", q.float(), k.float()) * scale
+        return torch.einsum("bhqk,bkhd->bqhd", torch.softmax(s, dim=-1), v.float()).to(q.dtype)
+    att.flash_attn_kvpacked_func = kvpacked
+    import importlib
+    importlib.import_module("contrastors.layers.mlp").swiglu = None  # "fused op unavailable": GatedMLP's own y * silu(gate) branch (mlp.py:80-81)
+    for name, (B, S, d, H, inner, act) in POOLER_CASES.items():
+        cfg = types.SimpleNamespace(n_embd=d, n_head=H, n_inner=inner, activation_function=act, use_flash_attn=True,
+                                    fused_bias_fc=False, qkv_proj_bias=True, mlp_fc1_bias=True, mlp_fc2_bias=True, causal=False,
+                                    attn_pdrop=0.0, use_rms_norm=False, layer_norm_epsilon=1e-5, num_heads_kv=None)
+        torch.manual_seed(11)
+        pool = mb.MultiHeadAttentionPooling(cfg).float().eval()
+        with torch.no_grad():
+            for p in pool.parameters():
+                p.copy_(torch.randn_like(p) * (0.5 if p.dim() == 1 else p.shape[-1] ** -0.5))
+        rs = np.random.RandomState(5)
+        hidden = torch.tensor(rs.randn(B, S, d).astype(np.float32), requires_grad=True)
+        cot = torch.tensor(rs.randn(B, d).astype(np.float32))
+        out = pool(hidden, None, None)
+        out.backward(cot)
+        res = {"hidden": hidden.detach().numpy(), "cot": cot.numpy(), "out": out.detach().numpy(), "d_hidden": hidden.grad.numpy(),
+               "cls": mb.ClsSelector()(hidden.detach(), None, None).numpy(), "n_head": np.int64(H), "activation": np.array(act)}
+        for k, v in pool.state_dict().items():
+            res["sd." + k] = v.numpy()
+        for k, p in pool.named_parameters():
+            res["g." + k] = p.grad.numpy()
+        # the tail of BiEncoder.forward (modeling_biencoder.py:307-317) on the pooled rows: cast to the trunk dtype, proj, normalize
+        proj = torch.nn.Linear(d, 48)
+        emb = out.detach()
+        if emb.dtype != torch.bfloat16:
+            emb = emb.to(torch.bfloat16)   # `embedding.to(trunk_output.dtype)` with a bf16 trunk
+        tail = F.normalize(proj(emb.float()), dim=-1)
+        res.update(proj_w=proj.weight.detach().numpy(), proj_b=proj.bias.detach().numpy(), tail=tail.detach().numpy())
+        np.savez_compressed(os.path.join(GOLDEN, f"pooler_{name}.npz"), **res)
+        print("pooler", name, out[0, :3].tolist())
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "gradcache_soft":
         gen_gradcache_soft()
+    elif len(sys.argv) > 1 and sys.argv[1] == "poolers":
+        gen_poolers()
     else:
         main()

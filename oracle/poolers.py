@@ -6,6 +6,8 @@
   * ``ClsSelector``                        modeling_biencoder.py:44-49
   * ``proj`` + cast + normalize            modeling_biencoder.py:270-273, 307-317
 The flash kernels are replaced by the explicit softmax they compute; parameter names are the reference's.
+Pinned: tests/golden/pooler_map_{gelu,swiglu}.npz are outputs and gradients of the reference's own MultiHeadAttentionPooling /
+ClsSelector run on CPU (oracle/gen_golden.py::gen_poolers); tests/test_oracle_golden.py holds this file to them.
 """
 from __future__ import annotations
 

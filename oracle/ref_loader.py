@@ -56,3 +56,54 @@ def load():
     ns.hf_cfg = importlib.import_module("contrastors.models.huggingface.configuration_hf_nomic_bert")
     ns.hf = importlib.import_module("contrastors.models.huggingface.modeling_hf_nomic_bert")
     return ns
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# The BiEncoder tail (poolers, projection) lives in models/biencoder/modeling_biencoder.py, whose import chain pulls in optional
+# third-party extensions this image does not have (flash-attn's fused dropout_layer_norm / fused_dense_lib, megablocks, ...).  None
+# of them is CALLED by the pooler path; they are satisfied with empty stand-in modules so that the reference's own classes
+# (MultiHeadAttentionPooling, FlashAttentionPooling, ClsSelector, MLP / GatedMLP) import untouched.
+_OPTIONAL_THIRD_PARTY = ("dropout_layer_norm", "fused_dense_lib", "rotary_emb", "xentropy_cuda_lib", "megablocks", "stk",
+                         "grouped_gemm", "deepspeed", "wandb", "webdataset", "open_clip", "timm")
+
+
+def load_biencoder_tail():
+    """Returns (modeling_biencoder module, layers.attention module) of the unmodified reference."""
+    import importlib.abc
+    import importlib.machinery
+    load()
+
+    class _Stub(types.ModuleType):
+        __path__: list = []
+
+        def __getattr__(self, name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+            return type(name, (), {})
+
+    class _OptionalStubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+        def find_spec(self, fullname, path, target=None):
+            if fullname.split(".")[0] in _OPTIONAL_THIRD_PARTY:
+                try:  # a real installation wins
+                    for f in sys.meta_path:
+                        if f is not self and hasattr(f, "find_spec") and f.find_spec(fullname, path, target) is not None:
+                            return None
+                except Exception:
+                    pass
+                return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
+            return None
+
+        def create_module(self, spec):
+            return _Stub(spec.name)
+
+        def exec_module(self, module):
+            pass
+
+    if not any(type(f).__name__ == "_OptionalStubFinder" for f in sys.meta_path):
+        sys.meta_path.append(_OptionalStubFinder())
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", SyntaxWarning)
+        mb = importlib.import_module("contrastors.models.biencoder.modeling_biencoder")
+        att = importlib.import_module("contrastors.layers.attention")
+    return mb, att

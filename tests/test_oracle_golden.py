@@ -157,3 +157,25 @@ def test_vit_oracle_vs_hf_clip_golden(name):
     close(sd["embeddings.proj.weight"].grad.numpy() @ np.linspace(-1.0, 1.0, K, dtype=np.float32), z["g_patch_proj"], rtol=2e-3, atol=1e-6)
     close(sd["prepre_layernom.weight"].grad.numpy(), z["g_prepre_w"], rtol=2e-3, atol=1e-7)
     close(sd["ln_f.bias"].grad.numpy(), z["g_lnf_b"], rtol=2e-3, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["map_gelu", "map_swiglu"])
+def test_pooler_oracle_vs_reference_golden(name):
+    """oracle/poolers.py against the reference's OWN MultiHeadAttentionPooling / ClsSelector / projection tail (modeling_biencoder.py,
+    run on CPU by oracle/gen_golden.py with flash_attn_kvpacked_func given its published definition): output, input gradient and
+    every parameter gradient."""
+    from oracle.poolers import map_pool, project_normalize
+    z = golden(f"pooler_{name}.npz")
+    sd = {k[3:]: torch.tensor(z[k]).requires_grad_() for k in z.files if k.startswith("sd.")}
+    hidden = torch.tensor(z["hidden"]).requires_grad_()
+    out = map_pool(sd, hidden, int(z["n_head"]), activation=str(z["activation"]))
+    close(out.detach().numpy(), z["out"], rtol=1e-5, atol=1e-6)
+    out.backward(torch.tensor(z["cot"]))
+    close(hidden.grad.numpy(), z["d_hidden"], rtol=1e-4, atol=1e-7)
+    grads = [k for k in z.files if k.startswith("g.")]
+    assert len(grads) == len(sd)  # every parameter of the reference module is a parameter of the restatement
+    for k in grads:
+        close(sd[k[2:]].grad.numpy(), z[k], rtol=1e-4, atol=1e-7)
+    assert np.array_equal(hidden.detach().numpy()[:, 0], z["cls"])  # ClsSelector
+    tail = project_normalize(torch.tensor(z["out"]), torch.tensor(z["proj_w"]), torch.tensor(z["proj_b"]))
+    close(tail.numpy(), z["tail"], rtol=1e-5, atol=1e-6)
