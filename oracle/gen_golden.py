@@ -382,6 +382,14 @@ def gen_poolers():
         res.update(proj_w=proj.weight.detach().numpy(), proj_b=proj.bias.detach().numpy(), tail=tail.detach().numpy())
         np.savez_compressed(os.path.join(GOLDEN, f"pooler_{name}.npz"), **res)
         print("pooler", name, out[0, :3].tolist())
+    # the reference's own LogitScale (modeling_biencoder.py:30-41): output, parameter gradient, state-dict key, repr
+    ls = mb.LogitScale(types.SimpleNamespace(logit_scale=1 / 0.07, trainable_logit_scale=True))
+    x = torch.tensor(np.random.RandomState(9).randn(5, 3).astype(np.float32))
+    y = ls(x)
+    y.sum().backward()
+    np.savez_compressed(os.path.join(GOLDEN, "logit_scale.npz"), x=x.numpy(), y=y.detach().numpy(), dp=ls.logit_scale.grad.numpy(),
+                        keys=np.array(list(ls.state_dict().keys())), p=ls.logit_scale.detach().numpy(), repr=np.array(repr(ls)))
+    print("logit_scale", repr(ls))
 
 
 if __name__ == "__main__":

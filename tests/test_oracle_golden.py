@@ -179,3 +179,19 @@ def test_pooler_oracle_vs_reference_golden(name):
     assert np.array_equal(hidden.detach().numpy()[:, 0], z["cls"])  # ClsSelector
     tail = project_normalize(torch.tensor(z["out"]), torch.tensor(z["proj_w"]), torch.tensor(z["proj_b"]))
     close(tail.numpy(), z["tail"], rtol=1e-5, atol=1e-6)
+
+
+def test_logit_scale_vs_reference_golden():
+    """contrastors_b200.LogitScale against the reference's own class (golden from oracle/gen_golden.py::gen_poolers): arithmetic,
+    parameter gradient, state-dict key, repr."""
+    import types
+
+    import contrastors_b200 as cb
+    z = golden("logit_scale.npz")
+    ls = cb.LogitScale(types.SimpleNamespace(logit_scale=1 / 0.07, trainable_logit_scale=True))
+    y = ls(torch.tensor(z["x"]))
+    assert np.array_equal(y.detach().numpy(), z["y"])
+    y.sum().backward()
+    close(ls.logit_scale.grad.numpy(), z["dp"], rtol=1e-6, atol=0)
+    assert list(ls.state_dict().keys()) == list(z["keys"]) and np.array_equal(ls.logit_scale.detach().numpy(), z["p"])
+    assert repr(ls) == str(z["repr"])
